@@ -1,0 +1,61 @@
+"""Pin the CPU oracle (oracle/diral_oracle.c) to the reference: replay every golden fixture
+(outputs of the unmodified reference env) and demand bit-identical float64 results."""
+import numpy as np
+import pytest
+
+from golden_util import fingerprint_args, golden_names, kwargs_from_meta, load_golden
+from oracle.c_oracle import COracle
+
+
+def _same(a, b, what, t):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    ok = (a == b) | (np.isnan(a) & np.isnan(b))
+    assert ok.all(), "%s differs at slot %d: %d entries, max |d|=%g" % (
+        what, t, (~ok).sum(), np.nanmax(np.abs(a - b)))
+    # also the sign of zero (the reference produces -0.0 rewards under my_step_ch design 2)
+    assert (np.signbit(a) == np.signbit(b))[~np.isnan(a)].all(), "%s sign-of-zero differs at slot %d" % (what, t)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_c_oracle_matches_reference(name):
+    g, m = load_golden(name)
+    orc = COracle(num_envs=1, **kwargs_from_meta(m))
+    assert orc.S == m["state_space"]
+    if "trace" in g:
+        orc.load_trace(g["trace"])
+    orc.reset(g["x0"][None], g["y0"][None], g["v0"][None])
+    T = g["actions"].shape[0]
+    for t in range(T):
+        mode = str(g["modes"][t])
+        obs, rews = orc.step(mode, g["actions"][t][None], t)
+        ep, eps = fingerprint_args(m, t)
+        state = orc.obtain_state(obs, g["actions"][t][None], rews, ep, eps)
+        _same(obs[0], g["obs"][t], "obs", t)
+        _same(rews[0], g["rews"][t], "rews", t)
+        _same(orc.pos_x[0], g["pos_x"][t], "pos_x", t)
+        _same(state[0], g["state"][t], "state", t)
+        assert (orc.tab_seq[0] == g["tab_seq"][t]).all(), "seq table, slot %d" % t
+        assert (orc.tab_lu[0] == g["tab_lu"][t]).all(), "last_updated table, slot %d" % t
+        _same(orc.tab_x[0], g["tab_x"][t], "xpos table", t)
+        _same(orc.tab_y[0], g["tab_y"][t], "ypos table", t)
+        assert (orc.lat[0] == g["lat"][t]).all(), "last_arrival_time, slot %d" % t
+        assert (orc.information_age(t)[0] == g["ia"][t]).all(), "information age, slot %d" % t
+        if m["episode_interval"] and t % m["episode_interval"] == m["episode_interval"] - 1:
+            orc.update_velocity(g["draws"][t][None])
+        _same(orc.vel[0], g["vel"][t], "velocity", t)
+
+
+def test_survey_known_answers():
+    """SURVEY.md section 2b KAT-1..4, read back from the fixtures (guards the fixtures themselves)."""
+    g, _ = load_golden("kat1_design6_step_design")
+    assert g["rews"].tolist() == [[1] * 6, [-2, -2, 1, 1, 1, 1], [-3, -3, -3, 1, 1, 1]]
+    vpd0 = g["state"][0][0][5:]
+    assert {i: round(v, 6) for i, v in enumerate(vpd0) if v} == {9: 0.8, 13: 0.2}
+    g, _ = load_golden("kat2_design6_my_step")
+    assert g["rews"].tolist() == [[0, 1, 1, 1, 1, 0], [-2, -2, 1, 1, 1, 1], [0, 1, 0, 1, 1, 1]]
+    assert g["obs"][0][0].tolist() == [0, 195, 1e5, 1e5, 1e5]
+    g, _ = load_golden("kat3_design6_ch_d2")
+    assert g["rews"][2].tolist() == [-0.0, 1, -0.5, 1, 1, 1] and np.signbit(g["rews"][2][0])
+    g, _ = load_golden("kat4_toy_fixed")
+    assert g["rews"][:3].tolist() == [[-2, 1, 1, -2], [0, 1, 1, 0], [-4] * 4]
+    assert g["pos_x"][4].tolist() == [5.5, 10.0, 9.25, 12.5]
