@@ -1,0 +1,60 @@
+"""Builds diral_b200/libdiral_env.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+The shared object is git-ignored but travels to the GPU box with the working-tree snapshot, so the
+box never needs to compile.  `python -m diral_b200._build [--force]` rebuilds by hand.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+LIB = os.path.join(HERE, "libdiral_env.so")
+SOURCES = ["diral_api.cu", "diral_step_group.cu", "diral_step_block.cu", "diral_aux.cu"]
+HEADERS = [os.path.join(CSRC, "diral_dev.cuh"), os.path.join(CSRC, "diral_launch.h"),
+           os.path.join(os.path.dirname(HERE), "include", "diral_env.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-Xptxas", "-v"]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: libdiral_env.so cannot be built here")
+    return exe
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + HEADERS):
+            cmd = [nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            with open(o + ".log", "w") as f:
+                f.write(r.stdout + r.stderr)
+            if verbose or r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode:
+                raise RuntimeError("nvcc failed on %s" % src)
+    if force or _stale(LIB, objs):
+        subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

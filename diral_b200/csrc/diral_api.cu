@@ -1,0 +1,430 @@
+// diral_api.cu -- the C ABI declared in include/diral_env.h: configuration checks, kernel-variant
+// choice, per-call parameter blocks and launches.  No torch, no CPU compute path: every entry point
+// either launches the sm_100a kernels or fails with a message.
+#include "../../include/diral_env.h"
+#include "diral_dev.cuh"
+#include "diral_launch.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define DIRAL_CUDA(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t err__ = (expr);                                                            \
+        if (err__ != cudaSuccess)                                                              \
+            return fail(DIRAL_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2 };
+
+struct Handle {
+    diral_cfg cfg{};
+    diral_buffers bufs{};
+    diral::Params base{};
+    bool bound = false;
+    int device = 0;
+    int variant = VARIANT_AUTO;
+    int force_track_lat = 0;
+    bool lat_live = false;          // a my_step_ch call has stamped last_arrival_time since the reset
+    long long ticks = 0;            // table ticks since the reset (= every vehicle's own seq number)
+    long long launches = 0;
+    double *d_edges = nullptr;      // [2*(B+1)]: linspace(-W, W, B+1) then linspace(-1, 1, B+1)
+    int32_t *d_actions = nullptr;   // staging for generated / host-side actions
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int state_space(const diral_cfg &c)
+{
+    int s = 0;                                              // test_env.py:49-85
+    if (c.add_action) s += c.action_binary ? c.R : 1;
+    if (c.add_channel_obs) s += c.R;
+    if (c.add_reward) s += 1;
+    if (c.add_index) s += 1;
+    if (c.add_velocity) s += 1;
+    if (c.add_position) s += 2;
+    if (c.add_positional_dist) s += c.N - 1;
+    if (c.fingerprint) s += 2;
+    if (c.add_piggy) s += c.B;
+    return s;
+}
+
+int check_cfg(const diral_cfg *c)
+{
+    if (!c) return fail(DIRAL_ERR_ARG, "cfg is NULL");
+    if (c->E < 1) return fail(DIRAL_ERR_ARG, "E must be >= 1 (got %lld)", (long long)c->E);
+    if (c->N < 1 || c->N > diral::BLOCK_MAX_N) return fail(DIRAL_ERR_ARG, "num_users must be in [1, %d] (got %d)", diral::BLOCK_MAX_N, c->N);
+    if (c->R < 1 || c->R > 4096) return fail(DIRAL_ERR_ARG, "num_channels must be in [1, 4096] (got %d)", c->R);
+    if (c->B < 1 || c->B > 256) return fail(DIRAL_ERR_ARG, "num_bins must be in [1, 256] (got %d)", c->B);
+    if (!(c->L > 0.0) || c->L >= 4294967296.0) return fail(DIRAL_ERR_ARG, "highway_length must be in (0, 2^32)");
+    if (!(c->W > 0.0)) return fail(DIRAL_ERR_ARG, "bin_range must be > 0");
+    if (c->add_piggy && c->pos_dist_type != 1 && c->pos_dist_type != 2)
+        return fail(DIRAL_ERR_ARG, "add_positional_dist_type must be 1 or 2 (the reference raises for %d)", c->pos_dist_type);
+    if ((c->add_positional_dist || (c->add_piggy && c->pos_dist_type == 1)) && c->N > 256)
+        return fail(DIRAL_ERR_UNSUPPORTED, "sorted positional-distribution variants support num_users <= 256");
+    if (state_space(*c) < 1) return fail(DIRAL_ERR_ARG, "State selects an empty state vector");
+    return DIRAL_OK;
+}
+
+bool use_group(const Handle *h)
+{
+    if (h->variant == VARIANT_BLOCK) return false;
+    return h->cfg.N <= diral::GROUP_MAX_N;
+}
+
+bool fused_state_ok(const diral_cfg &c)
+{
+    return !c.add_positional_dist && !(c.add_piggy && c.pos_dist_type == 1);
+}
+
+void fill_base(Handle *h)
+{
+    const diral_cfg &c = h->cfg;
+    diral::Params &p = h->base;
+    p = diral::Params{};
+    p.E = c.E; p.env0 = c.env0; p.N = c.N; p.R = c.R; p.B = c.B; p.S = state_space(c);
+    p.Rp = c.R | 1; p.Sp = p.S | 1;
+    p.L = c.L; p.C = c.C; p.C2 = 2 * c.C; p.W = c.W; p.sentinel = c.sentinel;
+    p.inv_binw = (double)c.B / (2.0 * c.W);
+    p.age_threshold = c.age_threshold;
+    p.reward_design = c.reward_design; p.state_type = c.state_type; p.toy = c.toy != 0;
+    p.mobility = c.mobility != 0; p.mobility_vary = c.mobility_vary != 0; p.design_topology = c.design_topology != 0; p.piggy = c.add_piggy != 0;
+    p.add_action = c.add_action != 0; p.action_binary = c.action_binary != 0;
+    p.add_channel_obs = c.add_channel_obs != 0; p.add_reward = c.add_reward != 0; p.add_index = c.add_index != 0;
+    p.add_velocity = c.add_velocity != 0; p.add_position = c.add_position != 0;
+    p.add_positional_dist = c.add_positional_dist != 0; p.pos_dist_type = c.pos_dist_type;
+    p.fingerprint = c.fingerprint != 0;
+    p.vpd_enabled = p.piggy && (p.mobility || p.design_topology);
+    p.edges = h->d_edges;
+}
+
+void bind_params(Handle *h)
+{
+    diral::Params &p = h->base;
+    const diral_buffers &b = h->bufs;
+    p.pos_x = b.pos_x; p.pos_y = b.pos_y; p.vel = b.vel;
+    p.tab_seq = b.tab_seq; p.tab_lu = b.tab_lu; p.tab_x = b.tab_x; p.lat = b.lat;
+    p.obs = b.obs; p.rews = b.rews; p.state = b.state;
+    p.acc_reward = b.acc_reward; p.acc_count = reinterpret_cast<long long *>(b.acc_count);
+    p.scratch = b.scratch; p.trace = b.trace; p.trace_len = b.trace ? b.trace_len : 0;
+}
+
+// numpy.linspace(start, stop, num) as numpy/_core/function_base.py evaluates it (float64,
+// arange(num) * step + start, last element forced to stop).  Built without FMA contraction.
+void np_linspace(double start, double stop, int num, double *y)
+{
+    const int div = num - 1;
+    const double delta = stop - start;
+    volatile double step = delta / div;
+    for (int k = 0; k < num; ++k) {
+        volatile double t = (double)k;
+        if (step == 0) { t = t / div; t = t * delta; } else { t = t * step; }
+        y[k] = t + start;
+    }
+    if (num > 1) y[num - 1] = stop;
+}
+
+Handle *as_handle(void *h) { return static_cast<Handle *>(h); }
+
+int require_bound(Handle *h)
+{
+    if (!h) return fail(DIRAL_ERR_ARG, "handle is NULL");
+    if (!h->bound) return fail(DIRAL_ERR_UNBOUND, "diral_bind() has not been called on this handle");
+    return DIRAL_OK;
+}
+
+int ensure_actions_staging(Handle *h)
+{
+    if (!h->d_actions) DIRAL_CUDA(cudaMalloc(&h->d_actions, sizeof(int32_t) * (size_t)h->cfg.E * h->cfg.N));
+    return DIRAL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t diral_abi_version(void) { return DIRAL_ABI_VERSION; }
+
+const char *diral_last_error(void) { return g_last_error.c_str(); }
+
+int32_t diral_state_space(const diral_cfg *cfg) { return cfg ? state_space(*cfg) : 0; }
+
+size_t diral_state_bytes(const diral_cfg *c)
+{
+    if (!c) return 0;
+    const size_t E = (size_t)c->E, N = (size_t)c->N, NN = N * N;
+    return E * N * 8 * 3 + E * NN * (4 + 4 + 8 + 4) + E * N * 4 * ((size_t)c->R + 1 + (size_t)state_space(*c))
+         + E * (8 + 8 * diral::ACC_COUNTS) + diral_scratch_bytes(c);
+}
+
+size_t diral_scratch_bytes(const diral_cfg *c)
+{
+    if (!c || !c->add_piggy) return 0;
+    diral::Params p{};
+    p.N = c->N; p.R = c->R; p.B = c->B; p.vpd_enabled = c->add_piggy && (c->mobility || c->design_topology);
+    // the group kernel keeps keys in registers; the block kernel needs scratch only past its smem budget
+    if (diral::step_block_keys_fit_smem(p)) return 0;
+    return diral::step_block_scratch_bytes(c->E, c->N);
+}
+
+int diral_create(const diral_cfg *cfg, void **handle)
+{
+    if (!handle) return fail(DIRAL_ERR_ARG, "handle out-pointer is NULL");
+    *handle = nullptr;
+    if (int rc = check_cfg(cfg)) return rc;
+    int dev = 0;
+    DIRAL_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    DIRAL_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(DIRAL_ERR_CUDA, "device %d is sm_%d%d; libdiral_env.so carries sm_100a code only", dev, prop.major, prop.minor);
+    Handle *h = new (std::nothrow) Handle();
+    if (!h) return fail(DIRAL_ERR_ARG, "out of host memory");
+    h->cfg = *cfg; h->device = dev;
+    std::vector<double> edges(2 * (cfg->B + 1));
+    np_linspace(-cfg->W, cfg->W, cfg->B + 1, edges.data());
+    np_linspace(-1.0, 1.0, cfg->B + 1, edges.data() + cfg->B + 1);
+    cudaError_t err = cudaMalloc(&h->d_edges, sizeof(double) * edges.size());
+    if (err == cudaSuccess) err = cudaMemcpy(h->d_edges, edges.data(), sizeof(double) * edges.size(), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) { delete h; return fail(DIRAL_ERR_CUDA, "edge table upload: %s", cudaGetErrorString(err)); }
+    fill_base(h);
+    // make the (possibly > 48 KB) dynamic shared memory carve-ups legal once, up front
+    if (cfg->N <= diral::GROUP_MAX_N) err = diral::prepare_step_group(h->base);
+    if (err == cudaSuccess) {
+        diral::Params q = h->base; q.build_state = 1;
+        const size_t need = diral::step_block_smem_bytes(q, diral::step_block_keys_fit_smem(q));
+        if (need > (size_t)prop.sharedMemPerBlockOptin) {
+            if (cfg->N > diral::GROUP_MAX_N) {
+                cudaFree(h->d_edges); delete h;
+                return fail(DIRAL_ERR_UNSUPPORTED, "N=%d R=%d B=%d needs %zu B of shared memory per CTA (limit %zu)",
+                            cfg->N, cfg->R, cfg->B, need, (size_t)prop.sharedMemPerBlockOptin);
+            }
+        } else err = diral::prepare_step_block(h->base);
+    }
+    if (err != cudaSuccess) { cudaFree(h->d_edges); delete h; return fail(DIRAL_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(err)); }
+    *handle = h;
+    return DIRAL_OK;
+}
+
+int diral_destroy(void *handle)
+{
+    Handle *h = as_handle(handle);
+    if (!h) return DIRAL_OK;
+    DeviceGuard g(h->device);
+    cudaFree(h->d_edges);
+    cudaFree(h->d_actions);
+    delete h;
+    return DIRAL_OK;
+}
+
+int diral_set_option(void *handle, const char *name, int64_t value)
+{
+    Handle *h = as_handle(handle);
+    if (!h || !name) return fail(DIRAL_ERR_ARG, "handle/name is NULL");
+    if (!strcmp(name, "variant")) {
+        if (value < 0 || value > 2) return fail(DIRAL_ERR_ARG, "variant must be 0 (auto), 1 (group) or 2 (block)");
+        if (value == VARIANT_GROUP && h->cfg.N > diral::GROUP_MAX_N)
+            return fail(DIRAL_ERR_ARG, "the group kernel handles num_users <= %d", diral::GROUP_MAX_N);
+        h->variant = (int)value;
+        return DIRAL_OK;
+    }
+    if (!strcmp(name, "track_lat")) { h->force_track_lat = value != 0; return DIRAL_OK; }
+    return fail(DIRAL_ERR_ARG, "unknown option '%s'", name);
+}
+
+int diral_bind(void *handle, const diral_buffers *b)
+{
+    Handle *h = as_handle(handle);
+    if (!h || !b) return fail(DIRAL_ERR_ARG, "handle/buffers is NULL");
+    if (!b->pos_x || !b->pos_y || !b->vel || !b->obs || !b->rews || !b->state || !b->acc_reward || !b->acc_count)
+        return fail(DIRAL_ERR_ARG, "pos_x/pos_y/vel/obs/rews/state/acc_* must all be bound");
+    if (h->cfg.add_piggy && (!b->tab_seq || !b->tab_lu || !b->tab_x))
+        return fail(DIRAL_ERR_ARG, "add_positional_dist_piggy needs tab_seq/tab_lu/tab_x");
+    if (diral_scratch_bytes(&h->cfg) > 0 && !b->scratch)
+        return fail(DIRAL_ERR_ARG, "this configuration needs %zu B of scratch", diral_scratch_bytes(&h->cfg));
+    if (b->trace && b->trace_len < 1) return fail(DIRAL_ERR_ARG, "trace_len must be >= 1 when a trace is bound");
+    h->bufs = *b;
+    bind_params(h);
+    h->bound = true;
+    return DIRAL_OK;
+}
+
+int diral_reset(void *handle, const double *x0, const double *y0, const double *v0, uint64_t seed, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (x0 && (!y0 || !v0)) return fail(DIRAL_ERR_ARG, "x0, y0 and v0 must be given together");
+    DeviceGuard g(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const diral_cfg &c = h->cfg;
+    const size_t EN = (size_t)c.E * c.N, ENN = EN * c.N;
+    if (h->bufs.tab_seq) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_seq, 0, ENN * 4, s));     // vehicle.py:24-33
+    if (h->bufs.tab_lu) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_lu, 0, ENN * 4, s));
+    if (h->bufs.tab_x) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_x, 0, ENN * 8, s));
+    if (h->bufs.lat) DIRAL_CUDA(cudaMemsetAsync(h->bufs.lat, 0xFF, ENN * 4, s));           // network.py:39-42
+    DIRAL_CUDA(cudaMemsetAsync(h->bufs.acc_reward, 0, (size_t)c.E * 8, s));
+    DIRAL_CUDA(cudaMemsetAsync(h->bufs.acc_count, 0, (size_t)c.E * 8 * diral::ACC_COUNTS, s));
+    diral::Params p = h->base;
+    p.seed = seed;
+    DIRAL_CUDA(diral::launch_reset(p, x0, y0, v0, s));
+    h->launches += 1;
+    h->ticks = 0; h->lat_live = false;
+    return DIRAL_OK;
+}
+
+int diral_sample(void *handle, uint64_t seed, int64_t t, int32_t *out, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!out) return fail(DIRAL_ERR_ARG, "out is NULL");
+    DeviceGuard g(h->device);
+    diral::Params p = h->base;
+    p.seed = seed; p.timestep = t;
+    DIRAL_CUDA(diral::launch_sample(p, out, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return DIRAL_OK;
+}
+
+int diral_obtain_state(void *handle, const float *obs, const int32_t *actions, const float *rews, double episode,
+                       double epsilon, float *out, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!obs || !actions || !rews || !out) return fail(DIRAL_ERR_ARG, "obs/actions/rews/out must not be NULL");
+    DeviceGuard g(h->device);
+    diral::Params p = h->base;
+    p.episode = episode; p.epsilon = epsilon;
+    DIRAL_CUDA(diral::launch_obtain_state(p, obs, actions, rews, out, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return DIRAL_OK;
+}
+
+int diral_step(void *handle, int mode, const int32_t *actions, int64_t timestep, int build_state, double episode,
+               double epsilon, uint64_t seed, int32_t *actions_out, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (mode < DIRAL_MY_STEP || mode > DIRAL_MY_STEP_CH) return fail(DIRAL_ERR_ARG, "mode must be 0, 1 or 2 (got %d)", mode);
+    const bool group = use_group(h);
+    const int src_bits = group ? diral::key_src_bits(diral::group_width(h->cfg.N)) : diral::key_src_bits(h->cfg.N);
+    if (h->cfg.add_piggy && h->ticks + 1 >= (1ll << (32 - src_bits)))
+        return fail(DIRAL_ERR_SEQ_RANGE, "slot %lld since reset exceeds the %d-bit sequence field of the packed table keys",
+                    h->ticks + 1, 32 - src_bits);
+    DeviceGuard g(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool fused = build_state && fused_state_ok(h->cfg);
+    diral::Params p = h->base;
+    p.mode = mode; p.timestep = timestep; p.episode = episode; p.epsilon = epsilon; p.seed = seed;
+    p.build_state = fused ? 1 : 0;
+    p.actions = actions; p.gen_actions = actions == nullptr; p.actions_out = actions_out;
+    if (mode == DIRAL_MY_STEP_CH && h->bufs.lat) h->lat_live = true;
+    p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;
+    if (build_state && !fused && !actions && !actions_out) {
+        if (int rc = ensure_actions_staging(h)) return rc;
+        p.actions_out = h->d_actions;
+    }
+    DIRAL_CUDA(group ? diral::launch_step_group(p, s) : diral::launch_step_block(p, s));
+    h->launches += 1;
+    if (h->cfg.add_piggy) h->ticks += 1;
+    if (build_state && !fused) {
+        const int32_t *acts = actions ? actions : p.actions_out;
+        DIRAL_CUDA(diral::launch_obtain_state(p, h->bufs.obs, acts, h->bufs.rews, h->bufs.state, s));
+        h->launches += 1;
+    }
+    return DIRAL_OK;
+}
+
+int diral_rollout(void *handle, int mode, int32_t T, int64_t t0, uint64_t seed, void *stream)
+{
+    for (int32_t k = 0; k < T; ++k)
+        if (int rc = diral_step(handle, mode, nullptr, t0 + k, 1, 0.0, 1.0, seed, nullptr, stream)) return rc;
+    return DIRAL_OK;
+}
+
+int diral_update_velocity(void *handle, const int8_t *draws, uint64_t seed, int64_t episode, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!h->cfg.mobility_vary) return DIRAL_OK;                         // test_env.py:498-504
+    DeviceGuard g(h->device);
+    diral::Params p = h->base;
+    p.seed = seed;
+    DIRAL_CUDA(diral::launch_update_velocity(p, h->bufs.vel, draws, episode, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return DIRAL_OK;
+}
+
+int diral_information_age(void *handle, int64_t timestep, int32_t *out, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!out) return fail(DIRAL_ERR_ARG, "out is NULL");
+    if (!h->bufs.lat) return fail(DIRAL_ERR_ARG, "last_arrival_time (lat) is not bound");
+    DeviceGuard g(h->device);
+    diral::Params p = h->base;
+    p.timestep = timestep;
+    DIRAL_CUDA(diral::launch_information_age(p, out, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return DIRAL_OK;
+}
+
+int diral_episode_metrics(void *handle, int64_t timestep, double *out110, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!out110) return fail(DIRAL_ERR_ARG, "out110 is NULL");
+    DeviceGuard g(h->device);
+    diral::Params p = h->base;
+    p.timestep = timestep;
+    p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;
+    DIRAL_CUDA(diral::launch_episode_metrics(p, out110, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return DIRAL_OK;
+}
+
+int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
+                    float *h_state, float *h_rews, float *h_obs, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!h_actions || !h_state || !h_rews) return fail(DIRAL_ERR_ARG, "h_actions/h_state/h_rews must not be NULL");
+    if (int rc = ensure_actions_staging(h)) return rc;
+    DeviceGuard g(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t EN = (size_t)h->cfg.E * h->cfg.N;
+    DIRAL_CUDA(cudaMemcpyAsync(h->d_actions, h_actions, EN * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (int rc = diral_step(handle, mode, h->d_actions, timestep, 1, episode, epsilon, 0, nullptr, stream)) return rc;
+    DIRAL_CUDA(cudaMemcpyAsync(h_state, h->bufs.state, EN * (size_t)h->base.S * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DIRAL_CUDA(cudaMemcpyAsync(h_rews, h->bufs.rews, EN * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (h_obs) DIRAL_CUDA(cudaMemcpyAsync(h_obs, h->bufs.obs, EN * (size_t)h->cfg.R * sizeof(float), cudaMemcpyDeviceToHost, s));
+    DIRAL_CUDA(cudaStreamSynchronize(s));
+    return DIRAL_OK;
+}
+
+int64_t diral_launch_count(void *handle)
+{
+    Handle *h = as_handle(handle);
+    return h ? h->launches : 0;
+}
+
+}  // extern "C"

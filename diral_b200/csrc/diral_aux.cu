@@ -1,0 +1,278 @@
+// diral_aux.cu -- the kernels around the fused slot: standalone observation build, reset, action
+// sampling, velocity jitter, information age and the end-of-episode metric reduction.
+#include "diral_dev.cuh"
+#include "diral_launch.h"
+
+namespace diral {
+
+namespace {
+
+constexpr int SORT_MAX_N = 256;      // per-thread local arrays of the sorted variants
+constexpr int HIST_MAX_B = 256;
+
+__device__ __forceinline__ void insertion_sort(double *a, int n)
+{
+    for (int i = 1; i < n; ++i) {
+        const double v = a[i];
+        int k = i - 1;
+        while (k >= 0 && a[k] > v) { a[k + 1] = a[k]; --k; }
+        a[k + 1] = v;
+    }
+}
+
+// TestEnv.obtain_state (reference envs/test_env.py:527-583) on caller-supplied obs / actions /
+// rewards, one thread per (env, vehicle).  Every State flag is honoured, including the two variants
+// the fused kernels leave to this one: the direct sorted positional distribution
+// (Network.get_positional_dist, network.py:409-430) and VPD type 1
+// (Network.get_positional_dist_piggy, network.py:432-471).
+template <bool SORTED>
+__global__ void __launch_bounds__(128) obtain_state_kernel(const Params p, const float *__restrict__ obs,
+                                                           const int32_t *__restrict__ actions,
+                                                           const float *__restrict__ rews, float *__restrict__ out,
+                                                           const double *__restrict__ edges1)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.E * p.N) return;
+    const int N = p.N, R = p.R, B = p.B;
+    const long long e = gid / N;
+    const int u = (int)(gid - e * N);
+    const long long vbase = e * N, tbase = e * (long long)N * N;
+    const double xu = p.pos_x[gid], yu = p.pos_y[gid];
+    float *row = out + gid * p.S;
+    int k = 0;
+    const int a = actions[gid];
+    if (p.add_action) {
+        if (p.action_binary) { for (int r = 0; r < R; ++r) row[k++] = (a == r) ? 1.0f : 0.0f; }
+        else row[k++] = (float)a;
+    }
+    if (p.add_channel_obs) { for (int r = 0; r < R; ++r) row[k++] = obs[gid * R + r]; }
+
+    double buf[SORTED ? SORT_MAX_N : 1];
+    if (SORTED && p.add_positional_dist) {          // network.py:409-430
+        int m = 0; double max_dist = 0.0;
+        for (int t = 0; t < N; ++t) {
+            if (t == u) continue;
+            const double xt = p.pos_x[vbase + t], yt = p.pos_y[vbase + t];
+            const double d = dist2d(xt, yt, xu, yu);
+            if (d > max_dist) max_dist = d;
+            buf[m++] = (__dsub_rn(xt, xu) > 0.0) ? d : -d;
+        }
+        insertion_sort(buf, m);
+        for (int q = 0; q < m; ++q) row[k++] = (float)__ddiv_rn(buf[q], max_dist);
+    }
+    if (p.piggy) {
+        const int32_t *seqp = p.tab_seq + tbase, *lup = p.tab_lu + tbase;
+        const double *xp = p.tab_x + tbase;
+        if (p.pos_dist_type == 2 || !p.vpd_enabled) {        // network.py:473-513
+            unsigned short hist[HIST_MAX_B];
+            for (int b = 0; b < B; ++b) hist[b] = 0;
+            int m = 0;
+            if (p.vpd_enabled) {
+                for (int j = 0; j < N; ++j) {
+                    if (j == u || lup[j * N + u] >= p.age_threshold) continue;
+                    const double x1 = xp[j * N + u];
+                    const double y1 = seqp[j * N + u] > 0 ? p.pos_y[vbase + j] : 0.0;
+                    const double d = dist2d(x1, y1, xu, yu);
+                    if (d < p.W) {
+                        const double s = (__dsub_rn(x1, xu) > 0.0) ? d : -d;
+                        hist[vpd_bin(s, p.W, p.inv_binw, B, p.edges)] += 1;
+                        ++m;
+                    }
+                }
+            }
+            const float den = (float)m;
+            for (int b = 0; b < B; ++b) row[k++] = m > 0 ? __fdiv_rn((float)hist[b], den) : 0.0f;
+        } else if (SORTED) {                                  // network.py:432-471 (type 1)
+            int m = 0;
+            for (int j = 0; j < N; ++j) {
+                if (j == u || lup[j * N + u] >= p.age_threshold) continue;
+                const double x1 = xp[j * N + u];
+                const double y1 = seqp[j * N + u] > 0 ? p.pos_y[vbase + j] : 0.0;
+                const double d = dist2d(x1, y1, xu, yu);
+                buf[m++] = (__dsub_rn(x1, xu) > 0.0) ? d : -d;
+            }
+            if (m == 0) { for (int b = 0; b < B; ++b) row[k++] = 0.0f; }
+            else {
+                insertion_sort(buf, m);
+                double nrm = 0.0;
+                for (int q = 0; q < m; ++q) nrm = fmax(nrm, fabs(buf[q]));
+                for (int q = 0; q < m; ++q) buf[q] = __ddiv_rn(buf[q], nrm);
+                // np.histogram(values, explicit edges, weights=values): cumulative sums of the sorted
+                // weights, searchsorted 'left' for every edge but the last ('right'), differences
+                int idx = 0; double cum = 0.0, prev = 0.0;
+                for (int b = 0; b <= B; ++b) {
+                    const double edge = edges1[b];
+                    if (b < B) { while (idx < m && buf[idx] < edge)  { cum = __dadd_rn(cum, buf[idx]); ++idx; } }
+                    else       { while (idx < m && buf[idx] <= edge) { cum = __dadd_rn(cum, buf[idx]); ++idx; } }
+                    if (b > 0) row[k++] = (float)__dsub_rn(cum, prev);
+                    prev = cum;
+                }
+            }
+        }
+    }
+    if (p.add_reward) row[k++] = rews[gid];
+    if (p.add_index) row[k++] = (float)(u + 1);
+    if (p.add_position) { row[k++] = (float)__ddiv_rn(xu, p.L); row[k++] = (float)__ddiv_rn(yu, 2.0); }
+    if (p.add_velocity) row[k++] = (float)p.vel[gid];
+    if (p.fingerprint) { row[k++] = (float)p.episode; row[k++] = (float)p.epsilon; }
+}
+
+// Network.initialize_mobility_topology* (network.py:69-79,92-112) on the counter-based generator
+__global__ void reset_kernel(const Params p, const double *x0, const double *y0, const double *v0,
+                             double *pos_y, double *vel)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.E * p.N) return;
+    const long long e = gid / p.N;
+    const int u = (int)(gid - e * p.N);
+    double x, y, v;
+    if (x0) { x = x0[gid]; y = y0[gid]; v = v0[gid]; }
+    else if (p.design_topology) { x = 195.0 * u; y = u < 2 ? 1.0 : 2.0; v = 1.0; }   // network.py:74-79
+    else {
+        const uint4 o = philox_draw(p.seed, STREAM_TOPOLOGY, (uint32_t)u, p.env0 + e, 0);
+        x = (double)__umulhi(o.x, (uint32_t)p.L);                  // integer-valued uniform on [0, L)
+        y = 0.0;                                                   // randint(0, highway_height/2) == 0
+        const double r53 = __dmul_rn(__dadd_rn(__dmul_rn((double)(o.y >> 5), 67108864.0), (double)(o.z >> 6)),
+                                     1.0 / 9007199254740992.0);
+        v = p.mobility_vary ? 1.7 : __dadd_rn(1.1, __dmul_rn(2.7 - 1.1, r53));   // random.uniform(1.1, 2.7)
+    }
+    p.pos_x[gid] = x; pos_y[gid] = y; vel[gid] = v;
+}
+
+__global__ void sample_kernel(const Params p, int32_t *out)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.E * p.N) return;
+    const long long e = gid / p.N;
+    out[gid] = philox_action(p.seed, (int)(gid - e * p.N), p.env0 + e, p.timestep, p.R);
+}
+
+// Network.update_velocity (network.py:208-222)
+__global__ void update_velocity_kernel(const Params p, double *vel, const int8_t *draws, long long episode)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.E * p.N) return;
+    const long long e = gid / p.N;
+    int d;
+    if (draws) d = draws[gid];
+    else d = 1 + (int)__umulhi(philox_draw(p.seed, STREAM_VELOCITY, (uint32_t)(gid - e * p.N), p.env0 + e, episode).x, 3u);
+    double v = vel[gid];
+    if (d == 1) { v = __dadd_rn(v, 0.55); if (v > 2.77) v = 2.77; }
+    else if (d == 2) { v = __dsub_rn(v, 0.55); if (v < 1.1) v = 1.1; }
+    vel[gid] = v;
+}
+
+__device__ __forceinline__ void ia_accumulate(int *h, int lat, long long timestep)
+{
+    if (lat == -1) return;                                         // network.py:569
+    long long ia = timestep - lat;
+    if (ia >= IA_BINS) return;
+    if (ia < 0) ia += IA_BINS;                                     // Python negative index
+    if (ia >= 0) atomicAdd(&h[ia], 1);
+}
+
+// Network.get_information_age (network.py:560-574), one CTA per env
+__global__ void information_age_kernel(const Params p, int32_t *out)
+{
+    __shared__ int h[IA_BINS];
+    const long long e = blockIdx.x;
+    for (int i = threadIdx.x; i < IA_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const int NN = p.N * p.N;
+    const int32_t *lat = p.lat + e * (long long)NN;
+    for (int i = threadIdx.x; i < NN; i += blockDim.x) {
+        const int t = i / p.N, r = i - t * p.N;
+        if (t != r) ia_accumulate(h, lat[i], p.timestep);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < IA_BINS; i += blockDim.x) out[e * IA_BINS + i] = h[i];
+}
+
+// End-of-episode metric vector; single CTA, fixed reduction order => bit-reproducible.
+__global__ void __launch_bounds__(1024) episode_metrics_kernel(const Params p, double *out)
+{
+    __shared__ double red[5][1024];
+    __shared__ int h[IA_BINS];
+    const int T = blockDim.x, tid = threadIdx.x;
+    for (int i = tid; i < IA_BINS; i += T) h[i] = 0;
+    double s[5] = {0, 0, 0, 0, 0};
+    for (long long e = tid; e < p.E; e += T) {
+        s[0] += p.acc_reward[e];
+        long long *c = p.acc_count + e * ACC_COUNTS;
+        s[1] += (double)c[0]; s[2] += (double)c[1]; s[3] += (double)c[2]; s[4] += (double)c[3];
+        p.acc_reward[e] = 0.0; c[0] = 0; c[1] = 0; c[2] = 0; c[3] = 0;
+    }
+    for (int q = 0; q < 5; ++q) red[q][tid] = s[q];
+    __syncthreads();
+    if (p.track_lat && p.lat) {
+        const long long tot = p.E * (long long)p.N * p.N;
+        for (long long i = tid; i < tot; i += T) {
+            const long long w = i % ((long long)p.N * p.N);
+            const int t = (int)(w / p.N), r = (int)(w - (long long)t * p.N);
+            if (t != r) ia_accumulate(h, p.lat[i], p.timestep);
+        }
+    }
+    for (int o = T / 2; o > 0; o >>= 1) {
+        if (tid < o) { for (int q = 0; q < 5; ++q) red[q][tid] += red[q][tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double slots = red[4][0];
+        out[0] = red[0][0];
+        out[1] = slots * p.R - red[0][0];          // main_test.py:178 summed over env-slots
+        out[2] = red[1][0]; out[3] = red[2][0];
+        out[4] = slots * p.N; out[5] = red[3][0];
+        out[6] = slots; out[7] = 0.0; out[8] = 0.0; out[9] = 0.0;
+    }
+    for (int i = tid; i < IA_BINS; i += T) out[10 + i] = (double)h[i];
+}
+
+inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+cudaError_t launch_obtain_state(const Params &p, const float *obs, const int32_t *actions, const float *rews,
+                                float *out, cudaStream_t stream)
+{
+    const bool sorted = p.add_positional_dist || (p.piggy && p.pos_dist_type == 1);
+    const unsigned grid = blocks_for(p.E * p.N, 128);
+    // edges1 (linspace(-1, 1, B+1)) lives right behind edges in the same device allocation
+    const double *edges1 = p.edges + (p.B + 1);
+    if (sorted) obtain_state_kernel<true><<<grid, 128, 0, stream>>>(p, obs, actions, rews, out, edges1);
+    else        obtain_state_kernel<false><<<grid, 128, 0, stream>>>(p, obs, actions, rews, out, edges1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reset(const Params &p, const double *x0, const double *y0, const double *v0, cudaStream_t stream)
+{
+    reset_kernel<<<blocks_for(p.E * p.N, 256), 256, 0, stream>>>(p, x0, y0, v0, const_cast<double *>(p.pos_y),
+                                                                 const_cast<double *>(p.vel));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample(const Params &p, int32_t *out, cudaStream_t stream)
+{
+    sample_kernel<<<blocks_for(p.E * p.N, 256), 256, 0, stream>>>(p, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_update_velocity(const Params &p, double *vel, const int8_t *draws, long long episode,
+                                   cudaStream_t stream)
+{
+    update_velocity_kernel<<<blocks_for(p.E * p.N, 256), 256, 0, stream>>>(p, vel, draws, episode);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_information_age(const Params &p, int32_t *out, cudaStream_t stream)
+{
+    information_age_kernel<<<(unsigned)p.E, 128, 0, stream>>>(p, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_episode_metrics(const Params &p, double *out110, cudaStream_t stream)
+{
+    episode_metrics_kernel<<<1, 1024, 0, stream>>>(p, out110);
+    return cudaGetLastError();
+}
+
+}  // namespace diral

@@ -1,0 +1,36 @@
+// diral_launch.h -- host-side launch entry points of the CUDA kernels (internal to libdiral_env.so)
+#pragma once
+#include <cstddef>
+#include <cuda_runtime.h>
+
+namespace diral {
+
+struct Params;
+
+// N <= 32: one lane group per environment, table keys in registers (diral_step_group.cu)
+constexpr int GROUP_MAX_N = 32;
+int group_width(int N);
+size_t step_group_smem_bytes(const Params &p);
+cudaError_t prepare_step_group(const Params &p);
+cudaError_t launch_step_group(const Params &p, cudaStream_t stream);
+
+// any N <= 1024: one CTA per environment, table keys in shared memory or scratch (diral_step_block.cu)
+constexpr int BLOCK_MAX_N = 1024;
+int key_src_bits(int N);
+size_t step_block_smem_bytes(const Params &p, bool keys_in_smem);
+bool step_block_keys_fit_smem(const Params &p);
+size_t step_block_scratch_bytes(long long E, int N);
+cudaError_t prepare_step_block(const Params &p);
+cudaError_t launch_step_block(const Params &p, cudaStream_t stream);
+
+// standalone kernels (diral_aux.cu)
+cudaError_t launch_obtain_state(const Params &p, const float *obs, const int32_t *actions, const float *rews,
+                                float *out, cudaStream_t stream);
+cudaError_t launch_reset(const Params &p, const double *x0, const double *y0, const double *v0, cudaStream_t stream);
+cudaError_t launch_sample(const Params &p, int32_t *out, cudaStream_t stream);
+cudaError_t launch_update_velocity(const Params &p, double *vel, const int8_t *draws, long long episode,
+                                   cudaStream_t stream);
+cudaError_t launch_information_age(const Params &p, int32_t *out, cudaStream_t stream);
+cudaError_t launch_episode_metrics(const Params &p, double *out110, cudaStream_t stream);
+
+}  // namespace diral

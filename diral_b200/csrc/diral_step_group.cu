@@ -1,0 +1,400 @@
+// diral_step_group.cu -- fused time-slot kernel for N <= 32 vehicles per environment.
+//
+// One group of G lanes (G = 4, 8, 16 or 32, the power of two >= N) owns one environment; lane u is
+// vehicle u both as a receiver and as the owner of row u of the neighbour table.  A slot is
+//
+//   A  load actions / kinematics; load the seq column-by-column (subject-major => every load is one
+//      coalesced G*4-byte segment) into REGISTERS as packed keys  (seq << log2 G) | origin-row
+//   B  table tick (Vehicle.periodic_update, reference envs/vehicle.py:56-70)
+//   C  for r = 0..R-1 in order (test_env.py:147 -- a true sequential dependency):
+//        ballot the transmitters on r (the per-resource collision histogram, test_env.py:149-157),
+//        reward model for them, nearest in-range transmitter for every other lane
+//        (Network.find_closest_tx, network.py:378-398), then the table merge
+//        (Vehicle.received_update, vehicle.py:35-47) as ONE shuffle + ONE integer max per column:
+//        key[j] = max(key[j], shfl(key[j], nearest)).  Because (xpos, ypos) of an entry is a pure
+//        function of (subject, seq), the max-by-seq join never has to move positions: the key's low
+//        bits remember which row held that version at the start of the slot.
+//   D  mobility (Network.update_positions, network.py:189-206)
+//   E  one streaming pass over the table columns: gather xpos from the origin row by shuffle,
+//      last_updated bookkeeping, write seq / last_updated / xpos back (coalesced), and in the same
+//      pass accumulate the view-based positional distribution histogram
+//      (Network.get_positional_dist_2_piggy + dist_piggy, network.py:473-513,538-558)
+//   F  TestEnv.obtain_state (test_env.py:527-583): assemble [E][N][S] float32 rows in shared memory
+//      and write obs / rewards / state with coalesced stores.
+//
+// HBM traffic per env-slot is the algorithmic minimum SURVEY.md 8(d) states: the table is read once
+// and written once (16 B per entry each way), everything else is O(N).
+#include "diral_dev.cuh"
+#include "diral_launch.h"
+
+namespace diral {
+
+namespace {
+
+constexpr int WARPS = 4;
+
+template <int G> struct Log2;
+template <> struct Log2<4>  { static constexpr int v = 2; };
+template <> struct Log2<8>  { static constexpr int v = 3; };
+template <> struct Log2<16> { static constexpr int v = 4; };
+template <> struct Log2<32> { static constexpr int v = 5; };
+
+__host__ __device__ inline int align8i(int x) { return (x + 7) & ~7; }
+
+// shared-memory carve-up of one group (bytes); mirrored by group_smem_bytes() on the host
+struct GroupSmem {
+    int off_sx, off_sy, off_obs, off_hist, off_st, bytes;
+    __host__ __device__ GroupSmem(int G, int Rp, int B, int Sp, bool state, bool vpd)
+    {
+        int o = 0;
+        off_sx = o;   o += 8 * G;
+        off_sy = o;   o += 8 * G;
+        off_obs = o;  o += align8i(4 * G * Rp);
+        off_hist = o; o += (state && vpd) ? align8i(4 * G * B) : 0;
+        off_st = o;   o += state ? align8i(4 * G * Sp) : 0;
+        bytes = o;
+    }
+};
+
+template <int G>
+__device__ __forceinline__ int reward_weight(const Params &p, const double *sx, const double *sy,
+                                             unsigned txm, double norm)
+{
+    // Network.calculate_reward_weights / calculate_avg_distance (network.py:273-316):
+    // mean of dist over itertools.combinations(transmitters, 2), Python sum() semantics
+    PySum s; int pairs = 0;
+    for (unsigned mi = txm; mi; mi &= mi - 1) {
+        const int i = __ffs(mi) - 1;
+        for (unsigned mj = mi & (mi - 1); mj; mj &= mj - 1) {
+            const int j = __ffs(mj) - 1;
+            s.add(dist2d(sx[i], sy[i], sx[j], sy[j]));
+            ++pairs;
+        }
+    }
+    const double m = __ddiv_rn(s.result(), (double)pairs);
+    return p.toy ? (m == norm) : (m > p.C);
+}
+
+template <int G>
+__global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
+{
+    constexpr int EPW = 32 / G;              // environments per warp
+    constexpr int SB = Log2<G>::v;           // low key bits holding the origin row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int u = lane & (G - 1), sub = lane / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
+    const long long e = ((long long)blockIdx.x * WARPS + warp) * EPW + sub;
+    const int N = p.N, R = p.R, B = p.B;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_edges = reinterpret_cast<double *>(smem_raw);
+    for (int i = threadIdx.x; i <= B; i += blockDim.x) s_edges[i] = p.edges[i];
+    __syncthreads();
+    if (e >= p.E) return;                    // whole groups leave; only group-masked syncs below
+
+    const bool want_state = p.build_state != 0;
+    const bool vpd = want_state && p.vpd_enabled;
+    const GroupSmem lay(G, p.Rp, B, p.Sp, want_state, p.vpd_enabled);
+    unsigned char *gbase = smem_raw + align8i(8 * (B + 1)) + (size_t)(warp * EPW + sub) * lay.bytes;
+    double *sx = reinterpret_cast<double *>(gbase + lay.off_sx);
+    double *sy = reinterpret_cast<double *>(gbase + lay.off_sy);
+    float *obsS = reinterpret_cast<float *>(gbase + lay.off_obs);
+    unsigned *hist = reinterpret_cast<unsigned *>(gbase + lay.off_hist);
+    float *st = reinterpret_cast<float *>(gbase + lay.off_st);
+
+    const bool act = u < N;
+    const long long vbase = e * N;           // first vehicle of this env in the [E][N] arrays
+
+    // ---- A: per-vehicle inputs ---------------------------------------------------------------
+    int a = -1; double x = 0.0, y = 0.0, v = 0.0; int bad = 0;
+    if (act) {
+        a = p.gen_actions ? philox_action(p.seed, u, p.env0 + e, p.timestep, R) : p.actions[vbase + u];
+        if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
+        if (p.gen_actions && p.actions_out) p.actions_out[vbase + u] = a;
+        x = p.pos_x[vbase + u]; y = p.pos_y[vbase + u]; v = p.vel[vbase + u];
+    }
+    sx[u] = x; sy[u] = y;
+
+    // ---- A/B: seq columns -> packed keys in registers, with the tick applied --------------------
+    unsigned key[G]; int seq0[G];
+    const long long tbase = e * (long long)N * N;
+    if (p.piggy) {
+        const int32_t *seqp = p.tab_seq + tbase;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            int s = 0;
+            if (j < N && act) s = seqp[j * N + u];
+            if (j == u) s += 1;                                  // vehicle.py:58
+            seq0[j] = s;
+            key[j] = ((unsigned)s << SB) | (unsigned)u;
+        }
+    }
+    __syncwarp(gmask);
+
+    // toy reward: distance between the first-min-x and first-max-x vehicle (network.py:225-246)
+    double norm = 0.0;
+    if (p.toy && p.mode == MODE_STEP) {
+        double xmin = act ? x : INFINITY, xmax = act ? x : -INFINITY; int imin = u, imax = u;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const double ox = __shfl_xor_sync(gmask, xmin, o, G); const int oi = __shfl_xor_sync(gmask, imin, o, G);
+            if (ox < xmin || (ox == xmin && oi < imin)) { xmin = ox; imin = oi; }
+            const double px = __shfl_xor_sync(gmask, xmax, o, G); const int pi = __shfl_xor_sync(gmask, imax, o, G);
+            if (px > xmax || (px == xmax && pi < imax)) { xmax = px; imax = pi; }
+        }
+        norm = dist2d(sx[imin], sy[imin], sx[imax], sy[imax]);
+    }
+
+    // ---- C: resources in ascending order ---------------------------------------------------------
+    double rew = 0.0;
+    int n_recv = 0, n_pairs = 0;
+    int32_t *latp = p.track_lat ? p.lat + tbase : nullptr;
+    const bool merge_mode = p.piggy && (p.mode != MODE_STEP || p.state_type == 1 || p.state_type == 2);
+
+    for (int r = 0; r < R; ++r) {
+        const unsigned txm = (__ballot_sync(gmask, a == r) & gmask) >> (sub * G);   // collision histogram
+        if (txm == 0u) { if (act) obsS[u * p.Rp + r] = 0.0f; continue; }
+        const int tot = __popc(txm);
+        const bool is_tx = (a == r);
+        const bool is_rx = act && !is_tx;
+
+        // nearest in-range transmitter, ascending id, strict '<' (first wins ties)
+        double best = p.sentinel; int tstar = -1, my_inr = 0;
+        for (unsigned m = txm; m; m &= m - 1) {
+            const int t = __ffs(m) - 1;
+            const double d = dist2d(sx[t], sy[t], x, y);
+            const bool inr = is_rx && d < p.C;
+            if (inr) { ++n_pairs; if (d < best) { best = d; tstar = t; } }
+            else if (is_rx && latp) latp[t * N + u] = -1;                            // network.py:394
+            if (p.mode == MODE_CH && tot > 1) {
+                const unsigned bm = __ballot_sync(gmask, inr);
+                if (u == t) my_inr = __popc(bm);
+            }
+        }
+        if (tstar >= 0) ++n_recv;
+
+        // rewards for the transmitters on r
+        if (p.mode == MODE_STEP) {
+            double rr = 1.0;
+            if (tot > 1) {
+                int w = 0;
+                if (design_needs_weight(p.reward_design, tot)) w = reward_weight<G>(p, sx, sy, txm, norm);
+                rr = collision_reward_step(p.reward_design, tot, w);
+            }
+            if (is_tx) rew = rr;
+        } else if (p.mode == MODE_DESIGN) {
+            if (is_tx) {
+                if (tot == 1) rew = 1.0;
+                else {   // TestEnv.calculate_reward_design (test_env.py:319-349)
+                    int k = 1, last = u;
+                    for (unsigned m = txm; m; m &= m - 1) {
+                        const int t = __ffs(m) - 1;
+                        if (t != u && dist2d(x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
+                    }
+                    if (k == 1) rew = 1.0;
+                    else if (k == 2) rew = (dist2d(x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
+                    else rew = -(double)k;
+                }
+            }
+        } else {
+            int my_recv = 0;
+            if (tot > 1) {
+                for (unsigned m = txm; m; m &= m - 1) {
+                    const int t = __ffs(m) - 1;
+                    const unsigned bm = __ballot_sync(gmask, tstar == t);
+                    if (u == t) my_recv = __popc(bm);
+                }
+            }
+            if (is_tx) rew = channel_reward(p.reward_design, tot, my_recv, my_inr);
+            if (tstar >= 0 && latp) latp[tstar * N + u] = (int32_t)p.timestep;       // test_env.py:436
+        }
+
+        // channel observation (test_env.py:203-240 / :305-306 / :431)
+        if (act) {
+            float o = 0.0f;
+            if (!is_tx) {
+                if (p.mode == MODE_STEP) o = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
+                else o = 1.0f;
+            }
+            obsS[u * p.Rp + r] = o;
+        }
+
+        // table merge: row u <- row u JOIN row tstar, all G receivers at once, one column per step
+        if (merge_mode) {
+            const bool any = __ballot_sync(gmask, tstar >= 0) != 0u;
+            if (any) {
+                const int srcl = tstar >= 0 ? tstar : u;
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    if (j < N) {
+                        const unsigned o = __shfl_sync(gmask, key[j], srcl, G);
+                        key[j] = max(key[j], o);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- D: mobility -------------------------------------------------------------------------------
+    const double x_new = act ? mobility_step(p, x, v, u) : 0.0;
+    if (act && p.mobility) p.pos_x[vbase + u] = x_new;
+
+    // ---- E: stream the table columns: gather xpos, age, write back, VPD histogram -----------------
+    int m_cnt = 0;
+    if (vpd) {
+        for (int k = 0; k < B; ++k) hist[k * G + u] = 0u;
+    }
+    if (p.piggy) {
+        int32_t *seqp = p.tab_seq + tbase, *lup = p.tab_lu + tbase;
+        double *xp = p.tab_x + tbase;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            if (j < N) {
+                int lu = 0; double xo = 0.0;
+                if (act) { lu = lup[j * N + u]; xo = xp[j * N + u]; }
+                if (j == u) { lu = 0; xo = x; } else lu += 1;      // vehicle.py:59-70 (tick)
+                const int sn = (int)(key[j] >> SB);
+                const bool changed = sn != seq0[j];                // strictly newer version merged in
+                const int src = changed ? (int)(key[j] & (unsigned)(G - 1)) : u;
+                const double xn = __shfl_sync(gmask, xo, src, G);
+                if (changed) lu = 0;                               // vehicle.py:47
+                if (act) { seqp[j * N + u] = sn; lup[j * N + u] = lu; xp[j * N + u] = xn; }
+                if (vpd && act && j != u && lu < p.age_threshold) {   // network.py:547
+                    const double y1 = sn > 0 ? sy[j] : 0.0;
+                    const double d = dist2d(xn, y1, x_new, y);
+                    if (d < p.W) {                                 // network.py:487
+                        const double s = (__dsub_rn(xn, x_new) > 0.0) ? d : -d;
+                        const int k = vpd_bin(s, p.W, p.inv_binw, B, s_edges);
+                        hist[k * G + u] += 1u;
+                        ++m_cnt;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- per-env metric accumulators -------------------------------------------------------------
+    {
+        double rs = act ? rew : 0.0; int nr = n_recv, np = n_pairs, nb = bad;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            rs += __shfl_xor_sync(gmask, rs, o, G);
+            nr += __shfl_xor_sync(gmask, nr, o, G);
+            np += __shfl_xor_sync(gmask, np, o, G);
+            nb += __shfl_xor_sync(gmask, nb, o, G);
+        }
+        if (u == 0) {
+            p.acc_reward[e] += rs;
+            long long *c = p.acc_count + e * ACC_COUNTS;
+            c[0] += nr; c[1] += np; c[2] += nb; c[3] += 1;
+        }
+    }
+    if (act) p.rews[vbase + u] = (float)rew;
+
+    // ---- F: state rows (TestEnv.obtain_state) in shared memory -----------------------------------
+    if (want_state && act) {
+        float *row = st + u * p.Sp;
+        int k = 0;
+        if (p.add_action) {
+            if (p.action_binary) { for (int r = 0; r < R; ++r) row[k++] = (a == r) ? 1.0f : 0.0f; }
+            else row[k++] = (float)a;
+        }
+        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) row[k++] = obsS[u * p.Rp + r]; }
+        if (p.piggy) {
+            const float inv_den = (float)m_cnt;
+            for (int b = 0; b < B; ++b)
+                row[k++] = (vpd && m_cnt > 0) ? __fdiv_rn((float)hist[b * G + u], inv_den) : 0.0f;
+        }
+        if (p.add_reward) row[k++] = (float)rew;
+        if (p.add_index) row[k++] = (float)(u + 1);
+        if (p.add_position) { row[k++] = (float)__ddiv_rn(x_new, p.L); row[k++] = (float)__ddiv_rn(y, 2.0); }
+        if (p.add_velocity) row[k++] = (float)v;
+        if (p.fingerprint) { row[k++] = (float)p.episode; row[k++] = (float)p.epsilon; }
+    }
+    __syncwarp(gmask);
+
+    // coalesced copy-out of the [N][R] observation block and the [N][S] state block
+    {
+        float *og = p.obs + vbase * R;
+        int uu = 0, rr = u;                  // element index = uu * R + rr, starting at u, step G
+        for (int idx = u; idx < N * R; idx += G) {
+            while (rr >= R) { rr -= R; ++uu; }
+            og[idx] = obsS[uu * p.Rp + rr];
+            rr += G;
+        }
+    }
+    if (want_state) {
+        const int S = p.S;
+        float *sg = p.state + vbase * S;
+        int uu = 0, ss = u;
+        for (int idx = u; idx < N * S; idx += G) {
+            while (ss >= S) { ss -= S; ++uu; }
+            sg[idx] = st[uu * p.Sp + ss];
+            ss += G;
+        }
+    }
+}
+
+template <int G>
+size_t smem_bytes(const Params &p)
+{
+    const GroupSmem lay(G, p.Rp, p.B, p.Sp, p.build_state != 0, p.vpd_enabled != 0);
+    return (size_t)align8i(8 * (p.B + 1)) + (size_t)WARPS * (32 / G) * lay.bytes;
+}
+
+template <int G>
+cudaError_t prepare_g(const Params &p)
+{
+    Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for
+    const size_t smem = smem_bytes<G>(q);
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(step_group_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int G>
+cudaError_t launch_g(const Params &p, cudaStream_t stream)
+{
+    const long long envs_per_cta = (long long)WARPS * (32 / G);
+    const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
+    step_group_kernel<G><<<(unsigned)grid, WARPS * 32, smem_bytes<G>(p), stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int group_width(int N)
+{
+    return N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
+}
+
+size_t step_group_smem_bytes(const Params &p)
+{
+    switch (group_width(p.N)) {
+    case 4: return smem_bytes<4>(p);
+    case 8: return smem_bytes<8>(p);
+    case 16: return smem_bytes<16>(p);
+    default: return smem_bytes<32>(p);
+    }
+}
+
+cudaError_t prepare_step_group(const Params &p)
+{
+    switch (group_width(p.N)) {
+    case 4: return prepare_g<4>(p);
+    case 8: return prepare_g<8>(p);
+    case 16: return prepare_g<16>(p);
+    default: return prepare_g<32>(p);
+    }
+}
+
+cudaError_t launch_step_group(const Params &p, cudaStream_t stream)
+{
+    switch (group_width(p.N)) {
+    case 4: return launch_g<4>(p, stream);
+    case 8: return launch_g<8>(p, stream);
+    case 16: return launch_g<16>(p, stream);
+    default: return launch_g<32>(p, stream);
+    }
+}
+
+}  // namespace diral

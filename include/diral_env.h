@@ -1,0 +1,160 @@
+/*
+ * diral_env.h -- C ABI of libdiral_env.so: the per-time-slot body of the DIRAL V2V "test
+ * simulator" environment as hand-written sm_100a CUDA kernels over a batch of E independent
+ * environments x N vehicles.
+ *
+ * The reference (gundoganalperen/DIRAL, pure Python) has no FFI layer; its boundary is the
+ * duck-typed env object (envs/test_env.py:6-595) that main_test.py:46-236 drives and the learners
+ * query (algorithms/drl_drqn.py:30,38,39).  Each entry point below cites the reference method it
+ * replaces; the Python mirror of that object (diral_b200/env.py) is a thin ctypes caller of this
+ * file and nothing else.  No torch types cross this boundary: plain pointers, sizes and a
+ * CUstream/cudaStream_t passed as void*.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success or a negative DIRAL_ERR_* code; the message for the
+ *     calling thread's last failure is diral_last_error().
+ *   - "device pointer" arguments must be valid on the handle's CUDA device; launches go to the
+ *     stream the caller passes and never synchronise, except where stated.
+ *   - batched arrays carry a leading env axis E.  Neighbour tables are stored SUBJECT-major:
+ *     tab_*[e][j][i] is vehicle i's belief about vehicle j (the reference keeps
+ *     vehicles[i].pos_of_neighbors[j], envs/vehicle.py:20-33, i.e. the transpose).
+ */
+#ifndef DIRAL_ENV_H
+#define DIRAL_ENV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIRAL_ABI_VERSION 1
+
+enum {
+    DIRAL_OK = 0,
+    DIRAL_ERR_ARG = -1,        /* bad configuration / null pointer / shape             */
+    DIRAL_ERR_CUDA = -2,       /* a CUDA runtime call failed (message has the detail)   */
+    DIRAL_ERR_UNBOUND = -3,    /* diral_bind() has not been called                      */
+    DIRAL_ERR_SEQ_RANGE = -4,  /* slot counter beyond what the packed table keys hold   */
+    DIRAL_ERR_UNSUPPORTED = -5 /* a reference variant SURVEY.md section 8(a) lists as out of scope */
+};
+
+/* step modes: TestEnv.my_step / my_step_design / my_step_ch (envs/test_env.py:124,269,351) */
+enum { DIRAL_MY_STEP = 0, DIRAL_MY_STEP_DESIGN = 1, DIRAL_MY_STEP_CH = 2 };
+
+/* POD mirror of the reference's EnvironmentTest + State kwargs (envs/test_env.py:12-48) */
+typedef struct diral_cfg {
+    int64_t E;                 /* number of independent environments on this device            */
+    int64_t env0;              /* global index of env 0 (keys the counter-based RNG, so results
+                                  do not depend on how the batch is sharded across GPUs)       */
+    int32_t N, R, B;           /* num_users, num_channels, State.num_bins    (test_env.py:12,13,40) */
+    double  L, C, W;           /* highway_length, communication_range, bin_range (:18,21,24)   */
+    int32_t reward_design;     /* :20 */
+    int32_t state_type;        /* State.type :27 */
+    int32_t toy;               /* congestion_test -> Network.toy_example (network.py:36)       */
+    int32_t mobility;          /* :14 */
+    int32_t mobility_vary;     /* :15 */
+    int32_t design_topology;   /* enable_design_topology :16 */
+    int32_t add_action, action_binary, add_channel_obs, add_reward, add_index, add_velocity,
+            add_position, add_positional_dist, add_piggy, pos_dist_type, fingerprint; /* :28-41,19 */
+    int32_t age_threshold;     /* hard-coded 20 in network.py:547 */
+    double  sentinel;          /* hard-coded 100000 in network.py:385 */
+} diral_cfg;
+
+/* Device memory the caller (the Python layer, through torch.empty) owns and binds once.
+ * Element counts use N, R and S = diral_state_space(cfg). */
+typedef struct diral_buffers {
+    double  *pos_x;            /* [E][N]   Vehicle.pos_x   (vehicle.py:10)                      */
+    double  *pos_y;            /* [E][N]   Vehicle.pos_y   (vehicle.py:11)                      */
+    double  *vel;              /* [E][N]   Vehicle.velocity(vehicle.py:14)                      */
+    int32_t *tab_seq;          /* [E][N][N] seq_number,   subject-major (vehicle.py:32)         */
+    int32_t *tab_lu;           /* [E][N][N] last_updated, subject-major (vehicle.py:33)         */
+    double  *tab_x;            /* [E][N][N] xpos,         subject-major (vehicle.py:30)         */
+                               /* ypos is not stored: pos_y never changes between resets, so
+                                  ypos[i][j] == (seq[i][j] > 0 ? pos_y[j] : 0)                 */
+    int32_t *lat;              /* [E][N(tx)][N(rx)] Network.last_arrival_time (network.py:39-42) */
+    float   *obs;              /* [E][N][R] channel observations returned by my_step*           */
+    float   *rews;             /* [E][N]    rewards returned by my_step*                        */
+    float   *state;            /* [E][N][S] obtain_state output                                 */
+    double  *acc_reward;       /* [E]       running sum of rewards since the last episode_metrics */
+    int64_t *acc_count;        /* [E][4]    running {packets received, (tx,rx) pairs in range,
+                                             out-of-range actions, slots}                       */
+    uint32_t *scratch;         /* [diral_scratch_bytes/4] work space (may be NULL if that is 0) */
+    const double *trace;       /* [trace_len][N] Network.x_positions (network.py:171-178) or NULL */
+    int64_t trace_len;
+} diral_buffers;
+
+/* Bytes of device memory behind diral_buffers for this configuration (tables + outputs). */
+size_t diral_state_bytes(const diral_cfg *cfg);
+/* Bytes the `scratch` member must hold (0 when the table keys fit in shared memory). */
+size_t diral_scratch_bytes(const diral_cfg *cfg);
+/* TestEnv.get_state_space (test_env.py:49-85,492). */
+int32_t diral_state_space(const diral_cfg *cfg);
+int32_t diral_abi_version(void);
+
+/* TestEnv.__init__ (test_env.py:7-107): validates the configuration, picks the kernel variant. */
+int diral_create(const diral_cfg *cfg, void **handle);
+int diral_destroy(void *handle);
+int diral_bind(void *handle, const diral_buffers *bufs);
+
+/* Network.__init__ + initialize_mobility_topology* (network.py:15-119): zero tables, lat = -1,
+ * topology from x0/y0/v0 (device, [E][N] float64) or -- when x0 is NULL -- from the counter-based
+ * generator (Philox4x32-10 keyed by seed and the GLOBAL env index). */
+int diral_reset(void *handle, const double *x0, const double *y0, const double *v0, uint64_t seed,
+                void *stream);
+
+/* TestEnv.sample (test_env.py:116-122): uniform actions on [0,R), out [E][N] int32 (device). */
+int diral_sample(void *handle, uint64_t seed, int64_t t, int32_t *out, void *stream);
+
+/* TestEnv.my_step / my_step_design / my_step_ch (test_env.py:124-266, 269-316, 351-443), batched:
+ * table tick, per-resource collision histogram, reward model, nearest-transmitter search, table
+ * merges in ascending resource order, last_arrival_time, mobility.  Writes bufs.obs and bufs.rews.
+ * When build_state != 0 it also writes bufs.state = obtain_state(obs, actions, rews, episode,
+ * epsilon) (test_env.py:527-583) from the same pass over the tables (one read, one write).
+ * actions: [E][N] int32 device pointer, or NULL to draw them on device as diral_sample(seed,
+ * timestep) would (then they are also written to actions_out if that is not NULL). */
+int diral_step(void *handle, int mode, const int32_t *actions, int64_t timestep, int build_state,
+               double episode, double epsilon, uint64_t seed, int32_t *actions_out, void *stream);
+
+/* TestEnv.obtain_state (test_env.py:527-583) on caller-supplied obs/acts/rewards (device). */
+int diral_obtain_state(void *handle, const float *obs, const int32_t *actions, const float *rews,
+                       double episode, double epsilon, float *out, void *stream);
+
+/* T consecutive slots of diral_step(mode, NULL, t0 + k, build_state=1, ...) with on-device actions. */
+int diral_rollout(void *handle, int mode, int32_t T, int64_t t0, uint64_t seed, void *stream);
+
+/* Network.update_velocity (network.py:208-222); draws [E][N] int8 in {1,2,3} or NULL -> Philox. */
+int diral_update_velocity(void *handle, const int8_t *draws, uint64_t seed, int64_t episode,
+                          void *stream);
+
+/* Network.get_information_age (network.py:560-574); out [E][100] int32 (device). */
+int diral_information_age(void *handle, int64_t timestep, int32_t *out, void *stream);
+
+/* End-of-episode metric vector (the only cross-GPU exchange: one all-reduce(sum) of out110):
+ * [0] sum of rewards, [1] sum of collisions = slots*R - sum rewards (main_test.py:178), [2] packets
+ * received, [3] (tx,rx) pairs in range, [4] agent-steps, [5] out-of-range actions, [6..9] reserved,
+ * [10..109] information-age histogram at `timestep`.  Deterministic (fixed-order) reduction over
+ * this device's envs; clears the per-env accumulators.  out110: device, float64[110]. */
+int diral_episode_metrics(void *handle, int64_t timestep, double *out110, void *stream);
+
+/* Host-buffer convenience for callers that keep data on the CPU (the reference's learners do):
+ * copies h_actions in, runs diral_step(build_state=1), copies state/rews (and obs if not NULL) out,
+ * synchronises the stream.  Host pointers should be pinned for full PCIe bandwidth. */
+int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t timestep,
+                    double episode, double epsilon, float *h_state, float *h_rews, float *h_obs,
+                    void *stream);
+
+/* Test/bench knobs: "variant" = 0 auto | 1 lane-group kernel (N <= 32) | 2 one-CTA-per-env kernel;
+ * "track_lat" = 1 keeps last_arrival_time bookkeeping on even before the first my_step_ch call. */
+int diral_set_option(void *handle, const char *name, int64_t value);
+
+/* Number of kernels launched through this handle since creation (bench bookkeeping). */
+int64_t diral_launch_count(void *handle);
+
+const char *diral_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,222 @@
+"""GPU parity: the CUDA path (through the C ABI) against (a) the golden fixtures recorded from the
+unmodified reference and (b) the CPU oracle on seeded random batches.
+
+Bars: integer state (seq / last_updated / last_arrival_time / information age / collision-derived
+rewards / VPD bin counts) bit-exact; float64 positions and table xpos bit-exact; float32 outputs equal
+to the float32 rounding of the reference's float64 values, with a 1e-6 relative allowance where libm's
+exp / pow differ from CUDA's in the last float64 bit (reward designs 3/4, distances with dy != 0).
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import fingerprint_args, golden_names, kwargs_from_meta, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(E, variant="auto", **kw):
+    from diral_b200 import TestEnv
+    return TestEnv(num_envs=E, device="cuda", variant=variant, **kw)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _close32(got, ref64, what, t, exact=False):
+    ref = np.asarray(ref64, dtype=np.float64).astype(np.float32)
+    got = np.asarray(got)
+    if exact:
+        bad = ~((got == ref) | (np.isnan(got) & np.isnan(ref)))
+        assert not bad.any(), "%s differs at slot %d in %d entries" % (what, t, bad.sum())
+    else:
+        ok = np.isclose(got, ref, rtol=1e-6, atol=1e-6, equal_nan=True)
+        assert ok.all(), "%s differs at slot %d: max |d|=%g" % (what, t, np.nanmax(np.abs(got - ref)))
+
+
+def _variants(n):
+    return ["group", "block"] if n <= 32 else ["block"]
+
+
+def _cases():
+    out = []
+    for name in golden_names():
+        _, m = load_golden(name)
+        for v in _variants(m["num_users"]):
+            for fused in (False, True):
+                out.append(pytest.param(name, v, fused, id="%s-%s-%s" % (name, v, "fused" if fused else "split")))
+    return out
+
+
+@pytest.mark.parametrize("name,variant,fused", _cases())
+def test_golden_fixture(name, variant, fused):
+    g, m = load_golden(name)
+    E = 3                                   # identical replicas: every env must reproduce the fixture
+    env = _env(E, variant=variant, **kwargs_from_meta(m))
+    assert env.get_state_space() == m["state_space"]
+    if "trace" in g:
+        env.load_saved_positions(g["trace"])
+    env.reset(init=(g["x0"], g["y0"], g["v0"]))
+    T = g["actions"].shape[0]
+    exact_rewards = m["reward_design"] in (1, 2, 5) or all(str(x) == "my_step_design" for x in g["modes"])
+    for t in range(T):
+        mode = str(g["modes"][t])
+        a = np.broadcast_to(g["actions"][t], (E, env.N))
+        ep, eps = fingerprint_args(m, t)
+        if fused:
+            obs, rews = env._step(mode, a, t, True, ep, eps)
+            state = env._state
+        else:
+            obs, rews = getattr(env, mode)(a, t)
+            state = env.obtain_state(obs, a, rews, ep, eps)
+        for e in (0, E - 1):
+            _close32(_np(obs)[e], g["obs"][t], "obs", t)
+            _close32(_np(rews)[e], g["rews"][t], "rews", t, exact=exact_rewards)
+            assert (np.signbit(_np(rews)[e]) == np.signbit(g["rews"][t])).all(), "reward sign-of-zero, slot %d" % t
+            assert (_np(env.pos_x)[e] == g["pos_x"][t]).all(), "pos_x, slot %d" % t
+            _close32(_np(state)[e], g["state"][t], "state", t)
+            if m["add_positional_dist_piggy"]:
+                assert (_np(env.tab_seq)[e] == g["tab_seq"][t]).all(), "seq table, slot %d" % t
+                assert (_np(env.tab_lu)[e] == g["tab_lu"][t]).all(), "last_updated table, slot %d" % t
+                assert (_np(env.tab_x)[e] == g["tab_x"][t]).all(), "xpos table, slot %d" % t
+                assert (_np(env.tab_y)[e] == g["tab_y"][t]).all(), "ypos table, slot %d" % t
+            assert (_np(env.lat)[e] == g["lat"][t]).all(), "last_arrival_time, slot %d" % t
+            assert (_np(env.network.get_information_age(t))[e] == g["ia"][t]).all(), "information age, slot %d" % t
+        if m["episode_interval"] and t % m["episode_interval"] == m["episode_interval"] - 1:
+            env.update_velocity(np.broadcast_to(g["draws"][t], (E, env.N)))
+        assert (_np(env.vel)[0] == g["vel"][t]).all(), "velocity, slot %d" % t
+    env.close()
+
+
+def _shipped_state(**over):
+    st = dict(type=2, add_action=True, add_reward=False, add_index=False, add_velocity=False,
+              action_index="binary", piggybacking=False, add_position=False, add_positional_dist=False,
+              add_positional_dist_piggy=True, add_positional_dist_type=2, add_channel_obs=False, num_bins=20)
+    st.update(over)
+    return st
+
+
+ORACLE_CASES = [
+    # name, E, T, mode, kwargs
+    ("c1_toy_4x3", 96, 60, "my_step", dict(num_users=4, num_channels=3, highway_length=100, congestion_test=True,
+                                           reward_design=2, communication_range=250, mobility=True)),
+    ("c2_6x5", 128, 60, "my_step", dict(num_users=6, num_channels=5, highway_length=1170, reward_design=2,
+                                        communication_range=250, mobility=True)),
+    ("c3_32x20", 64, 60, "my_step", dict(num_users=32, num_channels=20, highway_length=800, reward_design=2,
+                                         communication_range=250, mobility=True)),
+    ("c3_32x20_ch3", 48, 40, "my_step_ch", dict(num_users=32, num_channels=20, highway_length=800, reward_design=3,
+                                                communication_range=250, mobility=True)),
+    ("c3_32x20_design", 32, 30, "my_step_design", dict(num_users=32, num_channels=20, highway_length=800,
+                                                       reward_design=2, communication_range=250, mobility=True)),
+    ("n13x7_rd1", 40, 40, "my_step", dict(num_users=13, num_channels=7, highway_length=400, reward_design=1,
+                                          communication_range=120, mobility=True)),
+    ("n29x4_chanobs", 40, 40, "my_step", dict(num_users=29, num_channels=4, highway_length=3000, reward_design=5,
+                                              communication_range=250, mobility=True, chanobs=True)),
+    ("c4_128x64", 6, 12, "my_step", dict(num_users=128, num_channels=64, highway_length=3200, reward_design=2,
+                                         communication_range=250, mobility=True)),
+    ("c4_128x64_ch", 4, 10, "my_step_ch", dict(num_users=128, num_channels=64, highway_length=3200, reward_design=2,
+                                               communication_range=250, mobility=True)),
+    ("c5_256x128", 2, 6, "my_step", dict(num_users=256, num_channels=128, highway_length=6400, reward_design=2,
+                                         communication_range=250, mobility=True)),
+    ("c5_100x50", 5, 10, "my_step", dict(num_users=100, num_channels=50, highway_length=2500, reward_design=2,
+                                         communication_range=250, mobility=True)),
+]
+
+
+def _oracle_cases():
+    out = []
+    for name, E, T, mode, kw in ORACLE_CASES:
+        for v in _variants(kw["num_users"]):
+            out.append(pytest.param(name, E, T, mode, kw, v, id="%s-%s" % (name, v)))
+    return out
+
+
+@pytest.mark.parametrize("name,E,T,mode,kw,variant", _oracle_cases())
+def test_random_batch_against_oracle(name, E, T, mode, kw, variant):
+    """Seeded Philox topology + Philox actions on both sides (the generator is a shared
+    specification, so this also pins the device RNG), every output compared every slot."""
+    from oracle.c_oracle import COracle
+    kw = dict(kw)
+    chanobs = kw.pop("chanobs", False)
+    kw["bin_range"] = 500
+    kw["State"] = _shipped_state(add_channel_obs=chanobs)
+    seed, env0 = 1234, 7
+    orc = COracle(num_envs=E, threads=8, **kw)
+    x0, y0, v0 = orc.reset_philox(seed, env0)
+    env = _env(E, variant=variant, seed=seed, env_offset=env0, **kw)
+    assert (_np(env.pos_x) == x0).all() and (_np(env.vel) == v0).all() and (_np(env.pos_y) == y0).all()
+    exact_rewards = kw["reward_design"] in (1, 2, 5) or mode == "my_step_design"
+    tot_recv = tot_pairs = 0
+    for t in range(T):
+        a_ref = orc.philox_actions(seed, t, env0)
+        a = env.sample(t)
+        assert (_np(a) == a_ref).all(), "sample() differs from the Philox specification at t=%d" % t
+        o_ref, r_ref, counts = orc.step(mode, a_ref, t, want_counts=True)
+        s_ref = orc.obtain_state(o_ref, a_ref, r_ref)
+        env._step(mode, a, t, True)
+        _close32(_np(env._obs), o_ref, "obs", t, exact=True)
+        _close32(_np(env._rews), r_ref, "rews", t, exact=exact_rewards)
+        _close32(_np(env._state), s_ref, "state", t, exact=True)
+        assert (_np(env.pos_x) == orc.pos_x).all(), "pos_x, slot %d" % t
+        assert (_np(env.tab_seq) == orc.tab_seq).all(), "seq table, slot %d" % t
+        assert (_np(env.tab_lu) == orc.tab_lu).all(), "last_updated table, slot %d" % t
+        assert (_np(env.tab_x) == orc.tab_x).all(), "xpos table, slot %d" % t
+        assert (_np(env.lat) == orc.lat).all(), "last_arrival_time, slot %d" % t
+        tot_recv += int(counts[:, 0].sum()); tot_pairs += int(counts[:, 1].sum())
+    assert (_np(env.network.get_information_age(T - 1)) == orc.information_age(T - 1)).all()
+    met = _np(env.episode_metrics(T - 1))
+    assert met[2] == tot_recv and met[3] == tot_pairs and met[4] == E * T * kw["num_users"] and met[5] == 0
+    assert (met[10:] == orc.information_age(T - 1).sum(axis=0)).all()
+    env.close()
+
+
+def test_full_size_invariants_and_shard_invariance():
+    """BASELINE configs[2] at full size (4096 envs x 32 UE x 20 resources): size-independent
+    properties, and the 2-way sharded run equals the single-device run bit for bit."""
+    kw = dict(num_users=32, num_channels=20, highway_length=800, reward_design=2, communication_range=250,
+              mobility=True, bin_range=500, State=_shipped_state())
+    E, T = 4096, 30
+    full = _env(E, seed=99, **kw)
+    lo = _env(E // 2, seed=99, env_offset=0, **kw)
+    hi = _env(E // 2, seed=99, env_offset=E // 2, **kw)
+    for t in range(T):
+        s, r, info = full.step()
+        s0, r0, _ = lo.step(); s1, r1, _ = hi.step()
+        assert torch.equal(s, torch.cat([s0, s1])) and torch.equal(r, torch.cat([r0, r1]))
+        a = info["actions"]
+        assert int(a.min()) >= 0 and int(a.max()) < 20
+        onehot = s[..., :20]
+        assert torch.equal(onehot.sum(-1), torch.ones_like(onehot[..., 0]))
+        assert torch.equal(onehot.argmax(-1).int(), a)
+        vpd = s[..., 20:].double().sum(-1)
+        assert bool((((vpd - 1).abs() < 1e-5) | (vpd == 0)).all()), "VPD sums to 1 or is empty"
+        # a sole transmitter earns exactly 1; design 2 rewards live in {1, 0, -2, -3, ...}
+        cnt = torch.zeros((E, 20), device=a.device).scatter_add_(1, a.long(), torch.ones_like(a, dtype=torch.float32))
+        mine = cnt.gather(1, a.long())
+        assert torch.equal(r[mine == 1], torch.ones_like(r[mine == 1]))
+        assert torch.equal(r[mine > 2], -mine[mine > 2])
+        diag = torch.diagonal(full.tab_seq, dim1=1, dim2=2)
+        assert bool((diag == t + 1).all()), "own sequence number counts the slots"
+        assert bool((full.tab_seq <= t + 1).all()) and bool((full.pos_x >= 0).all()) and bool((full.pos_x < 800).all())
+    assert torch.equal(full._tab_seq, torch.cat([lo._tab_seq, hi._tab_seq]))
+    assert torch.equal(full._tab_x, torch.cat([lo._tab_x, hi._tab_x]))
+    m = full.episode_metrics(); m2 = lo.episode_metrics() + hi.episode_metrics()
+    assert torch.equal(m, m2)
+    assert float(m[4]) == E * T * 32
+
+
+def test_bad_actions_are_counted_and_errors_are_loud():
+    from diral_b200 import DiralError
+    kw = dict(num_users=6, num_channels=5, highway_length=1170, reward_design=2, communication_range=250,
+              mobility=True, State=_shipped_state())
+    env = _env(4, **kw)
+    a = torch.zeros((4, 6), dtype=torch.int32, device="cuda"); a[1, 2] = 9; a[3, 0] = -1
+    env.my_step(a, 0)
+    assert float(env.episode_metrics()[5]) == 2
+    with pytest.raises(ValueError):
+        env.my_step(torch.zeros((4, 5), dtype=torch.int32), 1)
+    with pytest.raises(ValueError):
+        _env(2, **dict(kw, State=_shipped_state(piggybacking=True)))
+    with pytest.raises(DiralError):
+        _env(2, **dict(kw, num_channels=0))
