@@ -104,6 +104,7 @@ void fill_base(Handle *h)
     p = diral::Params{};
     p.E = c.E; p.env0 = c.env0; p.N = c.N; p.R = c.R; p.B = c.B; p.S = state_space(c);
     p.Rp = c.R | 1; p.Sp = p.S | 1;
+    p.inv_R = (unsigned)(((1ull << 32) + c.R - 1) / c.R); p.inv_S = (unsigned)(((1ull << 32) + p.S - 1) / p.S);
     p.L = c.L; p.C = c.C; p.C2 = 2 * c.C; p.W = c.W; p.sentinel = c.sentinel;
     p.inv_binw = (double)c.B / (2.0 * c.W);
     p.age_threshold = c.age_threshold;

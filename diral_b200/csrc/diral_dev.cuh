@@ -26,6 +26,7 @@ struct Params {
     long long E, env0;
     int N, R, B, S;
     int Rp, Sp;               // odd-padded shared-memory row strides for the obs / state staging
+    unsigned inv_R, inv_S;    // ceil(2^32 / R), ceil(2^32 / S): row = umulhi(idx, inv) for idx * len < 2^32
     // geometry
     double L, C, C2, W, sentinel, inv_binw;
     int age_threshold;

@@ -15,15 +15,19 @@
 //        function of (subject, seq), the max-by-seq join never has to move positions: the key's low
 //        bits remember which row held that version at the start of the slot.
 //   D  mobility (Network.update_positions, network.py:189-206)
-//   E  one streaming pass over the table columns: gather xpos from the origin row by shuffle,
-//      last_updated bookkeeping, write seq / last_updated / xpos back (coalesced), and in the same
-//      pass accumulate the view-based positional distribution histogram
-//      (Network.get_positional_dist_2_piggy + dist_piggy, network.py:473-513,538-558)
+//   E  one streaming pass over the table columns, software-pipelined in chunks of CH columns:
+//      gather xpos from the origin row by shuffle, last_updated bookkeeping, write seq /
+//      last_updated / xpos back (coalesced), and in the same pass accumulate the view-based
+//      positional distribution histogram (Network.get_positional_dist_2_piggy + dist_piggy,
+//      network.py:473-513,538-558)
 //   F  TestEnv.obtain_state (test_env.py:527-583): assemble [E][N][S] float32 rows in shared memory
 //      and write obs / rewards / state with coalesced stores.
 //
 // HBM traffic per env-slot is the algorithmic minimum SURVEY.md 8(d) states: the table is read once
 // and written once (16 B per entry each way), everything else is O(N).
+//
+// FULL (N == G) instantiations drop every "is this lane / column live" predicate and turn all
+// table addresses into compile-time offsets from one base pointer.
 #include "diral_dev.cuh"
 #include "diral_launch.h"
 
@@ -31,7 +35,7 @@ namespace diral {
 
 namespace {
 
-constexpr int WARPS = 4;
+constexpr int CH = 8;                    // table columns per software-pipeline stage
 
 template <int G> struct Log2;
 template <> struct Log2<4>  { static constexpr int v = 2; };
@@ -41,7 +45,7 @@ template <> struct Log2<32> { static constexpr int v = 5; };
 
 __host__ __device__ inline int align8i(int x) { return (x + 7) & ~7; }
 
-// shared-memory carve-up of one group (bytes); mirrored by group_smem_bytes() on the host
+// shared-memory carve-up of one group (bytes); the host computes the same numbers
 struct GroupSmem {
     int off_sx, off_sy, off_obs, off_hist, off_st, bytes;
     __host__ __device__ GroupSmem(int G, int Rp, int B, int Sp, bool state, bool vpd)
@@ -56,18 +60,34 @@ struct GroupSmem {
     }
 };
 
-template <int G>
-__device__ __forceinline__ int reward_weight(const Params &p, const double *sx, const double *sy,
-                                             unsigned txm, double norm)
+// general distance, kept out of line so that the common dy == 0 highway never executes (or even
+// schedules around) the fp64 square-root sequence
+__device__ __noinline__ double dist_slow(double dx, double dy)
 {
-    // Network.calculate_reward_weights / calculate_avg_distance (network.py:273-316):
-    // mean of dist over itertools.combinations(transmitters, 2), Python sum() semantics
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+// Network.dist (network.py:318-332); `flat` (warp-uniform) promises dy == 0, where the result is |dx|
+__device__ __forceinline__ double dist_uni(bool flat, double x1, double y1, double x2, double y2)
+{
+    const double dx = __dsub_rn(x2, x1);
+    if (flat) return fabs(dx);
+    const double dy = __dsub_rn(y2, y1);
+    if (dy == 0.0) return fabs(dx);
+    return dist_slow(dx, dy);
+}
+
+// Network.calculate_reward_weights / calculate_avg_distance (network.py:273-316):
+// mean of dist over itertools.combinations(transmitters, 2), Python sum() semantics
+__device__ __noinline__ int reward_weight(const Params &p, bool flat, const double *sx, const double *sy,
+                                          unsigned txm, double norm)
+{
     PySum s; int pairs = 0;
     for (unsigned mi = txm; mi; mi &= mi - 1) {
         const int i = __ffs(mi) - 1;
         for (unsigned mj = mi & (mi - 1); mj; mj &= mj - 1) {
             const int j = __ffs(mj) - 1;
-            s.add(dist2d(sx[i], sy[i], sx[j], sy[j]));
+            s.add(dist_uni(flat, sx[i], sy[i], sx[j], sy[j]));
             ++pairs;
         }
     }
@@ -75,7 +95,7 @@ __device__ __forceinline__ int reward_weight(const Params &p, const double *sx, 
     return p.toy ? (m == norm) : (m > p.C);
 }
 
-template <int G>
+template <int G, bool FULL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
 {
     constexpr int EPW = 32 / G;              // environments per warp
@@ -84,7 +104,8 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     const int u = lane & (G - 1), sub = lane / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
     const long long e = ((long long)blockIdx.x * WARPS + warp) * EPW + sub;
-    const int N = p.N, R = p.R, B = p.B;
+    const int N = FULL ? G : p.N;
+    const int R = p.R, B = p.B;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_edges = reinterpret_cast<double *>(smem_raw);
@@ -102,8 +123,9 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     unsigned *hist = reinterpret_cast<unsigned *>(gbase + lay.off_hist);
     float *st = reinterpret_cast<float *>(gbase + lay.off_st);
 
-    const bool act = u < N;
+    const bool act = FULL ? true : (u < N);
     const long long vbase = e * N;           // first vehicle of this env in the [E][N] arrays
+    const long long tbase = e * (long long)N * N;
 
     // ---- A: per-vehicle inputs ---------------------------------------------------------------
     int a = -1; double x = 0.0, y = 0.0, v = 0.0; int bad = 0;
@@ -116,19 +138,24 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     sx[u] = x; sy[u] = y;
 
     // ---- A/B: seq columns -> packed keys in registers, with the tick applied --------------------
-    unsigned key[G]; int seq0[G];
-    const long long tbase = e * (long long)N * N;
+    unsigned key[G];
+    const int32_t *seq_in = p.tab_seq + tbase + u;       // column j of this lane: seq_in[j * N]
     if (p.piggy) {
-        const int32_t *seqp = p.tab_seq + tbase;
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             int s = 0;
-            if (j < N && act) s = seqp[j * N + u];
+            if (FULL || (j < N && act)) s = seq_in[j * N];
             if (j == u) s += 1;                                  // vehicle.py:58
-            seq0[j] = s;
             key[j] = ((unsigned)s << SB) | (unsigned)u;
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < G; ++j) key[j] = 0u;
     }
+    // every vehicle on the same lane of the highway (dy == 0 for every pair)?  warp-uniform per group
+    const double y0 = __shfl_sync(gmask, y, 0, G);
+    const bool flat = (__ballot_sync(gmask, act && y != y0) & gmask) == 0u;
+    const bool flat0 = flat && y0 == 0.0;    // ... and phantom (never heard, ypos = 0) entries too
     __syncwarp(gmask);
 
     // toy reward: distance between the first-min-x and first-max-x vehicle (network.py:225-246)
@@ -142,18 +169,19 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
             const double px = __shfl_xor_sync(gmask, xmax, o, G); const int pi = __shfl_xor_sync(gmask, imax, o, G);
             if (px > xmax || (px == xmax && pi < imax)) { xmax = px; imax = pi; }
         }
-        norm = dist2d(sx[imin], sy[imin], sx[imax], sy[imax]);
+        norm = dist_uni(flat, sx[imin], sy[imin], sx[imax], sy[imax]);
     }
 
     // ---- C: resources in ascending order ---------------------------------------------------------
     double rew = 0.0;
     int n_recv = 0, n_pairs = 0;
-    int32_t *latp = p.track_lat ? p.lat + tbase : nullptr;
+    int32_t *latp = p.track_lat ? p.lat + tbase + u : nullptr;       // lat[t][u] = latp[t * N]
     const bool merge_mode = p.piggy && (p.mode != MODE_STEP || p.state_type == 1 || p.state_type == 2);
+    float *obs_row = obsS + u * p.Rp;
 
     for (int r = 0; r < R; ++r) {
         const unsigned txm = (__ballot_sync(gmask, a == r) & gmask) >> (sub * G);   // collision histogram
-        if (txm == 0u) { if (act) obsS[u * p.Rp + r] = 0.0f; continue; }
+        if (txm == 0u) { obs_row[r] = 0.0f; continue; }
         const int tot = __popc(txm);
         const bool is_tx = (a == r);
         const bool is_rx = act && !is_tx;
@@ -162,10 +190,10 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
         double best = p.sentinel; int tstar = -1, my_inr = 0;
         for (unsigned m = txm; m; m &= m - 1) {
             const int t = __ffs(m) - 1;
-            const double d = dist2d(sx[t], sy[t], x, y);
+            const double d = dist_uni(flat, sx[t], sy[t], x, y);
             const bool inr = is_rx && d < p.C;
             if (inr) { ++n_pairs; if (d < best) { best = d; tstar = t; } }
-            else if (is_rx && latp) latp[t * N + u] = -1;                            // network.py:394
+            else if (latp && is_rx) latp[t * N] = -1;                                // network.py:394
             if (p.mode == MODE_CH && tot > 1) {
                 const unsigned bm = __ballot_sync(gmask, inr);
                 if (u == t) my_inr = __popc(bm);
@@ -178,7 +206,7 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
             double rr = 1.0;
             if (tot > 1) {
                 int w = 0;
-                if (design_needs_weight(p.reward_design, tot)) w = reward_weight<G>(p, sx, sy, txm, norm);
+                if (design_needs_weight(p.reward_design, tot)) w = reward_weight(p, flat, sx, sy, txm, norm);
                 rr = collision_reward_step(p.reward_design, tot, w);
             }
             if (is_tx) rew = rr;
@@ -189,10 +217,10 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
                     int k = 1, last = u;
                     for (unsigned m = txm; m; m &= m - 1) {
                         const int t = __ffs(m) - 1;
-                        if (t != u && dist2d(x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
+                        if (t != u && dist_uni(flat, x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
                     }
                     if (k == 1) rew = 1.0;
-                    else if (k == 2) rew = (dist2d(x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
+                    else if (k == 2) rew = (dist_uni(flat, x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
                     else rew = -(double)k;
                 }
             }
@@ -206,32 +234,24 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
                 }
             }
             if (is_tx) rew = channel_reward(p.reward_design, tot, my_recv, my_inr);
-            if (tstar >= 0 && latp) latp[tstar * N + u] = (int32_t)p.timestep;       // test_env.py:436
+            if (tstar >= 0 && latp) latp[tstar * N] = (int32_t)p.timestep;           // test_env.py:436
         }
 
         // channel observation (test_env.py:203-240 / :305-306 / :431)
-        if (act) {
+        {
             float o = 0.0f;
             if (!is_tx) {
                 if (p.mode == MODE_STEP) o = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
                 else o = 1.0f;
             }
-            obsS[u * p.Rp + r] = o;
+            obs_row[r] = o;
         }
 
         // table merge: row u <- row u JOIN row tstar, all G receivers at once, one column per step
-        if (merge_mode) {
-            const bool any = __ballot_sync(gmask, tstar >= 0) != 0u;
-            if (any) {
-                const int srcl = tstar >= 0 ? tstar : u;
+        if (merge_mode && __ballot_sync(gmask, tstar >= 0) != 0u) {
+            const int srcl = tstar >= 0 ? tstar : u;
 #pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    if (j < N) {
-                        const unsigned o = __shfl_sync(gmask, key[j], srcl, G);
-                        key[j] = max(key[j], o);
-                    }
-                }
-            }
+            for (int j = 0; j < G; ++j) key[j] = max(key[j], __shfl_sync(gmask, key[j], srcl, G));
         }
     }
 
@@ -245,25 +265,47 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
         for (int k = 0; k < B; ++k) hist[k * G + u] = 0u;
     }
     if (p.piggy) {
-        int32_t *seqp = p.tab_seq + tbase, *lup = p.tab_lu + tbase;
-        double *xp = p.tab_x + tbase;
+        int32_t *seqp = p.tab_seq + tbase + u, *lup = p.tab_lu + tbase + u;
+        double *xp = p.tab_x + tbase + u;
+        int s_buf[2][CH], l_buf[2][CH]; double x_buf[2][CH];
+        auto load_chunk = [&](int c, int slot) {
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            if (j < N) {
-                int lu = 0; double xo = 0.0;
-                if (act) { lu = lup[j * N + u]; xo = xp[j * N + u]; }
-                if (j == u) { lu = 0; xo = x; } else lu += 1;      // vehicle.py:59-70 (tick)
+            for (int q = 0; q < CH; ++q) {
+                const int j = c * CH + q;
+                if (j < G && (FULL || (j < N && act))) {
+                    s_buf[slot][q] = seqp[j * N]; l_buf[slot][q] = lup[j * N]; x_buf[slot][q] = xp[j * N];
+                } else { s_buf[slot][q] = 0; l_buf[slot][q] = 0; x_buf[slot][q] = 0.0; }
+            }
+        };
+        constexpr int NCH = (G + CH - 1) / CH;
+        load_chunk(0, 0);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            if (c + 1 < NCH) load_chunk(c + 1, (c + 1) & 1);
+#pragma unroll
+            for (int q = 0; q < CH; ++q) {
+                const int j = c * CH + q;
+                if (j >= G) continue;
+                int s0 = s_buf[c & 1][q], lu = l_buf[c & 1][q]; double xo = x_buf[c & 1][q];
+                if (j == u) { s0 += 1; lu = 0; xo = x; } else lu += 1;       // vehicle.py:58-70 (tick)
                 const int sn = (int)(key[j] >> SB);
-                const bool changed = sn != seq0[j];                // strictly newer version merged in
+                const bool changed = sn != s0;                     // strictly newer version merged in
                 const int src = changed ? (int)(key[j] & (unsigned)(G - 1)) : u;
                 const double xn = __shfl_sync(gmask, xo, src, G);
                 if (changed) lu = 0;                               // vehicle.py:47
-                if (act) { seqp[j * N + u] = sn; lup[j * N + u] = lu; xp[j * N + u] = xn; }
-                if (vpd && act && j != u && lu < p.age_threshold) {   // network.py:547
-                    const double y1 = sn > 0 ? sy[j] : 0.0;
-                    const double d = dist2d(xn, y1, x_new, y);
-                    if (d < p.W) {                                 // network.py:487
-                        const double s = (__dsub_rn(xn, x_new) > 0.0) ? d : -d;
+                if (FULL || (j < N && act)) { seqp[j * N] = sn; lup[j * N] = lu; xp[j * N] = xn; }
+                if (vpd && (FULL || (j < N && act)) && j != u && lu < p.age_threshold) {   // network.py:547
+                    double s; bool in;
+                    if (flat0) {           // dy == 0: signed distance is exactly xpos - own x
+                        s = __dsub_rn(xn, x_new);
+                        in = fabs(s) < p.W;
+                    } else {
+                        const double y1 = sn > 0 ? sy[j] : 0.0;
+                        const double d = dist_uni(false, xn, y1, x_new, y);
+                        in = d < p.W;
+                        s = (__dsub_rn(xn, x_new) > 0.0) ? d : -d;
+                    }
+                    if (in) {                                      // network.py:487
                         const int k = vpd_bin(s, p.W, p.inv_binw, B, s_edges);
                         hist[k * G + u] += 1u;
                         ++m_cnt;
@@ -299,11 +341,11 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
             if (p.action_binary) { for (int r = 0; r < R; ++r) row[k++] = (a == r) ? 1.0f : 0.0f; }
             else row[k++] = (float)a;
         }
-        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) row[k++] = obsS[u * p.Rp + r]; }
+        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) row[k++] = obs_row[r]; }
         if (p.piggy) {
-            const float inv_den = (float)m_cnt;
+            const float den = (float)m_cnt;
             for (int b = 0; b < B; ++b)
-                row[k++] = (vpd && m_cnt > 0) ? __fdiv_rn((float)hist[b * G + u], inv_den) : 0.0f;
+                row[k++] = (vpd && m_cnt > 0) ? __fdiv_rn((float)hist[b * G + u], den) : 0.0f;
         }
         if (p.add_reward) row[k++] = (float)rew;
         if (p.add_index) row[k++] = (float)(u + 1);
@@ -313,51 +355,66 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     }
     __syncwarp(gmask);
 
-    // coalesced copy-out of the [N][R] observation block and the [N][S] state block
+    // coalesced copy-out of the [N][R] observation block and the [N][S] state block; element idx of
+    // the block sits at row idx / len, found with a 2^32 / len reciprocal (exact for idx < 2^16)
     {
         float *og = p.obs + vbase * R;
-        int uu = 0, rr = u;                  // element index = uu * R + rr, starting at u, step G
+        const unsigned inv = p.inv_R;
         for (int idx = u; idx < N * R; idx += G) {
-            while (rr >= R) { rr -= R; ++uu; }
-            og[idx] = obsS[uu * p.Rp + rr];
-            rr += G;
+            const int uu = (int)__umulhi((unsigned)idx, inv);
+            og[idx] = obsS[uu * p.Rp + (idx - uu * R)];
         }
     }
     if (want_state) {
         const int S = p.S;
         float *sg = p.state + vbase * S;
-        int uu = 0, ss = u;
+        const unsigned inv = p.inv_S;
         for (int idx = u; idx < N * S; idx += G) {
-            while (ss >= S) { ss -= S; ++uu; }
-            sg[idx] = st[uu * p.Sp + ss];
-            ss += G;
+            const int uu = (int)__umulhi((unsigned)idx, inv);
+            sg[idx] = st[uu * p.Sp + (idx - uu * S)];
         }
     }
 }
 
 template <int G>
-size_t smem_bytes(const Params &p)
+size_t smem_bytes(const Params &p, int warps)
 {
     const GroupSmem lay(G, p.Rp, p.B, p.Sp, p.build_state != 0, p.vpd_enabled != 0);
-    return (size_t)align8i(8 * (p.B + 1)) + (size_t)WARPS * (32 / G) * lay.bytes;
+    return (size_t)align8i(8 * (p.B + 1)) + (size_t)warps * (32 / G) * lay.bytes;
 }
+
+template <int G, bool FULL, int WARPS>
+cudaError_t prepare_gw(const Params &p)
+{
+    Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for
+    const size_t smem = smem_bytes<G>(q, WARPS);
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(step_group_kernel<G, FULL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int G, bool FULL, int WARPS>
+cudaError_t launch_gw(const Params &p, cudaStream_t stream)
+{
+    const long long envs_per_cta = (long long)WARPS * (32 / G);
+    const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
+    step_group_kernel<G, FULL, WARPS><<<(unsigned)grid, WARPS * 32, smem_bytes<G>(p, WARPS), stream>>>(p);
+    return cudaGetLastError();
+}
+
+// one warp per CTA keeps the tail of the last wave short when few groups share a warp (G >= 16);
+// small groups pack 4 warps so that a CTA still carries a useful number of environments
+template <int G> struct WarpsFor { static constexpr int v = G >= 16 ? 1 : 4; };
 
 template <int G>
 cudaError_t prepare_g(const Params &p)
 {
-    Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for
-    const size_t smem = smem_bytes<G>(q);
-    if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(step_group_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return p.N == G ? prepare_gw<G, true, WarpsFor<G>::v>(p) : prepare_gw<G, false, WarpsFor<G>::v>(p);
 }
 
 template <int G>
 cudaError_t launch_g(const Params &p, cudaStream_t stream)
 {
-    const long long envs_per_cta = (long long)WARPS * (32 / G);
-    const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-    step_group_kernel<G><<<(unsigned)grid, WARPS * 32, smem_bytes<G>(p), stream>>>(p);
-    return cudaGetLastError();
+    return p.N == G ? launch_gw<G, true, WarpsFor<G>::v>(p, stream) : launch_gw<G, false, WarpsFor<G>::v>(p, stream);
 }
 
 }  // namespace
@@ -370,10 +427,10 @@ int group_width(int N)
 size_t step_group_smem_bytes(const Params &p)
 {
     switch (group_width(p.N)) {
-    case 4: return smem_bytes<4>(p);
-    case 8: return smem_bytes<8>(p);
-    case 16: return smem_bytes<16>(p);
-    default: return smem_bytes<32>(p);
+    case 4: return smem_bytes<4>(p, WarpsFor<4>::v);
+    case 8: return smem_bytes<8>(p, WarpsFor<8>::v);
+    case 16: return smem_bytes<16>(p, WarpsFor<16>::v);
+    default: return smem_bytes<32>(p, WarpsFor<32>::v);
     }
 }
 
