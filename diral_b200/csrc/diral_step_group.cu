@@ -43,19 +43,19 @@ template <> struct Log2<8>  { static constexpr int v = 3; };
 template <> struct Log2<16> { static constexpr int v = 4; };
 template <> struct Log2<32> { static constexpr int v = 5; };
 
-__host__ __device__ inline int align8i(int x) { return (x + 7) & ~7; }
+__host__ __device__ inline int align16i(int x) { return (x + 15) & ~15; }
 
 // shared-memory carve-up of one group (bytes); the host computes the same numbers
 struct GroupSmem {
     int off_sx, off_sy, off_obs, off_hist, off_st, bytes;
-    __host__ __device__ GroupSmem(int G, int Rp, int B, int Sp, bool state, bool vpd)
+    __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd)
     {
         int o = 0;
-        off_sx = o;   o += 8 * G;
-        off_sy = o;   o += 8 * G;
-        off_obs = o;  o += align8i(4 * G * Rp);
-        off_hist = o; o += (state && vpd) ? align8i(4 * G * B) : 0;
-        off_st = o;   o += state ? align8i(4 * G * Sp) : 0;
+        off_sx = o;   o += align16i(8 * G);
+        off_sy = o;   o += align16i(8 * G);
+        off_obs = o;  o += align16i(4 * G * R);
+        off_hist = o; o += (state && vpd) ? align16i(4 * G * B) : 0;
+        off_st = o;   o += state ? align16i(4 * G * S) : 0;
         bytes = o;
     }
 };
@@ -95,7 +95,24 @@ __device__ __noinline__ int reward_weight(const Params &p, bool flat, const doub
     return p.toy ? (m == norm) : (m > p.C);
 }
 
-template <int G, bool FULL, int WARPS>
+// exact bin of a sample against the linspace edges -- only reached within 1e-6 of a bin boundary
+__device__ __noinline__ int vpd_bin_edges(double s, double W, double inv_binw, int B, const double *edges)
+{
+    return vpd_bin(s, W, inv_binw, B, edges);
+}
+
+// numpy.histogram bin of s, |s| < W.  t = (s + W) * B / 2W is a few ulp from the real-valued bin
+// coordinate, so whenever t is not within 1e-6 of an integer, trunc(t) IS the bin NumPy's
+// edge-corrected search returns; the rare boundary case compares against the edges themselves.
+__device__ __forceinline__ int vpd_bin_fast(double s, double W, double inv_binw, int B, const double *edges)
+{
+    const double t = __dmul_rn(__dadd_rn(s, W), inv_binw);
+    const double r = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);   // rint(t)
+    if (fabs(__dsub_rn(t, r)) < 1e-6) return vpd_bin_edges(s, W, inv_binw, B, edges);
+    return (int)t;
+}
+
+template <int G, bool FULL, int WARPS, int MODE, bool LAT>
 __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
 {
     constexpr int EPW = 32 / G;              // environments per warp
@@ -105,7 +122,7 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
     const long long e = ((long long)blockIdx.x * WARPS + warp) * EPW + sub;
     const int N = FULL ? G : p.N;
-    const int R = p.R, B = p.B;
+    const int R = p.R, B = p.B, S = p.S;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_edges = reinterpret_cast<double *>(smem_raw);
@@ -115,13 +132,13 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
 
     const bool want_state = p.build_state != 0;
     const bool vpd = want_state && p.vpd_enabled;
-    const GroupSmem lay(G, p.Rp, B, p.Sp, want_state, p.vpd_enabled);
-    unsigned char *gbase = smem_raw + align8i(8 * (B + 1)) + (size_t)(warp * EPW + sub) * lay.bytes;
+    const GroupSmem lay(G, R, B, S, want_state, p.vpd_enabled);
+    unsigned char *gbase = smem_raw + align16i(8 * (B + 1)) + (size_t)(warp * EPW + sub) * lay.bytes;
     double *sx = reinterpret_cast<double *>(gbase + lay.off_sx);
     double *sy = reinterpret_cast<double *>(gbase + lay.off_sy);
-    float *obsS = reinterpret_cast<float *>(gbase + lay.off_obs);
+    float *obsS = reinterpret_cast<float *>(gbase + lay.off_obs);      // [N][R], same layout as global
     unsigned *hist = reinterpret_cast<unsigned *>(gbase + lay.off_hist);
-    float *st = reinterpret_cast<float *>(gbase + lay.off_st);
+    float *st = reinterpret_cast<float *>(gbase + lay.off_st);         // [N][S], rows rotated (see F)
 
     const bool act = FULL ? true : (u < N);
     const long long vbase = e * N;           // first vehicle of this env in the [E][N] arrays
@@ -139,8 +156,8 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
 
     // ---- A/B: seq columns -> packed keys in registers, with the tick applied --------------------
     unsigned key[G];
-    const int32_t *seq_in = p.tab_seq + tbase + u;       // column j of this lane: seq_in[j * N]
     if (p.piggy) {
+        const int32_t *seq_in = p.tab_seq + tbase + u;   // column j of this lane: seq_in[j * N]
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             int s = 0;
@@ -160,7 +177,7 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
 
     // toy reward: distance between the first-min-x and first-max-x vehicle (network.py:225-246)
     double norm = 0.0;
-    if (p.toy && p.mode == MODE_STEP) {
+    if (MODE == MODE_STEP && p.toy) {
         double xmin = act ? x : INFINITY, xmax = act ? x : -INFINITY; int imin = u, imax = u;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
@@ -175,9 +192,12 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     // ---- C: resources in ascending order ---------------------------------------------------------
     double rew = 0.0;
     int n_recv = 0, n_pairs = 0;
-    int32_t *latp = p.track_lat ? p.lat + tbase + u : nullptr;       // lat[t][u] = latp[t * N]
-    const bool merge_mode = p.piggy && (p.mode != MODE_STEP || p.state_type == 1 || p.state_type == 2);
-    float *obs_row = obsS + u * p.Rp;
+    int my_tot = 1, my_w = 0, my_inr = 0, my_recv = 0;
+    int32_t *latp = LAT ? p.lat + tbase + u : nullptr;               // lat[t][u] = latp[t * N]
+    const bool merge_mode = p.piggy && (MODE != MODE_STEP || p.state_type == 1 || p.state_type == 2);
+    const bool weighted = MODE == MODE_STEP && (p.reward_design == 1 || p.reward_design == 2 || p.reward_design == 5);
+    const double Cr = p.C, sentinel = p.sentinel;
+    float *obs_row = obsS + u * R;
 
     for (int r = 0; r < R; ++r) {
         const unsigned txm = (__ballot_sync(gmask, a == r) & gmask) >> (sub * G);   // collision histogram
@@ -187,45 +207,39 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
         const bool is_rx = act && !is_tx;
 
         // nearest in-range transmitter, ascending id, strict '<' (first wins ties)
-        double best = p.sentinel; int tstar = -1, my_inr = 0;
+        double best = sentinel; int tstar = -1;
         for (unsigned m = txm; m; m &= m - 1) {
             const int t = __ffs(m) - 1;
             const double d = dist_uni(flat, sx[t], sy[t], x, y);
-            const bool inr = is_rx && d < p.C;
+            const bool inr = is_rx && d < Cr;
             if (inr) { ++n_pairs; if (d < best) { best = d; tstar = t; } }
-            else if (latp && is_rx) latp[t * N] = -1;                                // network.py:394
-            if (p.mode == MODE_CH && tot > 1) {
+            if (LAT) { if (is_rx && !inr) latp[t * N] = -1; }                        // network.py:394
+            if (MODE == MODE_CH && tot > 1) {
                 const unsigned bm = __ballot_sync(gmask, inr);
                 if (u == t) my_inr = __popc(bm);
             }
         }
         if (tstar >= 0) ++n_recv;
+        if (is_tx) my_tot = tot;
 
-        // rewards for the transmitters on r
-        if (p.mode == MODE_STEP) {
-            double rr = 1.0;
-            if (tot > 1) {
-                int w = 0;
-                if (design_needs_weight(p.reward_design, tot)) w = reward_weight(p, flat, sx, sy, txm, norm);
-                rr = collision_reward_step(p.reward_design, tot, w);
+        // what the reward of the transmitters on r needs (the reward itself is formed after the loop)
+        if (MODE == MODE_STEP) {
+            if (weighted && tot > 1 && design_needs_weight(p.reward_design, tot)) {
+                const int w = reward_weight(p, flat, sx, sy, txm, norm);
+                if (is_tx) my_w = w;
             }
-            if (is_tx) rew = rr;
-        } else if (p.mode == MODE_DESIGN) {
-            if (is_tx) {
-                if (tot == 1) rew = 1.0;
-                else {   // TestEnv.calculate_reward_design (test_env.py:319-349)
-                    int k = 1, last = u;
-                    for (unsigned m = txm; m; m &= m - 1) {
-                        const int t = __ffs(m) - 1;
-                        if (t != u && dist_uni(flat, x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
-                    }
-                    if (k == 1) rew = 1.0;
-                    else if (k == 2) rew = (dist_uni(flat, x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
-                    else rew = -(double)k;
+        } else if (MODE == MODE_DESIGN) {
+            if (is_tx && tot > 1) {   // TestEnv.calculate_reward_design (test_env.py:319-349)
+                int k = 1, last = u;
+                for (unsigned m = txm; m; m &= m - 1) {
+                    const int t = __ffs(m) - 1;
+                    if (t != u && dist_uni(flat, x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
                 }
+                if (k == 1) rew = 1.0;
+                else if (k == 2) rew = (dist_uni(flat, x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
+                else rew = -(double)k;
             }
         } else {
-            int my_recv = 0;
             if (tot > 1) {
                 for (unsigned m = txm; m; m &= m - 1) {
                     const int t = __ffs(m) - 1;
@@ -233,15 +247,14 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
                     if (u == t) my_recv = __popc(bm);
                 }
             }
-            if (is_tx) rew = channel_reward(p.reward_design, tot, my_recv, my_inr);
-            if (tstar >= 0 && latp) latp[tstar * N] = (int32_t)p.timestep;           // test_env.py:436
+            if (LAT) { if (tstar >= 0) latp[tstar * N] = (int32_t)p.timestep; }      // test_env.py:436
         }
 
         // channel observation (test_env.py:203-240 / :305-306 / :431)
         {
             float o = 0.0f;
             if (!is_tx) {
-                if (p.mode == MODE_STEP) o = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
+                if (MODE == MODE_STEP) o = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
                 else o = 1.0f;
             }
             obs_row[r] = o;
@@ -255,6 +268,11 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
         }
     }
 
+    // rewards (test_env.py:159-199 / :294-302 / :408-429)
+    if (MODE == MODE_STEP) rew = my_tot == 1 ? 1.0 : collision_reward_step(p.reward_design, my_tot, my_w);
+    else if (MODE == MODE_DESIGN) { if (my_tot == 1) rew = 1.0; }
+    else rew = channel_reward(p.reward_design, my_tot, my_recv, my_inr);
+
     // ---- D: mobility -------------------------------------------------------------------------------
     const double x_new = act ? mobility_step(p, x, v, u) : 0.0;
     if (act && p.mobility) p.pos_x[vbase + u] = x_new;
@@ -265,53 +283,68 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
         for (int k = 0; k < B; ++k) hist[k * G + u] = 0u;
     }
     if (p.piggy) {
+        constexpr int UNR = (G >= 2 * CH) ? 2 * CH : G;      // columns per loop iteration (two stages)
         int32_t *seqp = p.tab_seq + tbase + u, *lup = p.tab_lu + tbase + u;
         double *xp = p.tab_x + tbase + u;
-        int s_buf[2][CH], l_buf[2][CH]; double x_buf[2][CH];
-        auto load_chunk = [&](int c, int slot) {
+        const double W = p.W, inv_binw = p.inv_binw;
+        const int age_thr = p.age_threshold;
+        int s_buf[UNR], l_buf[UNR]; double x_buf[UNR];
+        auto load_cols = [&](int q0, int q1, int jbase) {
 #pragma unroll
-            for (int q = 0; q < CH; ++q) {
-                const int j = c * CH + q;
-                if (j < G && (FULL || (j < N && act))) {
-                    s_buf[slot][q] = seqp[j * N]; l_buf[slot][q] = lup[j * N]; x_buf[slot][q] = xp[j * N];
-                } else { s_buf[slot][q] = 0; l_buf[slot][q] = 0; x_buf[slot][q] = 0.0; }
+            for (int q = q0; q < q1; ++q) {
+                const int j = jbase + q;
+                if (FULL || (j < N && act)) { s_buf[q] = seqp[q * N]; l_buf[q] = lup[q * N]; x_buf[q] = xp[q * N]; }
+                else { s_buf[q] = 0; l_buf[q] = 0; x_buf[q] = 0.0; }
             }
         };
-        constexpr int NCH = (G + CH - 1) / CH;
-        load_chunk(0, 0);
+        auto do_cols = [&](int q0, int q1, int jbase) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            if (c + 1 < NCH) load_chunk(c + 1, (c + 1) & 1);
-#pragma unroll
-            for (int q = 0; q < CH; ++q) {
-                const int j = c * CH + q;
-                if (j >= G) continue;
-                int s0 = s_buf[c & 1][q], lu = l_buf[c & 1][q]; double xo = x_buf[c & 1][q];
+            for (int q = q0; q < q1; ++q) {
+                const int j = jbase + q;
+                int s0 = s_buf[q], lu = l_buf[q]; double xo = x_buf[q];
                 if (j == u) { s0 += 1; lu = 0; xo = x; } else lu += 1;       // vehicle.py:58-70 (tick)
-                const int sn = (int)(key[j] >> SB);
+                const int sn = (int)(key[q] >> SB);
                 const bool changed = sn != s0;                     // strictly newer version merged in
-                const int src = changed ? (int)(key[j] & (unsigned)(G - 1)) : u;
+                const int src = changed ? (int)(key[q] & (unsigned)(G - 1)) : u;
                 const double xn = __shfl_sync(gmask, xo, src, G);
                 if (changed) lu = 0;                               // vehicle.py:47
-                if (FULL || (j < N && act)) { seqp[j * N] = sn; lup[j * N] = lu; xp[j * N] = xn; }
-                if (vpd && (FULL || (j < N && act)) && j != u && lu < p.age_threshold) {   // network.py:547
+                const bool live = FULL || (j < N && act);
+                if (live) { seqp[q * N] = sn; lup[q * N] = lu; xp[q * N] = xn; }
+                if (vpd && live && j != u && lu < age_thr) {       // network.py:547
                     double s; bool in;
                     if (flat0) {           // dy == 0: signed distance is exactly xpos - own x
                         s = __dsub_rn(xn, x_new);
-                        in = fabs(s) < p.W;
+                        in = fabs(s) < W;
                     } else {
                         const double y1 = sn > 0 ? sy[j] : 0.0;
                         const double d = dist_uni(false, xn, y1, x_new, y);
-                        in = d < p.W;
+                        in = d < W;
                         s = (__dsub_rn(xn, x_new) > 0.0) ? d : -d;
                     }
                     if (in) {                                      // network.py:487
-                        const int k = vpd_bin(s, p.W, p.inv_binw, B, s_edges);
+                        const int k = vpd_bin_fast(s, W, inv_binw, B, s_edges);
                         hist[k * G + u] += 1u;
                         ++m_cnt;
                     }
                 }
             }
+        };
+        // a rolled loop over UNR-column slabs keeps the body inside the instruction cache; the key
+        // registers rotate down by UNR after each slab so that the body always indexes key[0..UNR)
+#pragma unroll 1
+        for (int jbase = 0; jbase < G; jbase += UNR) {
+            if (UNR >= 2 * CH) {
+                load_cols(0, CH, jbase);
+                load_cols(CH, UNR, jbase);
+                do_cols(0, CH, jbase);
+                do_cols(CH, UNR, jbase);
+            } else {
+                load_cols(0, UNR, jbase);
+                do_cols(0, UNR, jbase);
+            }
+            seqp += UNR * N; lup += UNR * N; xp += UNR * N;
+#pragma unroll
+            for (int j = 0; j + UNR < G; ++j) key[j] = key[j + UNR];
         }
     }
 
@@ -334,44 +367,63 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     if (act) p.rews[vbase + u] = (float)rew;
 
     // ---- F: state rows (TestEnv.obtain_state) in shared memory -----------------------------------
+    // Row u lives at st[u*S .. u*S+S) exactly as in global memory, but rotated by rot(u) words
+    // (a multiple of 4 chosen on the host) so that the 32 lanes' scalar writes of the same column hit
+    // different banks while the read-out can still move aligned float4s.
+    const int rot = p.st_vec ? 4 * (u >> p.st_sh) : 0;
     if (want_state && act) {
-        float *row = st + u * p.Sp;
-        int k = 0;
+        float *row = st + u * S;
+        float *wp = row + rot, *row_end = row + S;
+        auto emit = [&](float val) { *wp = val; if (++wp == row_end) wp = row; };
         if (p.add_action) {
-            if (p.action_binary) { for (int r = 0; r < R; ++r) row[k++] = (a == r) ? 1.0f : 0.0f; }
-            else row[k++] = (float)a;
+            if (p.action_binary) { for (int r = 0; r < R; ++r) emit((a == r) ? 1.0f : 0.0f); }
+            else emit((float)a);
         }
-        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) row[k++] = obs_row[r]; }
+        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) emit(obs_row[r]); }
         if (p.piggy) {
-            const float den = (float)m_cnt;
-            for (int b = 0; b < B; ++b)
-                row[k++] = (vpd && m_cnt > 0) ? __fdiv_rn((float)hist[b * G + u], den) : 0.0f;
+            // counts / len with one correctly rounded reciprocal and two FMAs per bin: exact
+            // (== RN(c / m)) for all 0 <= c <= m < 1024, checked exhaustively (tests/test_host.py)
+            const float den = (float)m_cnt, rcp = __frcp_rn(den);
+            for (int b = 0; b < B; ++b) {
+                float q = 0.0f;
+                if (vpd && m_cnt > 0) {
+                    const float c = (float)hist[b * G + u];
+                    const float q0 = __fmul_rn(c, rcp);
+                    q = __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0);
+                }
+                emit(q);
+            }
         }
-        if (p.add_reward) row[k++] = (float)rew;
-        if (p.add_index) row[k++] = (float)(u + 1);
-        if (p.add_position) { row[k++] = (float)__ddiv_rn(x_new, p.L); row[k++] = (float)__ddiv_rn(y, 2.0); }
-        if (p.add_velocity) row[k++] = (float)v;
-        if (p.fingerprint) { row[k++] = (float)p.episode; row[k++] = (float)p.epsilon; }
+        if (p.add_reward) emit((float)rew);
+        if (p.add_index) emit((float)(u + 1));
+        if (p.add_position) { emit((float)__ddiv_rn(x_new, p.L)); emit((float)__ddiv_rn(y, 2.0)); }
+        if (p.add_velocity) emit((float)v);
+        if (p.fingerprint) { emit((float)p.episode); emit((float)p.epsilon); }
     }
     __syncwarp(gmask);
 
-    // coalesced copy-out of the [N][R] observation block and the [N][S] state block; element idx of
-    // the block sits at row idx / len, found with a 2^32 / len reciprocal (exact for idx < 2^16)
+    // coalesced copy-out of the [N][R] observation block and the [N][S] state block
     {
         float *og = p.obs + vbase * R;
-        const unsigned inv = p.inv_R;
-        for (int idx = u; idx < N * R; idx += G) {
-            const int uu = (int)__umulhi((unsigned)idx, inv);
-            og[idx] = obsS[uu * p.Rp + (idx - uu * R)];
+        const int n = N * R;
+        if ((n & 3) == 0 && (lay.off_obs & 15) == 0) {
+            for (int i = u; i < n / 4; i += G) reinterpret_cast<float4 *>(og)[i] = reinterpret_cast<const float4 *>(obsS)[i];
+        } else {
+            for (int i = u; i < n; i += G) og[i] = obsS[i];
         }
     }
     if (want_state) {
-        const int S = p.S;
         float *sg = p.state + vbase * S;
-        const unsigned inv = p.inv_S;
-        for (int idx = u; idx < N * S; idx += G) {
-            const int uu = (int)__umulhi((unsigned)idx, inv);
-            sg[idx] = st[uu * p.Sp + (idx - uu * S)];
+        if (p.st_vec) {
+            const int S4 = S >> 2;
+            for (int i = u; i < N * S4; i += G) {
+                const int uu = (int)__umulhi((unsigned)i, p.inv_S4);
+                int c = i - uu * S4 + (uu >> p.st_sh);       // undo the row rotation, in float4 units
+                if (c >= S4) c -= S4;
+                reinterpret_cast<float4 *>(sg)[i] = reinterpret_cast<const float4 *>(st)[uu * S4 + c];
+            }
+        } else {
+            for (int i = u; i < N * S; i += G) sg[i] = st[i];
         }
     }
 }
@@ -379,42 +431,61 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
 template <int G>
 size_t smem_bytes(const Params &p, int warps)
 {
-    const GroupSmem lay(G, p.Rp, p.B, p.Sp, p.build_state != 0, p.vpd_enabled != 0);
-    return (size_t)align8i(8 * (p.B + 1)) + (size_t)warps * (32 / G) * lay.bytes;
-}
-
-template <int G, bool FULL, int WARPS>
-cudaError_t prepare_gw(const Params &p)
-{
-    Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for
-    const size_t smem = smem_bytes<G>(q, WARPS);
-    if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(step_group_kernel<G, FULL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-
-template <int G, bool FULL, int WARPS>
-cudaError_t launch_gw(const Params &p, cudaStream_t stream)
-{
-    const long long envs_per_cta = (long long)WARPS * (32 / G);
-    const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-    step_group_kernel<G, FULL, WARPS><<<(unsigned)grid, WARPS * 32, smem_bytes<G>(p, WARPS), stream>>>(p);
-    return cudaGetLastError();
+    const GroupSmem lay(G, p.R, p.B, p.S, p.build_state != 0, p.vpd_enabled != 0);
+    return (size_t)align16i(8 * (p.B + 1)) + (size_t)warps * (32 / G) * lay.bytes;
 }
 
 // one warp per CTA keeps the tail of the last wave short when few groups share a warp (G >= 16);
 // small groups pack 4 warps so that a CTA still carries a useful number of environments
 template <int G> struct WarpsFor { static constexpr int v = G >= 16 ? 1 : 4; };
 
-template <int G>
-cudaError_t prepare_g(const Params &p)
+template <int G, bool FULL, int MODE, bool LAT>
+cudaError_t prepare_k(const Params &p)
 {
-    return p.N == G ? prepare_gw<G, true, WarpsFor<G>::v>(p) : prepare_gw<G, false, WarpsFor<G>::v>(p);
+    Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for
+    const size_t smem = smem_bytes<G>(q, WarpsFor<G>::v);
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int G, bool FULL, int MODE, bool LAT>
+cudaError_t launch_k(const Params &p, cudaStream_t stream)
+{
+    constexpr int W = WarpsFor<G>::v;
+    const long long envs_per_cta = (long long)W * (32 / G);
+    const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
+    step_group_kernel<G, FULL, W, MODE, LAT><<<(unsigned)grid, W * 32, smem_bytes<G>(p, W), stream>>>(p);
+    return cudaGetLastError();
+}
+
+// run `prepare` (launch == false) or `launch` for the instantiation p selects
+template <int G, bool FULL>
+cudaError_t dispatch_mode(const Params &p, cudaStream_t stream, bool launch, int mode, bool lat)
+{
+#define DIRAL_CASE(M, L) return launch ? launch_k<G, FULL, M, L>(p, stream) : prepare_k<G, FULL, M, L>(p)
+    if (mode == MODE_STEP)   { if (lat) DIRAL_CASE(MODE_STEP, true);   DIRAL_CASE(MODE_STEP, false); }
+    if (mode == MODE_DESIGN) { if (lat) DIRAL_CASE(MODE_DESIGN, true); DIRAL_CASE(MODE_DESIGN, false); }
+    if (lat) DIRAL_CASE(MODE_CH, true);
+    DIRAL_CASE(MODE_CH, false);
+#undef DIRAL_CASE
 }
 
 template <int G>
-cudaError_t launch_g(const Params &p, cudaStream_t stream)
+cudaError_t dispatch_g(const Params &p, cudaStream_t stream, bool launch, int mode, bool lat)
 {
-    return p.N == G ? launch_gw<G, true, WarpsFor<G>::v>(p, stream) : launch_gw<G, false, WarpsFor<G>::v>(p, stream);
+    return p.N == G ? dispatch_mode<G, true>(p, stream, launch, mode, lat)
+                    : dispatch_mode<G, false>(p, stream, launch, mode, lat);
+}
+
+cudaError_t dispatch(const Params &p, cudaStream_t stream, bool launch, int mode, bool lat)
+{
+    switch (group_width(p.N)) {
+    case 4: return dispatch_g<4>(p, stream, launch, mode, lat);
+    case 8: return dispatch_g<8>(p, stream, launch, mode, lat);
+    case 16: return dispatch_g<16>(p, stream, launch, mode, lat);
+    default: return dispatch_g<32>(p, stream, launch, mode, lat);
+    }
 }
 
 }  // namespace
@@ -436,22 +507,17 @@ size_t step_group_smem_bytes(const Params &p)
 
 cudaError_t prepare_step_group(const Params &p)
 {
-    switch (group_width(p.N)) {
-    case 4: return prepare_g<4>(p);
-    case 8: return prepare_g<8>(p);
-    case 16: return prepare_g<16>(p);
-    default: return prepare_g<32>(p);
-    }
+    for (int mode = 0; mode < 3; ++mode)
+        for (int lat = 0; lat < 2; ++lat) {
+            cudaError_t err = dispatch(p, nullptr, false, mode, lat != 0);
+            if (err != cudaSuccess) return err;
+        }
+    return cudaSuccess;
 }
 
 cudaError_t launch_step_group(const Params &p, cudaStream_t stream)
 {
-    switch (group_width(p.N)) {
-    case 4: return launch_g<4>(p, stream);
-    case 8: return launch_g<8>(p, stream);
-    case 16: return launch_g<16>(p, stream);
-    default: return launch_g<32>(p, stream);
-    }
+    return dispatch(p, stream, true, p.mode, p.track_lat != 0 && p.lat != nullptr);
 }
 
 }  // namespace diral
