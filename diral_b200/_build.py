@@ -35,7 +35,20 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Compile the library.  `defines` (e.g. ["DIRAL_MIN_BLOCKS=16"]) and `out` build an experimental
+    variant next to the default one (tuning runs select it with DIRAL_ENV_LIB=<path>)."""
+    if defines or out:
+        out = out or LIB.replace(".so", "_" + "_".join(d.replace("=", "") for d in defines) + ".so")
+        cmd = [nvcc()] + NVCC_FLAGS + ["-shared", "-o", out] + ["-D" + d for d in defines] \
+            + [os.path.join(CSRC, s) for s in SOURCES]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(out + ".log", "w") as f:
+            f.write(r.stdout + r.stderr)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed building %s" % out)
+        return out
     os.makedirs(OBJ, exist_ok=True)
     objs = []
     for src in SOURCES:

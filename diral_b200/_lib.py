@@ -83,7 +83,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("DIRAL_ENV_LIB") or _build.LIB      # DIRAL_ENV_LIB: tuning variants only
     if not os.path.exists(path):
         path = _build.build()            # raises when nvcc is absent: no fallback exists
     lib = C.CDLL(path)

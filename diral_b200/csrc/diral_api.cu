@@ -129,6 +129,7 @@ void fill_base(Handle *h)
     p.add_positional_dist = c.add_positional_dist != 0; p.pos_dist_type = c.pos_dist_type;
     p.fingerprint = c.fingerprint != 0;
     p.vpd_enabled = p.piggy && (p.mobility || p.design_topology);
+    p.fast_nearest = c.C <= c.sentinel;
     p.edges = h->d_edges;
 }
 

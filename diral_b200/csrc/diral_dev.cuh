@@ -35,6 +35,7 @@ struct Params {
     int add_action, action_binary, add_channel_obs, add_reward, add_index, add_velocity, add_position,
         add_positional_dist, pos_dist_type, fingerprint;
     int vpd_enabled;          // piggy && (mobility || design_topology)  (network.py:545)
+    int fast_nearest;         // C <= sentinel: a lone in-range transmitter is the nearest without comparing
     // per-call
     int mode, track_lat, build_state, gen_actions;
     long long timestep;

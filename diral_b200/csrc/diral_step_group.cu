@@ -1,30 +1,34 @@
 // diral_step_group.cu -- fused time-slot kernel for N <= 32 vehicles per environment.
 //
 // One group of G lanes (G = 4, 8, 16 or 32, the power of two >= N) owns one environment; lane u is
-// vehicle u both as a receiver and as the owner of row u of the neighbour table.  A slot is
+// vehicle u both as a receiver and as the owner of row u of the neighbour table.  The slot splits
+// into a DECISION phase that never touches the table and a TABLE phase that streams it once:
 //
-//   A  load actions / kinematics; load the seq column-by-column (subject-major => every load is one
-//      coalesced G*4-byte segment) into REGISTERS as packed keys  (seq << log2 G) | origin-row
-//   B  table tick (Vehicle.periodic_update, reference envs/vehicle.py:56-70)
-//   C  for r = 0..R-1 in order (test_env.py:147 -- a true sequential dependency):
-//        ballot the transmitters on r (the per-resource collision histogram, test_env.py:149-157),
-//        reward model for them, nearest in-range transmitter for every other lane
-//        (Network.find_closest_tx, network.py:378-398), then the table merge
-//        (Vehicle.received_update, vehicle.py:35-47) as ONE shuffle + ONE integer max per column:
-//        key[j] = max(key[j], shfl(key[j], nearest)).  Because (xpos, ypos) of an entry is a pure
-//        function of (subject, seq), the max-by-seq join never has to move positions: the key's low
-//        bits remember which row held that version at the start of the slot.
+//   A  load actions / kinematics and kick off the loads of the first table slab
+//   C1 for r = 0..R-1 in order (reference envs/test_env.py:147): ballot the transmitters on r (the
+//      per-resource collision histogram, test_env.py:149-157), what their reward needs, the nearest
+//      in-range transmitter of every other lane (Network.find_closest_tx, network.py:378-398), channel
+//      observation, last_arrival_time; every pass in which somebody receives appends one row
+//      ts[pass][u] = "lane whose row u merges" to a small shared-memory script
 //   D  mobility (Network.update_positions, network.py:189-206)
-//   E  one streaming pass over the table columns, software-pipelined in chunks of CH columns:
-//      gather xpos from the origin row by shuffle, last_updated bookkeeping, write seq /
-//      last_updated / xpos back (coalesced), and in the same pass accumulate the view-based
-//      positional distribution histogram (Network.get_positional_dist_2_piggy + dist_piggy,
-//      network.py:473-513,538-558)
+//   C2/E per slab of 8 table columns (subject-major storage => every access is one coalesced G*4 or
+//      G*8 byte segment; the next slab's loads are in flight while this one computes):
+//        tick (Vehicle.periodic_update, vehicle.py:56-70) and pack  key = seq << log2 G | origin-row
+//        replay the script IN PASS ORDER -- the passes are a true sequential dependency (SURVEY.md
+//        2b), but table COLUMNS are independent, so a slab can run all passes by itself:
+//            key[q] = max(key[q], shfl(key[q], ts[pass][u]))            (Vehicle.received_update,
+//        vehicle.py:35-47: one shuffle + one integer max per entry).  (xpos, ypos) of an entry is a
+//        pure function of (subject, seq), so the max-by-seq join never moves positions: the key's low
+//        bits remember which row held that version when the slot began.
+//        then gather xpos from the origin row by shuffle, last_updated bookkeeping, write
+//        seq / last_updated / xpos back, and bin the view-based positional distribution
+//        (Network.get_positional_dist_2_piggy + dist_piggy, network.py:473-513,538-558)
 //   F  TestEnv.obtain_state (test_env.py:527-583): assemble [E][N][S] float32 rows in shared memory
-//      and write obs / rewards / state with coalesced stores.
+//      and write obs / rewards / state with coalesced float4 stores.
 //
 // HBM traffic per env-slot is the algorithmic minimum SURVEY.md 8(d) states: the table is read once
-// and written once (16 B per entry each way), everything else is O(N).
+// and written once (16 B per entry each way), everything else is O(N).  Only one slab of keys lives
+// in registers at a time, which is what lets ~20 warps stay resident per SM.
 //
 // FULL (N == G) instantiations drop every "is this lane / column live" predicate and turn all
 // table addresses into compile-time offsets from one base pointer.
@@ -34,8 +38,6 @@
 namespace diral {
 
 namespace {
-
-constexpr int CH = 8;                    // table columns per software-pipeline stage
 
 template <int G> struct Log2;
 template <> struct Log2<4>  { static constexpr int v = 2; };
@@ -47,10 +49,11 @@ __host__ __device__ inline int align16i(int x) { return (x + 15) & ~15; }
 
 // shared-memory carve-up of one group (bytes); the host computes the same numbers
 struct GroupSmem {
-    int off_sx, off_sy, off_obs, off_hist, off_st, bytes;
+    int off_sx, off_sy, off_script, off_obs, off_hist, off_st, bytes;
     __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd)
     {
         int o = 0;
+        off_script = o; o += align16i(G * R);          // merge script: one byte per (pass, lane)
         off_sx = o;   o += align16i(8 * G);
         off_sy = o;   o += align16i(8 * G);
         off_obs = o;  o += align16i(4 * G * R);
@@ -101,19 +104,13 @@ __device__ __noinline__ int vpd_bin_edges(double s, double W, double inv_binw, i
     return vpd_bin(s, W, inv_binw, B, edges);
 }
 
-// numpy.histogram bin of s, |s| < W.  t = (s + W) * B / 2W is a few ulp from the real-valued bin
-// coordinate, so whenever t is not within 1e-6 of an integer, trunc(t) IS the bin NumPy's
-// edge-corrected search returns; the rare boundary case compares against the edges themselves.
-__device__ __forceinline__ int vpd_bin_fast(double s, double W, double inv_binw, int B, const double *edges)
-{
-    const double t = __dmul_rn(__dadd_rn(s, W), inv_binw);
-    const double r = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);   // rint(t)
-    if (fabs(__dsub_rn(t, r)) < 1e-6) return vpd_bin_edges(s, W, inv_binw, B, edges);
-    return (int)t;
-}
+#ifndef DIRAL_MIN_BLOCKS
+#define DIRAL_MIN_BLOCKS 1
+#endif
 
 template <int G, bool FULL, int WARPS, int MODE, bool LAT>
-__global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 1 ? DIRAL_MIN_BLOCKS : 1))
+step_group_kernel(const Params p)
 {
     constexpr int EPW = 32 / G;              // environments per warp
     constexpr int SB = Log2<G>::v;           // low key bits holding the origin row
@@ -137,6 +134,7 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     double *sx = reinterpret_cast<double *>(gbase + lay.off_sx);
     double *sy = reinterpret_cast<double *>(gbase + lay.off_sy);
     float *obsS = reinterpret_cast<float *>(gbase + lay.off_obs);      // [N][R], same layout as global
+    unsigned char *script = gbase + lay.off_script;                    // [passes][G]
     unsigned *hist = reinterpret_cast<unsigned *>(gbase + lay.off_hist);
     float *st = reinterpret_cast<float *>(gbase + lay.off_st);         // [N][S], rows rotated (see F)
 
@@ -154,21 +152,29 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     }
     sx[u] = x; sy[u] = y;
 
-    // ---- A/B: seq columns -> packed keys in registers, with the tick applied --------------------
-    unsigned key[G];
+    // ---- table slabs: SL columns at a time --------------------------------------------------------------
+    constexpr int SL = G < 8 ? G : 8;        // columns per slab
+    constexpr int NSL = G / SL;              // slabs per table
+    int32_t *seqp = p.tab_seq + tbase + u, *lup = p.tab_lu + tbase + u;   // column j of this lane: [j * N]
+    double *xp = p.tab_x + tbase + u;
     if (p.piggy) {
-        const int32_t *seq_in = p.tab_seq + tbase + u;   // column j of this lane: seq_in[j * N]
-#pragma unroll
-        for (int j = 0; j < G; ++j) {
-            int s = 0;
-            if (FULL || (j < N && act)) s = seq_in[j * N];
-            if (j == u) s += 1;                                  // vehicle.py:58
-            key[j] = ((unsigned)s << SB) | (unsigned)u;
+        // pull this environment's whole table (16 * N * N bytes, contiguous per array) from HBM into L2
+        // now; the decision phase below runs while it arrives and the slab loads then hit L2
+        const char *b0 = reinterpret_cast<const char *>(p.tab_seq + tbase);
+        const char *b1 = reinterpret_cast<const char *>(p.tab_lu + tbase);
+        const char *b2 = reinterpret_cast<const char *>(p.tab_x + tbase);
+        const int bytes4 = N * N * 4;
+        for (int o = u * 128; o < bytes4; o += G * 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + bytes4 + o));
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < G; ++j) key[j] = 0u;
     }
+    int s_next[SL];                          // seq column of the upcoming slab (loaded one slab ahead)
+#pragma unroll
+    for (int q = 0; q < SL; ++q) s_next[q] = (p.piggy && (FULL || (q < N && act))) ? seqp[q * N] : 0;
+
     // every vehicle on the same lane of the highway (dy == 0 for every pair)?  warp-uniform per group
     const double y0 = __shfl_sync(gmask, y, 0, G);
     const bool flat = (__ballot_sync(gmask, act && y != y0) & gmask) == 0u;
@@ -198,6 +204,15 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     const bool weighted = MODE == MODE_STEP && (p.reward_design == 1 || p.reward_design == 2 || p.reward_design == 5);
     const double Cr = p.C, sentinel = p.sentinel;
     float *obs_row = obsS + u * R;
+    int npass = 0;                           // passes with at least one reception (group-uniform)
+
+    // who is within communication range of this vehicle (network.py:595-607), all G candidates at once
+    unsigned inr_mask = 0u;
+#pragma unroll
+    for (int t = 0; t < G; ++t) {
+        const double d = dist_uni(flat, sx[t], sy[t], x, y);
+        if (d < Cr) inr_mask |= 1u << t;
+    }
 
     for (int r = 0; r < R; ++r) {
         const unsigned txm = (__ballot_sync(gmask, a == r) & gmask) >> (sub * G);   // collision histogram
@@ -206,16 +221,35 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
         const bool is_tx = (a == r);
         const bool is_rx = act && !is_tx;
 
-        // nearest in-range transmitter, ascending id, strict '<' (first wins ties)
-        double best = sentinel; int tstar = -1;
-        for (unsigned m = txm; m; m &= m - 1) {
-            const int t = __ffs(m) - 1;
-            const double d = dist_uni(flat, sx[t], sy[t], x, y);
-            const bool inr = is_rx && d < Cr;
-            if (inr) { ++n_pairs; if (d < best) { best = d; tstar = t; } }
-            if (LAT) { if (is_rx && !inr) latp[t * N] = -1; }                        // network.py:394
-            if (MODE == MODE_CH && tot > 1) {
-                const unsigned bm = __ballot_sync(gmask, inr);
+        // nearest in-range transmitter (Network.find_closest_tx): the candidates are the bits of the
+        // precomputed in-range mask among the transmitters; with one candidate there is nothing to
+        // compare, otherwise scan them in ascending id with strict '<' (first wins ties)
+        const unsigned cand = is_rx ? (inr_mask & txm) : 0u;
+        n_pairs += __popc(cand);
+        int tstar = cand ? (__ffs(cand) - 1) : -1;
+        double best = sentinel;
+        if (!p.fast_nearest || (tot > 1 && __ballot_sync(gmask, (cand & (cand - 1)) != 0u) != 0u)) {
+            tstar = -1;
+            for (unsigned m = txm; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                const double d = dist_uni(flat, sx[t], sy[t], x, y);
+                if (((cand >> t) & 1u) && d < best) { best = d; tstar = t; }
+            }
+        } else if (MODE == MODE_STEP && p.state_type == 2) {
+            const int ts = max(tstar, 0);
+            const double d = dist_uni(flat, sx[ts], sy[ts], x, y);
+            if (tstar >= 0) best = d;
+        }
+        if (LAT) {                                                                    // network.py:394
+            for (unsigned m = txm; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                if (is_rx && !((inr_mask >> t) & 1u)) latp[t * N] = -1;
+            }
+        }
+        if (MODE == MODE_CH && tot > 1) {
+            for (unsigned m = txm; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                const unsigned bm = __ballot_sync(gmask, (cand >> t) & 1u);
                 if (u == t) my_inr = __popc(bm);
             }
         }
@@ -225,7 +259,12 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
         // what the reward of the transmitters on r needs (the reward itself is formed after the loop)
         if (MODE == MODE_STEP) {
             if (weighted && tot > 1 && design_needs_weight(p.reward_design, tot)) {
-                const int w = reward_weight(p, flat, sx, sy, txm, norm);
+                int w;
+                if (tot == 2) {      // one pair: the mean is that pair's distance (sum([d]) / 1 == d)
+                    const int t1 = __ffs(txm) - 1, t2 = __ffs(txm & (txm - 1)) - 1;
+                    const double m = dist_uni(flat, sx[t1], sy[t1], sx[t2], sy[t2]);
+                    w = p.toy ? (m == norm) : (m > Cr);
+                } else w = reward_weight(p, flat, sx, sy, txm, norm);
                 if (is_tx) my_w = w;
             }
         } else if (MODE == MODE_DESIGN) {
@@ -260,11 +299,10 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
             obs_row[r] = o;
         }
 
-        // table merge: row u <- row u JOIN row tstar, all G receivers at once, one column per step
+        // table merge (vehicle.py:35-47) is deferred: log which row this lane merges in this pass
         if (merge_mode && __ballot_sync(gmask, tstar >= 0) != 0u) {
-            const int srcl = tstar >= 0 ? tstar : u;
-#pragma unroll
-            for (int j = 0; j < G; ++j) key[j] = max(key[j], __shfl_sync(gmask, key[j], srcl, G));
+            script[npass * G + u] = (unsigned char)(tstar >= 0 ? tstar : u);
+            ++npass;
         }
     }
 
@@ -277,75 +315,101 @@ __global__ void __launch_bounds__(WARPS * 32) step_group_kernel(const Params p)
     const double x_new = act ? mobility_step(p, x, v, u) : 0.0;
     if (act && p.mobility) p.pos_x[vbase + u] = x_new;
 
-    // ---- E: stream the table columns: gather xpos, age, write back, VPD histogram -----------------
+    // ---- C2/E: per slab -- tick, replay the merge script, gather xpos, age, write back, VPD ---------
     int m_cnt = 0;
     if (vpd) {
         for (int k = 0; k < B; ++k) hist[k * G + u] = 0u;
     }
-    if (p.piggy) {
-        constexpr int UNR = (G >= 2 * CH) ? 2 * CH : G;      // columns per loop iteration (two stages)
-        int32_t *seqp = p.tab_seq + tbase + u, *lup = p.tab_lu + tbase + u;
-        double *xp = p.tab_x + tbase + u;
-        const double W = p.W, inv_binw = p.inv_binw;
-        const int age_thr = p.age_threshold;
-        int s_buf[UNR], l_buf[UNR]; double x_buf[UNR];
-        auto load_cols = [&](int q0, int q1, int jbase) {
+    __syncwarp(gmask);                       // script rows written by every lane are read by its own lane only,
+                                             // but the histogram zeroing above must precede the slab updates
+    const double W = p.W, inv_binw = p.inv_binw;
+    const int age_thr = p.age_threshold;
+    auto do_slab = [&](int jbase) {
+        // loads first: last_updated / xpos of this slab are consumed only after the replay loop, and
+        // the NEXT slab's seq column is requested now, so neither latency is exposed
+        int sb[SL], lb[SL]; double xb[SL];
 #pragma unroll
-            for (int q = q0; q < q1; ++q) {
-                const int j = jbase + q;
-                if (FULL || (j < N && act)) { s_buf[q] = seqp[q * N]; l_buf[q] = lup[q * N]; x_buf[q] = xp[q * N]; }
-                else { s_buf[q] = 0; l_buf[q] = 0; x_buf[q] = 0.0; }
+        for (int q = 0; q < SL; ++q) {
+            const int j = jbase + q;
+            sb[q] = s_next[q];
+            if (FULL || (j < N && act)) { lb[q] = lup[j * N]; xb[q] = xp[j * N]; }
+            else { lb[q] = 0; xb[q] = 0.0; }
+        }
+        if (jbase + SL < G) {
+#pragma unroll
+            for (int q = 0; q < SL; ++q) {
+                const int j = jbase + SL + q;
+                s_next[q] = (FULL || (j < N && act)) ? seqp[j * N] : 0;
             }
-        };
-        auto do_cols = [&](int q0, int q1, int jbase) {
+        }
+        unsigned key[SL];
 #pragma unroll
-            for (int q = q0; q < q1; ++q) {
+        for (int q = 0; q < SL; ++q) {
+            if (jbase + q == u) sb[q] += 1;                                       // vehicle.py:58 (tick)
+            key[q] = ((unsigned)sb[q] << SB) | (unsigned)u;
+        }
+        // replay the passes in order on this slab's columns
+        for (int pp = 0; pp < npass; ++pp) {
+            const int srcl = script[pp * G + u];
+#pragma unroll
+            for (int q = 0; q < SL; ++q) key[q] = max(key[q], __shfl_sync(gmask, key[q], srcl, G));
+        }
+        // gather xpos from the origin row, age, write back (independent per column => ILP)
+#pragma unroll
+        for (int q = 0; q < SL; ++q) {
+            if (jbase + q == u) { lb[q] = 0; xb[q] = x; } else lb[q] += 1;        // vehicle.py:59-70 (tick)
+            const int sn = (int)(key[q] >> SB);
+            const bool changed = sn != sb[q];                  // strictly newer version merged in
+            const int src = changed ? (int)(key[q] & (unsigned)(G - 1)) : u;
+            xb[q] = __shfl_sync(gmask, xb[q], src, G);
+            if (changed) lb[q] = 0;                            // vehicle.py:47
+            sb[q] = sn;
+        }
+#pragma unroll
+        for (int q = 0; q < SL; ++q) {
+            const int j = jbase + q;
+            if (FULL || (j < N && act)) { seqp[j * N] = sb[q]; lup[j * N] = lb[q]; xp[j * N] = xb[q]; }
+        }
+        if (vpd) {
+            unsigned fix = 0u;
+#pragma unroll
+            for (int q = 0; q < SL; ++q) {
                 const int j = jbase + q;
-                int s0 = s_buf[q], lu = l_buf[q]; double xo = x_buf[q];
-                if (j == u) { s0 += 1; lu = 0; xo = x; } else lu += 1;       // vehicle.py:58-70 (tick)
-                const int sn = (int)(key[q] >> SB);
-                const bool changed = sn != s0;                     // strictly newer version merged in
-                const int src = changed ? (int)(key[q] & (unsigned)(G - 1)) : u;
-                const double xn = __shfl_sync(gmask, xo, src, G);
-                if (changed) lu = 0;                               // vehicle.py:47
-                const bool live = FULL || (j < N && act);
-                if (live) { seqp[q * N] = sn; lup[q * N] = lu; xp[q * N] = xn; }
-                if (vpd && live && j != u && lu < age_thr) {       // network.py:547
-                    double s; bool in;
-                    if (flat0) {           // dy == 0: signed distance is exactly xpos - own x
-                        s = __dsub_rn(xn, x_new);
-                        in = fabs(s) < W;
-                    } else {
-                        const double y1 = sn > 0 ? sy[j] : 0.0;
-                        const double d = dist_uni(false, xn, y1, x_new, y);
-                        in = d < W;
-                        s = (__dsub_rn(xn, x_new) > 0.0) ? d : -d;
-                    }
-                    if (in) {                                      // network.py:487
-                        const int k = vpd_bin_fast(s, W, inv_binw, B, s_edges);
-                        hist[k * G + u] += 1u;
-                        ++m_cnt;
-                    }
+                const bool ok = (FULL || (j < N && act)) && j != u && lb[q] < age_thr;   // network.py:547
+                double sv; bool in;
+                if (flat0) {           // dy == 0: signed distance is exactly xpos - own x
+                    sv = __dsub_rn(xb[q], x_new);
+                    in = ok && fabs(sv) < W;                                    // network.py:487
+                } else {
+                    const double y1 = sb[q] > 0 ? sy[j] : 0.0;
+                    const double d = dist_uni(false, xb[q], y1, x_new, y);
+                    in = ok && d < W;
+                    sv = (__dsub_rn(xb[q], x_new) > 0.0) ? d : -d;
+                }
+                // numpy.histogram bin (network.py:500): t is a few ulp from the real-valued bin
+                // coordinate, so trunc(t) is NumPy's edge-corrected bin unless t sits within 1e-6
+                // of an integer; those (rare) samples are re-binned against the edges below
+                const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
+                const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
+                if (in) {
+                    const int kb = min(max((int)t, 0), B - 1);
+                    if (fabs(__dsub_rn(t, rt)) < 1e-6) {
+                        fix |= 1u << q;
+                        xb[q] = sv;                            // keep the sample for the exact re-binning
+                    } else hist[kb * G + u] += 1u;
+                    ++m_cnt;
                 }
             }
-        };
-        // a rolled loop over UNR-column slabs keeps the body inside the instruction cache; the key
-        // registers rotate down by UNR after each slab so that the body always indexes key[0..UNR)
-#pragma unroll 1
-        for (int jbase = 0; jbase < G; jbase += UNR) {
-            if (UNR >= 2 * CH) {
-                load_cols(0, CH, jbase);
-                load_cols(CH, UNR, jbase);
-                do_cols(0, CH, jbase);
-                do_cols(CH, UNR, jbase);
-            } else {
-                load_cols(0, UNR, jbase);
-                do_cols(0, UNR, jbase);
-            }
-            seqp += UNR * N; lup += UNR * N; xp += UNR * N;
+            if (fix) {
 #pragma unroll
-            for (int j = 0; j + UNR < G; ++j) key[j] = key[j + UNR];
+                for (int q = 0; q < SL; ++q)
+                    if ((fix >> q) & 1u) hist[vpd_bin_edges(xb[q], W, inv_binw, B, s_edges) * G + u] += 1u;
+            }
         }
+    };
+    if (p.piggy) {
+#pragma unroll 1
+        for (int jbase = 0; jbase < G; jbase += SL) do_slab(jbase);
     }
 
     // ---- per-env metric accumulators -------------------------------------------------------------
