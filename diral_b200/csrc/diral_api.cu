@@ -103,21 +103,6 @@ void fill_base(Handle *h)
     diral::Params &p = h->base;
     p = diral::Params{};
     p.E = c.E; p.env0 = c.env0; p.N = c.N; p.R = c.R; p.B = c.B; p.S = state_space(c);
-    p.st_vec = (p.S % 4 == 0) ? 1 : 0; p.st_sh = 0; p.inv_S4 = 0;
-    if (p.st_vec) {
-        // pick the row rotation 4 * (u >> sh) that spreads the 32 lanes' same-column scalar writes
-        // over the most shared-memory banks (and never rotates past the row)
-        const int S4 = p.S / 4;
-        p.inv_S4 = (unsigned)(((1ull << 32) + S4 - 1) / S4);
-        int best = -1, best_sh = 5;
-        for (int sh = 0; sh <= 5; ++sh) {
-            if ((31 >> sh) >= S4) continue;
-            unsigned hit[32] = {0}; int worst = 0;
-            for (int u = 0; u < 32; ++u) { int b = (u * p.S + 4 * (u >> sh)) & 31; worst = ++hit[b] > (unsigned)worst ? (int)hit[b] : worst; }
-            if (best < 0 || worst < best) { best = worst; best_sh = sh; }
-        }
-        p.st_sh = best_sh;
-    }
     p.L = c.L; p.C = c.C; p.C2 = 2 * c.C; p.W = c.W; p.sentinel = c.sentinel;
     p.inv_binw = (double)c.B / (2.0 * c.W);
     p.age_threshold = c.age_threshold;

@@ -25,8 +25,6 @@ struct Params {
     // sizes
     long long E, env0;
     int N, R, B, S;
-    unsigned inv_S4;          // ceil(2^32 / (S/4)): row = umulhi(idx, inv) for idx * len < 2^32
-    int st_vec, st_sh;        // state rows move as float4 (S % 4 == 0); row u is rotated by 4 * (u >> st_sh) words
     // geometry
     double L, C, C2, W, sentinel, inv_binw;
     int age_threshold;

@@ -49,11 +49,13 @@ __host__ __device__ inline int align16i(int x) { return (x + 15) & ~15; }
 
 // shared-memory carve-up of one group (bytes); the host computes the same numbers
 struct GroupSmem {
-    int off_sx, off_sy, off_script, off_obs, off_hist, off_st, bytes;
+    int off_sx, off_sy, off_script, off_txm, off_recv, off_obs, off_hist, off_st, bytes;
     __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd)
     {
         int o = 0;
         off_script = o; o += align16i(G * R);          // merge script: one byte per (pass, lane)
+        off_txm = o;    o += align16i(4 * R);          // transmitter mask of every resource
+        off_recv = o;   o += align16i(4 * G);          // packets received per transmitter (my_step_ch)
         off_sx = o;   o += align16i(8 * G);
         off_sy = o;   o += align16i(8 * G);
         off_obs = o;  o += align16i(4 * G * R);
@@ -98,6 +100,12 @@ __device__ __noinline__ int reward_weight(const Params &p, bool flat, const doub
     return p.toy ? (m == norm) : (m > p.C);
 }
 
+// hist[..] += 1 in shared memory without waiting for (or depending on) the old value
+__device__ __forceinline__ void smem_red_inc(unsigned *addr)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(addr)) : "memory");
+}
+
 // exact bin of a sample against the linspace edges -- only reached within 1e-6 of a bin boundary
 __device__ __noinline__ int vpd_bin_edges(double s, double W, double inv_binw, int B, const double *edges)
 {
@@ -135,6 +143,8 @@ step_group_kernel(const Params p)
     double *sy = reinterpret_cast<double *>(gbase + lay.off_sy);
     float *obsS = reinterpret_cast<float *>(gbase + lay.off_obs);      // [N][R], same layout as global
     unsigned char *script = gbase + lay.off_script;                    // [passes][G]
+    unsigned *txm_s = reinterpret_cast<unsigned *>(gbase + lay.off_txm);
+    unsigned *recv_s = reinterpret_cast<unsigned *>(gbase + lay.off_recv);
     unsigned *hist = reinterpret_cast<unsigned *>(gbase + lay.off_hist);
     float *st = reinterpret_cast<float *>(gbase + lay.off_st);         // [N][S], rows rotated (see F)
 
@@ -195,16 +205,14 @@ step_group_kernel(const Params p)
         norm = dist_uni(flat, sx[imin], sy[imin], sx[imax], sy[imax]);
     }
 
-    // ---- C: resources in ascending order ---------------------------------------------------------
+    // ---- C1: decisions (no table access) ---------------------------------------------------------------
     double rew = 0.0;
     int n_recv = 0, n_pairs = 0;
-    int my_tot = 1, my_w = 0, my_inr = 0, my_recv = 0;
     int32_t *latp = LAT ? p.lat + tbase + u : nullptr;               // lat[t][u] = latp[t * N]
     const bool merge_mode = p.piggy && (MODE != MODE_STEP || p.state_type == 1 || p.state_type == 2);
-    const bool weighted = MODE == MODE_STEP && (p.reward_design == 1 || p.reward_design == 2 || p.reward_design == 5);
     const double Cr = p.C, sentinel = p.sentinel;
     float *obs_row = obsS + u * R;
-    int npass = 0;                           // passes with at least one reception (group-uniform)
+    int npass = 0;                           // passes with at least one transmitter (group-uniform)
 
     // who is within communication range of this vehicle (network.py:595-607), all G candidates at once
     unsigned inr_mask = 0u;
@@ -213,81 +221,52 @@ step_group_kernel(const Params p)
         const double d = dist_uni(flat, sx[t], sy[t], x, y);
         if (d < Cr) inr_mask |= 1u << t;
     }
+    const unsigned live_mask = FULL ? 0xffffffffu >> (32 - G) : ((1u << N) - 1u);
+
+    // per-resource collision histogram (test_env.py:149-157): `own` = the lanes sharing this lane's
+    // resource, in one instruction; its popcount is tot_actions of that resource
+    const unsigned own_all = (__match_any_sync(gmask, a) & gmask) >> (sub * G);    // every lane takes part
+    const unsigned own = act ? own_all : 0u;
+    const int my_tot = __popc(own);
+    for (int r = u; r < R; r += G) txm_s[r] = 0u;
+    if (MODE == MODE_CH) recv_s[u] = 0u;
+    __syncwarp(gmask);
+    if (act) txm_s[a] = own;                 // every transmitter of a resource writes the same word
+    __syncwarp(gmask);
 
     for (int r = 0; r < R; ++r) {
-        const unsigned txm = (__ballot_sync(gmask, a == r) & gmask) >> (sub * G);   // collision histogram
+        const unsigned txm = txm_s[r];
         if (txm == 0u) { obs_row[r] = 0.0f; continue; }
-        const int tot = __popc(txm);
         const bool is_tx = (a == r);
-        const bool is_rx = act && !is_tx;
 
-        // nearest in-range transmitter (Network.find_closest_tx): the candidates are the bits of the
-        // precomputed in-range mask among the transmitters; with one candidate there is nothing to
-        // compare, otherwise scan them in ascending id with strict '<' (first wins ties)
-        const unsigned cand = is_rx ? (inr_mask & txm) : 0u;
+        // nearest in-range transmitter (Network.find_closest_tx, network.py:378-398): the candidates
+        // are the in-range bits among the transmitters, visited in ascending id with strict '<' (first
+        // wins ties).  The two lowest are compared branch-free; a third and later ones are rare.
+        const unsigned cand = (act && !is_tx) ? (inr_mask & txm) : 0u;
         n_pairs += __popc(cand);
-        int tstar = cand ? (__ffs(cand) - 1) : -1;
-        double best = sentinel;
-        if (!p.fast_nearest || (tot > 1 && __ballot_sync(gmask, (cand & (cand - 1)) != 0u) != 0u)) {
-            tstar = -1;
-            for (unsigned m = txm; m; m &= m - 1) {
-                const int t = __ffs(m) - 1;
-                const double d = dist_uni(flat, sx[t], sy[t], x, y);
-                if (((cand >> t) & 1u) && d < best) { best = d; tstar = t; }
-            }
-        } else if (MODE == MODE_STEP && p.state_type == 2) {
-            const int ts = max(tstar, 0);
-            const double d = dist_uni(flat, sx[ts], sy[ts], x, y);
-            if (tstar >= 0) best = d;
+        const unsigned rest = cand & (cand - 1u);
+        const int t1 = cand ? (__ffs(cand) - 1) : u;
+        const int t2 = rest ? (__ffs(rest) - 1) : t1;
+        double best = dist_uni(flat, sx[t1], sy[t1], x, y);
+        const double d2 = dist_uni(flat, sx[t2], sy[t2], x, y);
+        int tstar = t1;
+        if (d2 < best) { best = d2; tstar = t2; }
+        for (unsigned m = rest & (rest - 1u); m; m &= m - 1u) {
+            const int t = __ffs(m) - 1;
+            const double d = dist_uni(flat, sx[t], sy[t], x, y);
+            if (d < best) { best = d; tstar = t; }
         }
+        if (!cand || !(best < sentinel)) { tstar = -1; best = sentinel; }              // network.py:385
+        if (tstar >= 0) ++n_recv;
+
         if (LAT) {                                                                    // network.py:394
             for (unsigned m = txm; m; m &= m - 1) {
                 const int t = __ffs(m) - 1;
-                if (is_rx && !((inr_mask >> t) & 1u)) latp[t * N] = -1;
+                if (act && !is_tx && !((inr_mask >> t) & 1u)) latp[t * N] = -1;
             }
+            if (MODE == MODE_CH && tstar >= 0) latp[tstar * N] = (int32_t)p.timestep;    // test_env.py:436
         }
-        if (MODE == MODE_CH && tot > 1) {
-            for (unsigned m = txm; m; m &= m - 1) {
-                const int t = __ffs(m) - 1;
-                const unsigned bm = __ballot_sync(gmask, (cand >> t) & 1u);
-                if (u == t) my_inr = __popc(bm);
-            }
-        }
-        if (tstar >= 0) ++n_recv;
-        if (is_tx) my_tot = tot;
-
-        // what the reward of the transmitters on r needs (the reward itself is formed after the loop)
-        if (MODE == MODE_STEP) {
-            if (weighted && tot > 1 && design_needs_weight(p.reward_design, tot)) {
-                int w;
-                if (tot == 2) {      // one pair: the mean is that pair's distance (sum([d]) / 1 == d)
-                    const int t1 = __ffs(txm) - 1, t2 = __ffs(txm & (txm - 1)) - 1;
-                    const double m = dist_uni(flat, sx[t1], sy[t1], sx[t2], sy[t2]);
-                    w = p.toy ? (m == norm) : (m > Cr);
-                } else w = reward_weight(p, flat, sx, sy, txm, norm);
-                if (is_tx) my_w = w;
-            }
-        } else if (MODE == MODE_DESIGN) {
-            if (is_tx && tot > 1) {   // TestEnv.calculate_reward_design (test_env.py:319-349)
-                int k = 1, last = u;
-                for (unsigned m = txm; m; m &= m - 1) {
-                    const int t = __ffs(m) - 1;
-                    if (t != u && dist_uni(flat, x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
-                }
-                if (k == 1) rew = 1.0;
-                else if (k == 2) rew = (dist_uni(flat, x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
-                else rew = -(double)k;
-            }
-        } else {
-            if (tot > 1) {
-                for (unsigned m = txm; m; m &= m - 1) {
-                    const int t = __ffs(m) - 1;
-                    const unsigned bm = __ballot_sync(gmask, tstar == t);
-                    if (u == t) my_recv = __popc(bm);
-                }
-            }
-            if (LAT) { if (tstar >= 0) latp[tstar * N] = (int32_t)p.timestep; }      // test_env.py:436
-        }
+        if (MODE == MODE_CH && tstar >= 0) smem_red_inc(&recv_s[tstar]);              // test_env.py:396-397
 
         // channel observation (test_env.py:203-240 / :305-306 / :431)
         {
@@ -300,16 +279,46 @@ step_group_kernel(const Params p)
         }
 
         // table merge (vehicle.py:35-47) is deferred: log which row this lane merges in this pass
-        if (merge_mode && __ballot_sync(gmask, tstar >= 0) != 0u) {
+        if (merge_mode) {
             script[npass * G + u] = (unsigned char)(tstar >= 0 ? tstar : u);
             ++npass;
         }
     }
 
-    // rewards (test_env.py:159-199 / :294-302 / :408-429)
-    if (MODE == MODE_STEP) rew = my_tot == 1 ? 1.0 : collision_reward_step(p.reward_design, my_tot, my_w);
-    else if (MODE == MODE_DESIGN) { if (my_tot == 1) rew = 1.0; }
-    else rew = channel_reward(p.reward_design, my_tot, my_recv, my_inr);
+    // rewards (test_env.py:159-199 / :294-302 / :408-429), all lane-local
+    if (MODE == MODE_STEP) {
+        if (my_tot <= 1) rew = 1.0;
+        else {
+            int w = 0;
+            if (design_needs_weight(p.reward_design, my_tot)) {
+                if (my_tot == 2) {   // one pair: the mean is that pair's distance (sum([d]) / 1 == d)
+                    const int o = __ffs(own & ~(1u << u)) - 1;
+                    const double m = dist_uni(flat, x, y, sx[o], sy[o]);
+                    w = p.toy ? (m == norm) : (m > Cr);
+                } else w = reward_weight(p, flat, sx, sy, own, norm);
+            }
+            rew = collision_reward_step(p.reward_design, my_tot, w);
+        }
+    } else if (MODE == MODE_DESIGN) {
+        if (my_tot <= 1) rew = 1.0;
+        else {   // TestEnv.calculate_reward_design (test_env.py:319-349)
+            int k = 1, last = u;
+            for (unsigned m = own; m; m &= m - 1) {
+                const int t = __ffs(m) - 1;
+                if (t != u && dist_uni(flat, x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
+            }
+            if (k == 1) rew = 1.0;
+            else if (k == 2) rew = (dist_uni(flat, x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
+            else rew = -(double)k;
+        }
+    } else {
+        // PRR (test_env.py:384-405): receivers in range of this transmitter = its own in-range bits
+        // outside its collision set (distance is symmetric bit for bit); packets received were counted
+        // by the receivers into recv_s
+        __syncwarp(gmask);
+        const int in_range = __popc(inr_mask & ~own & live_mask);
+        rew = channel_reward(p.reward_design, max(my_tot, 1), (int)recv_s[u], in_range);
+    }
 
     // ---- D: mobility -------------------------------------------------------------------------------
     const double x_new = act ? mobility_step(p, x, v, u) : 0.0;
@@ -371,39 +380,39 @@ step_group_kernel(const Params p)
             if (FULL || (j < N && act)) { seqp[j * N] = sb[q]; lup[j * N] = lb[q]; xp[j * N] = xb[q]; }
         }
         if (vpd) {
+            // numpy.histogram bin (network.py:500): t = (s + W) * B / 2W is a few ulp from the
+            // real-valued bin coordinate, so trunc(t) is NumPy's edge-corrected bin unless t sits within
+            // 1e-6 of an integer; those (rare) samples are re-binned against the edges themselves.
+            // Straight-line per column; the histogram update is a fire-and-forget shared-memory
+            // reduction (lane-private column => conflict-free), so columns do not serialise on it.
             unsigned fix = 0u;
 #pragma unroll
             for (int q = 0; q < SL; ++q) {
                 const int j = jbase + q;
-                const bool ok = (FULL || (j < N && act)) && j != u && lb[q] < age_thr;   // network.py:547
-                double sv; bool in;
+                bool in = (FULL || (j < N && act)) && j != u && lb[q] < age_thr;       // network.py:547
+                double sv;
                 if (flat0) {           // dy == 0: signed distance is exactly xpos - own x
                     sv = __dsub_rn(xb[q], x_new);
-                    in = ok && fabs(sv) < W;                                    // network.py:487
+                    in = in && fabs(sv) < W;                                    // network.py:487
                 } else {
                     const double y1 = sb[q] > 0 ? sy[j] : 0.0;
                     const double d = dist_uni(false, xb[q], y1, x_new, y);
-                    in = ok && d < W;
+                    in = in && d < W;
                     sv = (__dsub_rn(xb[q], x_new) > 0.0) ? d : -d;
                 }
-                // numpy.histogram bin (network.py:500): t is a few ulp from the real-valued bin
-                // coordinate, so trunc(t) is NumPy's edge-corrected bin unless t sits within 1e-6
-                // of an integer; those (rare) samples are re-binned against the edges below
                 const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
                 const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
-                if (in) {
-                    const int kb = min(max((int)t, 0), B - 1);
-                    if (fabs(__dsub_rn(t, rt)) < 1e-6) {
-                        fix |= 1u << q;
-                        xb[q] = sv;                            // keep the sample for the exact re-binning
-                    } else hist[kb * G + u] += 1u;
-                    ++m_cnt;
-                }
+                const bool near = fabs(__dsub_rn(t, rt)) < 1e-6;
+                const int kb = min(max((int)t, 0), B - 1);
+                if (in && !near) smem_red_inc(&hist[kb * G + u]);
+                if (in && near) fix |= 1u << q;
+                m_cnt += in ? 1 : 0;
+                xb[q] = sv;                                    // keep the sample for the exact re-binning
             }
             if (fix) {
 #pragma unroll
                 for (int q = 0; q < SL; ++q)
-                    if ((fix >> q) & 1u) hist[vpd_bin_edges(xb[q], W, inv_binw, B, s_edges) * G + u] += 1u;
+                    if ((fix >> q) & 1u) smem_red_inc(&hist[vpd_bin_edges(xb[q], W, inv_binw, B, s_edges) * G + u]);
             }
         }
     };
@@ -431,19 +440,23 @@ step_group_kernel(const Params p)
     if (act) p.rews[vbase + u] = (float)rew;
 
     // ---- F: state rows (TestEnv.obtain_state) in shared memory -----------------------------------
-    // Row u lives at st[u*S .. u*S+S) exactly as in global memory, but rotated by rot(u) words
-    // (a multiple of 4 chosen on the host) so that the 32 lanes' scalar writes of the same column hit
-    // different banks while the read-out can still move aligned float4s.
-    const int rot = p.st_vec ? 4 * (u >> p.st_sh) : 0;
+    // Row u sits at st[u*S .. u*S+S) exactly as in global memory, so the copy-out is a plain
+    // contiguous float4 stream.  (The scalar row writes bank-conflict for some S; they are few.)
+    __syncwarp(gmask);                       // all histogram reductions of this group have landed
     if (want_state && act) {
-        float *row = st + u * S;
-        float *wp = row + rot, *row_end = row + S;
-        auto emit = [&](float val) { *wp = val; if (++wp == row_end) wp = row; };
+        float *wp = st + u * S;
         if (p.add_action) {
-            if (p.action_binary) { for (int r = 0; r < R; ++r) emit((a == r) ? 1.0f : 0.0f); }
-            else emit((float)a);
+            if (p.action_binary) {
+                int r = 0;
+                if ((S & 3) == 0) {          // rows are 16-byte aligned: four one-hot entries per store
+                    for (; r + 4 <= R; r += 4, wp += 4)
+                        *reinterpret_cast<float4 *>(wp) = make_float4(a == r ? 1.0f : 0.0f, a == r + 1 ? 1.0f : 0.0f,
+                                                                      a == r + 2 ? 1.0f : 0.0f, a == r + 3 ? 1.0f : 0.0f);
+                }
+                for (; r < R; ++r) *wp++ = (a == r) ? 1.0f : 0.0f;
+            } else *wp++ = (float)a;
         }
-        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) emit(obs_row[r]); }
+        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) *wp++ = obs_row[r]; }
         if (p.piggy) {
             // counts / len with one correctly rounded reciprocal and two FMAs per bin: exact
             // (== RN(c / m)) for all 0 <= c <= m < 1024, checked exhaustively (tests/test_host.py)
@@ -455,41 +468,27 @@ step_group_kernel(const Params p)
                     const float q0 = __fmul_rn(c, rcp);
                     q = __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0);
                 }
-                emit(q);
+                *wp++ = q;
             }
         }
-        if (p.add_reward) emit((float)rew);
-        if (p.add_index) emit((float)(u + 1));
-        if (p.add_position) { emit((float)__ddiv_rn(x_new, p.L)); emit((float)__ddiv_rn(y, 2.0)); }
-        if (p.add_velocity) emit((float)v);
-        if (p.fingerprint) { emit((float)p.episode); emit((float)p.epsilon); }
+        if (p.add_reward) *wp++ = (float)rew;
+        if (p.add_index) *wp++ = (float)(u + 1);
+        if (p.add_position) { *wp++ = (float)__ddiv_rn(x_new, p.L); *wp++ = (float)__ddiv_rn(y, 2.0); }
+        if (p.add_velocity) *wp++ = (float)v;
+        if (p.fingerprint) { *wp++ = (float)p.episode; *wp++ = (float)p.epsilon; }
     }
     __syncwarp(gmask);
 
     // coalesced copy-out of the [N][R] observation block and the [N][S] state block
-    {
-        float *og = p.obs + vbase * R;
-        const int n = N * R;
-        if ((n & 3) == 0 && (lay.off_obs & 15) == 0) {
-            for (int i = u; i < n / 4; i += G) reinterpret_cast<float4 *>(og)[i] = reinterpret_cast<const float4 *>(obsS)[i];
+    auto copy_out = [&](float *dst, const float *src, int n) {
+        if ((n & 3) == 0) {
+            for (int i = u; i < n / 4; i += G) reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(src)[i];
         } else {
-            for (int i = u; i < n; i += G) og[i] = obsS[i];
+            for (int i = u; i < n; i += G) dst[i] = src[i];
         }
-    }
-    if (want_state) {
-        float *sg = p.state + vbase * S;
-        if (p.st_vec) {
-            const int S4 = S >> 2;
-            for (int i = u; i < N * S4; i += G) {
-                const int uu = (int)__umulhi((unsigned)i, p.inv_S4);
-                int c = i - uu * S4 + (uu >> p.st_sh);       // undo the row rotation, in float4 units
-                if (c >= S4) c -= S4;
-                reinterpret_cast<float4 *>(sg)[i] = reinterpret_cast<const float4 *>(st)[uu * S4 + c];
-            }
-        } else {
-            for (int i = u; i < N * S; i += G) sg[i] = st[i];
-        }
-    }
+    };
+    copy_out(p.obs + vbase * R, obsS, N * R);
+    if (want_state) copy_out(p.state + vbase * S, st, N * S);
 }
 
 template <int G>
