@@ -103,7 +103,9 @@ __device__ __noinline__ int reward_weight(const Params &p, bool flat, const doub
 // hist[..] += 1 in shared memory without waiting for (or depending on) the old value
 __device__ __forceinline__ void smem_red_inc(unsigned *addr)
 {
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(addr)) : "memory");
+    // no "memory" clobber on purpose: the surrounding column code must stay free to interleave; every
+    // plain access to the histogram is separated from these reductions by a __syncwarp
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(addr)));
 }
 
 // exact bin of a sample against the linspace edges -- only reached within 1e-6 of a bin boundary
@@ -234,14 +236,13 @@ step_group_kernel(const Params p)
     if (act) txm_s[a] = own;                 // every transmitter of a resource writes the same word
     __syncwarp(gmask);
 
-    for (int r = 0; r < R; ++r) {
-        const unsigned txm = txm_s[r];
-        if (txm == 0u) { obs_row[r] = 0.0f; continue; }
+    // One resource: nearest in-range transmitter of this lane (Network.find_closest_tx,
+    // network.py:378-398) and its channel observation.  The candidates are the in-range bits among the
+    // transmitters, visited in ascending id with strict '<' (first wins ties): the two lowest are
+    // compared branch-free, a third and later ones are rare.  Pure (no stores), so two resources can be
+    // in flight at once.
+    auto decide = [&](int r, unsigned txm, int &tstar, float &o) {
         const bool is_tx = (a == r);
-
-        // nearest in-range transmitter (Network.find_closest_tx, network.py:378-398): the candidates
-        // are the in-range bits among the transmitters, visited in ascending id with strict '<' (first
-        // wins ties).  The two lowest are compared branch-free; a third and later ones are rare.
         const unsigned cand = (act && !is_tx) ? (inr_mask & txm) : 0u;
         n_pairs += __popc(cand);
         const unsigned rest = cand & (cand - 1u);
@@ -249,7 +250,7 @@ step_group_kernel(const Params p)
         const int t2 = rest ? (__ffs(rest) - 1) : t1;
         double best = dist_uni(flat, sx[t1], sy[t1], x, y);
         const double d2 = dist_uni(flat, sx[t2], sy[t2], x, y);
-        int tstar = t1;
+        tstar = t1;
         if (d2 < best) { best = d2; tstar = t2; }
         for (unsigned m = rest & (rest - 1u); m; m &= m - 1u) {
             const int t = __ffs(m) - 1;
@@ -258,30 +259,47 @@ step_group_kernel(const Params p)
         }
         if (!cand || !(best < sentinel)) { tstar = -1; best = sentinel; }              // network.py:385
         if (tstar >= 0) ++n_recv;
-
+        // channel observation (test_env.py:203-240 / :305-306 / :431)
+        o = 0.0f;
+        if (!is_tx && txm) {
+            if (MODE == MODE_STEP) o = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
+            else o = 1.0f;
+        }
+    };
+    // side effects of one resource, in resource order
+    auto commit = [&](int r, unsigned txm, int tstar, float o) {
+        obs_row[r] = o;
+        if (txm == 0u) return;
         if (LAT) {                                                                    // network.py:394
+            const bool is_rx = act && a != r;
             for (unsigned m = txm; m; m &= m - 1) {
                 const int t = __ffs(m) - 1;
-                if (act && !is_tx && !((inr_mask >> t) & 1u)) latp[t * N] = -1;
+                if (is_rx && !((inr_mask >> t) & 1u)) latp[t * N] = -1;
             }
             if (MODE == MODE_CH && tstar >= 0) latp[tstar * N] = (int32_t)p.timestep;    // test_env.py:436
         }
         if (MODE == MODE_CH && tstar >= 0) smem_red_inc(&recv_s[tstar]);              // test_env.py:396-397
-
-        // channel observation (test_env.py:203-240 / :305-306 / :431)
-        {
-            float o = 0.0f;
-            if (!is_tx) {
-                if (MODE == MODE_STEP) o = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
-                else o = 1.0f;
-            }
-            obs_row[r] = o;
-        }
-
         // table merge (vehicle.py:35-47) is deferred: log which row this lane merges in this pass
         if (merge_mode) {
             script[npass * G + u] = (unsigned char)(tstar >= 0 ? tstar : u);
             ++npass;
+        }
+    };
+    {
+        int r = 0;
+        for (; r + 2 <= R; r += 2) {
+            const unsigned m0 = txm_s[r], m1 = txm_s[r + 1];
+            int ts0, ts1; float o0, o1;
+            decide(r, m0, ts0, o0);
+            decide(r + 1, m1, ts1, o1);
+            commit(r, m0, ts0, o0);
+            commit(r + 1, m1, ts1, o1);
+        }
+        if (r < R) {
+            const unsigned m0 = txm_s[r];
+            int ts0; float o0;
+            decide(r, m0, ts0, o0);
+            commit(r, m0, ts0, o0);
         }
     }
 
