@@ -1,0 +1,165 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, configuration handling mirrors the reference constructor, the product path refuses to run
+without a GPU (no CPU fallback), and the small exactness lemmas the kernels rely on hold."""
+import ctypes as C
+import os
+import re
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _state(**over):
+    st = dict(type=2, add_action=True, add_reward=False, add_index=False, add_velocity=False,
+              action_index="binary", piggybacking=False, add_position=False, add_positional_dist=False,
+              add_positional_dist_piggy=True, add_positional_dist_type=2, add_channel_obs=False, num_bins=20)
+    st.update(over)
+    return st
+
+
+def test_library_exports_every_declared_symbol():
+    from diral_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "diral_env.h")).read()
+    declared = set(re.findall(r"\b(diral_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in include/diral_env.h"
+    assert declared == set(_lib.SYMBOLS), "binding and header disagree: %s" % (declared ^ set(_lib.SYMBOLS))
+    for name in declared:
+        assert hasattr(lib, name), "libdiral_env.so does not export %s" % name
+    assert lib.diral_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_the_header():
+    """ctypes mirrors must have the C layout: sizes are checked against a tiny C program."""
+    import subprocess
+    import tempfile
+    from diral_b200._lib import DiralBuffers, DiralCfg
+    src = '#include <stdio.h>\n#include "diral_env.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(diral_cfg), ' \
+          'sizeof(diral_buffers), __builtin_offsetof(diral_cfg, sentinel), __builtin_offsetof(diral_buffers, trace_len));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")]).split()
+    assert [int(x) for x in out] == [C.sizeof(DiralCfg), C.sizeof(DiralBuffers), DiralCfg.sentinel.offset,
+                                     DiralBuffers.trace_len.offset]
+
+
+def test_state_space_matches_reference_formula_and_oracle():
+    from diral_b200 import _lib, cfg_from_kwargs
+    from oracle.c_oracle import cfg_from_kwargs as orc_cfg, lib as orc_lib
+    lib = _lib.load()
+    rs = np.random.RandomState(3)
+    for _ in range(200):
+        st = _state(add_action=bool(rs.randint(2)), add_reward=bool(rs.randint(2)), add_index=bool(rs.randint(2)),
+                    add_velocity=bool(rs.randint(2)), action_index=["binary", "real"][rs.randint(2)],
+                    add_position=bool(rs.randint(2)), add_positional_dist=bool(rs.randint(2)),
+                    add_positional_dist_piggy=bool(rs.randint(2)), add_channel_obs=bool(rs.randint(2)),
+                    num_bins=int(rs.randint(1, 64)))
+        kw = dict(num_users=int(rs.randint(2, 64)), num_channels=int(rs.randint(1, 40)),
+                  enable_fingerprint=bool(rs.randint(2)), State=st)
+        cfg = cfg_from_kwargs(4, 0, kw)
+        s = lib.diral_state_space(C.byref(cfg))
+        n, r, b = kw["num_users"], kw["num_channels"], st["num_bins"]
+        want = ((r if st["action_index"] == "binary" else 1) if st["add_action"] else 0) + (r if st["add_channel_obs"] else 0) \
+            + st["add_reward"] + st["add_index"] + st["add_velocity"] + 2 * st["add_position"] \
+            + (n - 1) * st["add_positional_dist"] + 2 * kw["enable_fingerprint"] + b * st["add_positional_dist_piggy"]
+        assert s == want                                        # reference test_env.py:49-85
+        assert s == orc_lib().orc_state_space(C.byref(orc_cfg(**kw)))
+    # shipped toy config: S = R + B = 23
+    cfg = cfg_from_kwargs(1, 0, dict(num_users=4, num_channels=3, State=_state()))
+    assert lib.diral_state_space(C.byref(cfg)) == 23
+
+
+def test_constructor_defaults_and_rejections():
+    from diral_b200 import cfg_from_kwargs
+    cfg = cfg_from_kwargs(8, 16, dict(State=_state()))
+    # TestEnv.__init__ defaults (reference test_env.py:12-24)
+    assert (cfg.N, cfg.R, cfg.L, cfg.C, cfg.W, cfg.reward_design) == (3, 3, 200.0, 1.0, 500.0, 1)
+    assert (cfg.E, cfg.env0, cfg.age_threshold, cfg.sentinel) == (8, 16, 20, 100000.0)
+    assert not cfg.mobility and not cfg.toy and not cfg.fingerprint
+    with pytest.raises(ValueError):
+        cfg_from_kwargs(1, 0, dict())                           # State block is mandatory in the reference
+    with pytest.raises(ValueError):
+        cfg_from_kwargs(1, 0, dict(State=_state(piggybacking=True)))
+    with pytest.raises(ValueError):
+        cfg_from_kwargs(1, 0, dict(proportional_fair=True, State=_state()))
+    with pytest.raises(ValueError):
+        cfg_from_kwargs(1, 0, dict(State=_state(action_index="gray")))
+    bad = _state(); del bad["num_bins"]
+    with pytest.raises(ValueError):
+        cfg_from_kwargs(1, 0, dict(State=bad))
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from diral_b200 import TestEnv, _lib, cfg_from_kwargs
+    with pytest.raises(RuntimeError, match="CUDA"):
+        TestEnv(num_envs=2, device="cuda", num_users=4, num_channels=3, State=_state())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        TestEnv(num_envs=2, device="cpu", num_users=4, num_channels=3, State=_state())
+    lib = _lib.load()
+    cfg = cfg_from_kwargs(2, 0, dict(num_users=4, num_channels=3, State=_state()))
+    h = C.c_void_p()
+    rc = lib.diral_create(C.byref(cfg), C.byref(h))
+    assert rc == -2 and not h.value and b"cuda" in lib.diral_last_error().lower()
+
+
+def test_product_code_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "diral_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/diral_oracle.c", "").replace("oracle/", "") or f == "_never_", \
+                    "%s mentions the oracle" % f
+
+
+def test_size_helpers():
+    from diral_b200 import _lib, cfg_from_kwargs
+    lib = _lib.load()
+    cfg = cfg_from_kwargs(4096, 0, dict(num_users=32, num_channels=20, State=_state()))
+    n = lib.diral_state_bytes(C.byref(cfg))
+    tables = 4096 * 32 * 32 * (4 + 4 + 8 + 4)
+    assert tables < n < tables * 1.6
+    assert lib.diral_scratch_bytes(C.byref(cfg)) == 0
+    big = cfg_from_kwargs(16, 0, dict(num_users=256, num_channels=128, State=_state()))
+    assert lib.diral_scratch_bytes(C.byref(big)) == 16 * 256 * 257 * 4      # keys no longer fit shared memory
+
+
+def test_count_over_len_division_is_exact():
+    """The kernels form VPD = count / len as  q0 = c*r; q = fma(fma(-q0, m, c), r, q0)  with
+    r = RN(1/m): it must equal RN(c/m) (what float32(np.float64(c)/m) gives).  Sampled here, checked
+    exhaustively for all 0 <= c <= m < 1024 when the kernel was written."""
+    f32 = np.float32
+
+    def rn32(fr):
+        x = f32(float(fr))
+        cands = [x, np.nextafter(x, f32(np.inf)), np.nextafter(x, f32(-np.inf))]
+        return min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(np.asarray(c).view(np.uint32)) & 1))
+
+    rs = np.random.RandomState(0)
+    ms = sorted(set([1, 2, 3, 5, 7, 19, 31, 127, 255, 1023] + [int(v) for v in rs.randint(1, 1024, 30)]))
+    for m in ms:
+        r = rn32(Fraction(1, m))
+        for c in sorted(set([0, 1, m // 2, m - 1, m] + [int(v) for v in rs.randint(0, m + 1, 8)])):
+            q0 = rn32(Fraction(c) * Fraction(float(r)))
+            rem = rn32(Fraction(c) - Fraction(float(q0)) * m)
+            q = rn32(Fraction(float(rem)) * Fraction(float(r)) + Fraction(float(q0)))
+            assert q == f32(np.float64(c) / np.float64(m)), (c, m)
+
+
+def test_signed_distance_identity():
+    """On a flat highway the kernels use s = xpos - own_x for  sign * sqrt((own_x - xpos)**2):
+    identical in float64, including the reference's libm pow (network.py:549-555)."""
+    import math
+    rs = np.random.RandomState(1)
+    for _ in range(20000):
+        x1, x2 = float(rs.uniform(0, 8000)), float(rs.uniform(0, 8000))
+        d = math.sqrt((x2 - x1) ** 2 + (0.0 - 0.0) ** 2)
+        s_ref = d * (1 if x1 - x2 > 0.0 else -1)
+        assert s_ref == x1 - x2 or (s_ref == 0 and x1 - x2 == 0)
