@@ -35,6 +35,9 @@
 #include "diral_dev.cuh"
 #include "diral_launch.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace diral {
 
 namespace {
@@ -449,10 +452,11 @@ step_group_kernel(const Params p)
             np += __shfl_xor_sync(gmask, np, o, G);
             nb += __shfl_xor_sync(gmask, nb, o, G);
         }
-        if (u == 0) {
-            p.acc_reward[e] += rs;
-            long long *c = p.acc_count + e * ACC_COUNTS;
-            c[0] += nr; c[1] += np; c[2] += nb; c[3] += 1;
+        if (u == 0) {    // reductions, not read-modify-writes: nothing waits for the old values
+            atomicAdd(p.acc_reward + e, rs);
+            unsigned long long *c = reinterpret_cast<unsigned long long *>(p.acc_count + e * ACC_COUNTS);
+            atomicAdd(c + 0, (unsigned long long)nr); atomicAdd(c + 1, (unsigned long long)np);
+            atomicAdd(c + 2, (unsigned long long)nb); atomicAdd(c + 3, 1ull);
         }
     }
     if (act) p.rews[vbase + u] = (float)rew;
@@ -536,7 +540,9 @@ cudaError_t launch_k(const Params &p, cudaStream_t stream)
     constexpr int W = WarpsFor<G>::v;
     const long long envs_per_cta = (long long)W * (32 / G);
     const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
-    step_group_kernel<G, FULL, W, MODE, LAT><<<(unsigned)grid, W * 32, smem_bytes<G>(p, W), stream>>>(p);
+    size_t smem = smem_bytes<G>(p, W);
+    if (const char *pad = getenv("DIRAL_SMEM_PER_CTA")) smem = std::max(smem, (size_t)atoll(pad));   // tuning knob
+    step_group_kernel<G, FULL, W, MODE, LAT><<<(unsigned)grid, W * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
