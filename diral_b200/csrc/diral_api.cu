@@ -46,6 +46,8 @@ struct Handle {
     long long launches = 0;
     double *d_edges = nullptr;      // [2*(B+1)]: linspace(-W, W, B+1) then linspace(-1, 1, B+1)
     int32_t *d_actions = nullptr;   // staging for generated / host-side actions
+    cudaStream_t pipe[2] = {nullptr, nullptr};   // diral_step_host: env chunks alternate between these
+    cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
 };
 
 struct DeviceGuard {
@@ -153,6 +155,23 @@ int require_bound(Handle *h)
     return DIRAL_OK;
 }
 
+// the same parameter block restricted to envs [e0, e0 + n): every per-env array is contiguous per env
+diral::Params env_range(const diral::Params &p, long long e0, long long n)
+{
+    diral::Params q = p;
+    const long long N = p.N, NN = N * N;
+    q.E = n; q.env0 = p.env0 + e0;
+    if (q.actions) q.actions += e0 * N;
+    if (q.actions_out) q.actions_out += e0 * N;
+    q.pos_x += e0 * N; q.pos_y += e0 * N; q.vel += e0 * N;
+    if (q.tab_seq) { q.tab_seq += e0 * NN; q.tab_lu += e0 * NN; q.tab_x += e0 * NN; }
+    if (q.lat) q.lat += e0 * NN;
+    q.obs += e0 * N * p.R; q.rews += e0 * N; q.state += e0 * N * p.S;
+    q.acc_reward += e0; q.acc_count += e0 * diral::ACC_COUNTS;
+    if (q.scratch) q.scratch += e0 * N * (N + 1);
+    return q;
+}
+
 int ensure_actions_staging(Handle *h)
 {
     if (!h->d_actions) DIRAL_CUDA(cudaMalloc(&h->d_actions, sizeof(int32_t) * (size_t)h->cfg.E * h->cfg.N));
@@ -233,6 +252,8 @@ int diral_destroy(void *handle)
     DeviceGuard g(h->device);
     cudaFree(h->d_edges);
     cudaFree(h->d_actions);
+    for (auto &st : h->pipe) if (st) cudaStreamDestroy(st);
+    for (auto &ev : h->pipe_ev) if (ev) cudaEventDestroy(ev);
     delete h;
     return DIRAL_OK;
 }
@@ -408,15 +429,57 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
     Handle *h = as_handle(handle);
     if (int rc = require_bound(h)) return rc;
     if (!h_actions || !h_state || !h_rews) return fail(DIRAL_ERR_ARG, "h_actions/h_state/h_rews must not be NULL");
+    if (mode < DIRAL_MY_STEP || mode > DIRAL_MY_STEP_CH) return fail(DIRAL_ERR_ARG, "mode must be 0, 1 or 2 (got %d)", mode);
     if (int rc = ensure_actions_staging(h)) return rc;
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t EN = (size_t)h->cfg.E * h->cfg.N;
-    DIRAL_CUDA(cudaMemcpyAsync(h->d_actions, h_actions, EN * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    if (int rc = diral_step(handle, mode, h->d_actions, timestep, 1, episode, epsilon, 0, nullptr, stream)) return rc;
-    DIRAL_CUDA(cudaMemcpyAsync(h_state, h->bufs.state, EN * (size_t)h->base.S * sizeof(float), cudaMemcpyDeviceToHost, s));
-    DIRAL_CUDA(cudaMemcpyAsync(h_rews, h->bufs.rews, EN * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (h_obs) DIRAL_CUDA(cudaMemcpyAsync(h_obs, h->bufs.obs, EN * (size_t)h->cfg.R * sizeof(float), cudaMemcpyDeviceToHost, s));
+    const long long E = h->cfg.E, N = h->cfg.N, R = h->cfg.R, S = h->base.S;
+    // Envs are independent, so the batch is cut into chunks that alternate between two internal
+    // streams: chunk c's results travel over PCIe while chunk c+1 computes and chunk c+2's actions arrive.
+    const int chunks = (fused_state_ok(h->cfg) && E >= 1024) ? 4 : 1;
+    if (chunks == 1) {
+        DIRAL_CUDA(cudaMemcpyAsync(h->d_actions, h_actions, (size_t)(E * N) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        if (int rc = diral_step(handle, mode, h->d_actions, timestep, 1, episode, epsilon, 0, nullptr, stream)) return rc;
+        DIRAL_CUDA(cudaMemcpyAsync(h_state, h->bufs.state, (size_t)(E * N * S) * sizeof(float), cudaMemcpyDeviceToHost, s));
+        DIRAL_CUDA(cudaMemcpyAsync(h_rews, h->bufs.rews, (size_t)(E * N) * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_obs) DIRAL_CUDA(cudaMemcpyAsync(h_obs, h->bufs.obs, (size_t)(E * N * R) * sizeof(float), cudaMemcpyDeviceToHost, s));
+        DIRAL_CUDA(cudaStreamSynchronize(s));
+        return DIRAL_OK;
+    }
+    const bool group = use_group(h);
+    const int src_bits = group ? diral::key_src_bits(diral::group_width(h->cfg.N)) : diral::key_src_bits(h->cfg.N);
+    if (h->cfg.add_piggy && h->ticks + 1 >= (1ll << (32 - src_bits)))
+        return fail(DIRAL_ERR_SEQ_RANGE, "slot %lld since reset exceeds the %d-bit sequence field of the packed table keys",
+                    h->ticks + 1, 32 - src_bits);
+    for (auto &st : h->pipe) if (!st) DIRAL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &ev : h->pipe_ev) if (!ev) DIRAL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    diral::Params p = h->base;
+    p.mode = mode; p.timestep = timestep; p.episode = episode; p.epsilon = epsilon; p.seed = 0;
+    p.build_state = 1; p.actions = h->d_actions; p.gen_actions = 0; p.actions_out = nullptr;
+    if (mode == DIRAL_MY_STEP_CH && h->bufs.lat) h->lat_live = true;
+    p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;
+    DIRAL_CUDA(cudaEventRecord(h->pipe_ev[2], s));                 // everything queued on the caller's stream so far
+    for (int c = 0; c < chunks; ++c) {
+        const long long e0 = E * c / chunks, n = E * (c + 1) / chunks - e0;
+        cudaStream_t ps = h->pipe[c & 1];
+        if (c < 2) DIRAL_CUDA(cudaStreamWaitEvent(ps, h->pipe_ev[2], 0));
+        DIRAL_CUDA(cudaMemcpyAsync(h->d_actions + e0 * N, h_actions + e0 * N, (size_t)(n * N) * sizeof(int32_t),
+                                   cudaMemcpyHostToDevice, ps));
+        const diral::Params q = env_range(p, e0, n);
+        DIRAL_CUDA(group ? diral::launch_step_group(q, ps) : diral::launch_step_block(q, ps));
+        h->launches += 1;
+        DIRAL_CUDA(cudaMemcpyAsync(h_state + e0 * N * S, h->bufs.state + e0 * N * S, (size_t)(n * N * S) * sizeof(float),
+                                   cudaMemcpyDeviceToHost, ps));
+        DIRAL_CUDA(cudaMemcpyAsync(h_rews + e0 * N, h->bufs.rews + e0 * N, (size_t)(n * N) * sizeof(float),
+                                   cudaMemcpyDeviceToHost, ps));
+        if (h_obs) DIRAL_CUDA(cudaMemcpyAsync(h_obs + e0 * N * R, h->bufs.obs + e0 * N * R, (size_t)(n * N * R) * sizeof(float),
+                                              cudaMemcpyDeviceToHost, ps));
+    }
+    if (h->cfg.add_piggy) h->ticks += 1;
+    for (int k = 0; k < 2; ++k) {                                  // the caller's stream sees the step as done
+        DIRAL_CUDA(cudaEventRecord(h->pipe_ev[k], h->pipe[k]));
+        DIRAL_CUDA(cudaStreamWaitEvent(s, h->pipe_ev[k], 0));
+    }
     DIRAL_CUDA(cudaStreamSynchronize(s));
     return DIRAL_OK;
 }

@@ -157,21 +157,19 @@ step_group_kernel(const Params p)
     const long long vbase = e * N;           // first vehicle of this env in the [E][N] arrays
     const long long tbase = e * (long long)N * N;
 
-    // ---- A: per-vehicle inputs ---------------------------------------------------------------
-    int a = -1; double x = 0.0, y = 0.0, v = 0.0; int bad = 0;
-    if (act) {
-        a = p.gen_actions ? philox_action(p.seed, u, p.env0 + e, p.timestep, R) : p.actions[vbase + u];
-        if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
-        if (p.gen_actions && p.actions_out) p.actions_out[vbase + u] = a;
-        x = p.pos_x[vbase + u]; y = p.pos_y[vbase + u]; v = p.vel[vbase + u];
-    }
-    sx[u] = x; sy[u] = y;
-
-    // ---- table slabs: SL columns at a time --------------------------------------------------------------
+    // ---- A: start every independent global access before the first dependent use ------------------
     constexpr int SL = G < 8 ? G : 8;        // columns per slab
     constexpr int NSL = G / SL;              // slabs per table
     int32_t *seqp = p.tab_seq + tbase + u, *lup = p.tab_lu + tbase + u;   // column j of this lane: [j * N]
     double *xp = p.tab_x + tbase + u;
+    int a = -1; double x = 0.0, y = 0.0, v = 0.0; int bad = 0;
+    if (act) {
+        if (!p.gen_actions) a = p.actions[vbase + u];
+        x = p.pos_x[vbase + u]; y = p.pos_y[vbase + u]; v = p.vel[vbase + u];
+    }
+    int s_next[SL];                          // seq column of the upcoming slab (loaded one slab ahead)
+#pragma unroll
+    for (int q = 0; q < SL; ++q) s_next[q] = (p.piggy && (FULL || (q < N && act))) ? seqp[q * N] : 0;
     if (p.piggy) {
         // pull this environment's whole table (16 * N * N bytes, contiguous per array) from HBM into L2
         // now; the decision phase below runs while it arrives and the slab loads then hit L2
@@ -186,9 +184,12 @@ step_group_kernel(const Params p)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + bytes4 + o));
         }
     }
-    int s_next[SL];                          // seq column of the upcoming slab (loaded one slab ahead)
-#pragma unroll
-    for (int q = 0; q < SL; ++q) s_next[q] = (p.piggy && (FULL || (q < N && act))) ? seqp[q * N] : 0;
+    if (act) {
+        if (p.gen_actions) a = philox_action(p.seed, u, p.env0 + e, p.timestep, R);
+        if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
+        if (p.gen_actions && p.actions_out) p.actions_out[vbase + u] = a;
+    }
+    sx[u] = x; sy[u] = y;
 
     // every vehicle on the same lane of the highway (dy == 0 for every pair)?  warp-uniform per group
     const double y0 = __shfl_sync(gmask, y, 0, G);

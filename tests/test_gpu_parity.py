@@ -220,3 +220,47 @@ def test_bad_actions_are_counted_and_errors_are_loud():
         _env(2, **dict(kw, State=_shipped_state(piggybacking=True)))
     with pytest.raises(DiralError):
         _env(2, **dict(kw, num_channels=0))
+
+
+def test_host_buffer_step_matches_device_step():
+    """diral_step_host (chunked, pipelined over two internal streams) == diral_step on the same actions."""
+    kw = dict(num_users=32, num_channels=20, highway_length=800, reward_design=2, communication_range=250,
+              mobility=True, bin_range=500, State=_shipped_state(add_channel_obs=True))
+    E = 2048
+    dev = _env(E, seed=5, **kw)
+    host = _env(E, seed=5, **kw)
+    S = dev.S
+    h_state = torch.empty((E, 32, S), dtype=torch.float32).pin_memory()
+    h_rews = torch.empty((E, 32), dtype=torch.float32).pin_memory()
+    h_obs = torch.empty((E, 32, 20), dtype=torch.float32).pin_memory()
+    for t in range(12):
+        a = dev.sample(t)
+        s, r, info = dev.step(a)
+        host.step_host(a.cpu().pin_memory(), h_state, h_rews, h_obs)
+        assert torch.equal(s.cpu(), h_state) and torch.equal(r.cpu(), h_rews) and torch.equal(info["obs"].cpu(), h_obs)
+    assert torch.equal(dev._tab_seq, host._tab_seq) and torch.equal(dev._tab_x, host._tab_x)
+    assert torch.equal(dev.episode_metrics(), host.episode_metrics())
+
+
+def test_rollout_and_velocity_draws_follow_the_philox_specification():
+    from oracle.c_oracle import COracle
+    kw = dict(num_users=10, num_channels=4, highway_length=400, reward_design=2, communication_range=250,
+              mobility=True, mobility_vary=True, bin_range=500, State=_shipped_state(add_velocity=True))
+    E, seed = 33, 77
+    orc = COracle(num_envs=E, **kw)
+    orc.reset_philox(seed)
+    env = _env(E, seed=seed, **kw)
+    t = 0
+    for episode in range(3):
+        env.rollout(25)
+        for _ in range(25):
+            a = orc.philox_actions(seed, t)
+            o, r = orc.step("my_step", a, t)
+            s = orc.obtain_state(o, a, r)
+            t += 1
+        _close32(_np(env._state), s, "state after rollout", t, exact=True)
+        assert (_np(env.tab_seq) == orc.tab_seq).all() and (_np(env.pos_x) == orc.pos_x).all()
+        env.episode = episode
+        env.update_velocity()
+        orc.update_velocity(orc.philox_draws(seed, episode))
+        assert (_np(env.vel) == orc.vel).all(), "velocity jitter, episode %d" % episode
