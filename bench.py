@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+print_line = print
 METRIC = "agent-steps/sec (4096 envs x 32 UE x 20 res per GPU)"
 UNIT = "agent-steps/s"
 E_PER_GPU, N_UE, N_RES, N_BINS = 4096, 32, 20, 20
@@ -102,7 +103,7 @@ def run_reference(args):
             "note": "CPU port (oracle/diral_oracle.c) of the reference's my_step + obtain_state; the reference is "
                     "pure Python and cannot travel to the GPU box (it ran ~60x slower per core than this port in "
                     "the build container, SURVEY.md section 6)"}
-    print(json.dumps(line))
+    print_line(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -282,10 +283,22 @@ def run_gpu(args):
     if world == 1 and not args.no_cpu:
         v, dt, cores, sample = cpu_port_run(20, 3, target_seconds=15.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line))
+    print_line(json.dumps(line))
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, for one) print to fd 1; the driver wants exactly one JSON line
+    there.  Point fd 1 at stderr for the run and hand back a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return lambda text: os.write(real, (text + "\n").encode())
 
 
 def main():
+    emit = _claim_stdout()
+    global print_line
+    print_line = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
