@@ -37,6 +37,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace diral {
 
@@ -62,7 +63,7 @@ struct GroupSmem {
         off_sx = o;   o += align16i(8 * G);
         off_sy = o;   o += align16i(8 * G);
         off_obs = o;  o += align16i(4 * G * R);
-        off_hist = o; o += (state && vpd) ? align16i(4 * G * B) : 0;
+        off_hist = o; o += (state && vpd) ? align16i(4 * G * (B + 1)) : 0;   // + 1 dummy row
         off_st = o;   o += state ? align16i(4 * G * S) : 0;
         bytes = o;
     }
@@ -75,14 +76,22 @@ __device__ __noinline__ double dist_slow(double dx, double dy)
     return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
-// Network.dist (network.py:318-332); `flat` (warp-uniform) promises dy == 0, where the result is |dx|
-__device__ __forceinline__ double dist_uni(bool flat, double x1, double y1, double x2, double y2)
+// Network.dist (network.py:318-332).  FLAT promises dy == 0 (every vehicle on one lane of the
+// highway), where the result is |dx|; it is a compile-time flag in the hot loops so that they contain
+// no branch and no call, and the scheduler can interleave independent columns / resources.
+template <bool FLAT>
+__device__ __forceinline__ double dist_t(double x1, double y1, double x2, double y2)
 {
     const double dx = __dsub_rn(x2, x1);
-    if (flat) return fabs(dx);
+    if (FLAT) return fabs(dx);
     const double dy = __dsub_rn(y2, y1);
     if (dy == 0.0) return fabs(dx);
     return dist_slow(dx, dy);
+}
+
+__device__ __forceinline__ double dist_uni(bool flat, double x1, double y1, double x2, double y2)
+{
+    return flat ? dist_t<true>(x1, y1, x2, y2) : dist_t<false>(x1, y1, x2, y2);
 }
 
 // Network.calculate_reward_weights / calculate_avg_distance (network.py:273-316):
@@ -222,10 +231,12 @@ step_group_kernel(const Params p)
 
     // who is within communication range of this vehicle (network.py:595-607), all G candidates at once
     unsigned inr_mask = 0u;
+    if (flat) {
 #pragma unroll
-    for (int t = 0; t < G; ++t) {
-        const double d = dist_uni(flat, sx[t], sy[t], x, y);
-        if (d < Cr) inr_mask |= 1u << t;
+        for (int t = 0; t < G; ++t) if (dist_t<true>(sx[t], sy[t], x, y) < Cr) inr_mask |= 1u << t;
+    } else {
+#pragma unroll
+        for (int t = 0; t < G; ++t) if (dist_t<false>(sx[t], sy[t], x, y) < Cr) inr_mask |= 1u << t;
     }
     const unsigned live_mask = FULL ? 0xffffffffu >> (32 - G) : ((1u << N) - 1u);
 
@@ -245,20 +256,21 @@ step_group_kernel(const Params p)
     // transmitters, visited in ascending id with strict '<' (first wins ties): the two lowest are
     // compared branch-free, a third and later ones are rare.  Pure (no stores), so two resources can be
     // in flight at once.
-    auto decide = [&](int r, unsigned txm, int &tstar, float &o) {
+    auto decide = [&](auto flat_c, int r, unsigned txm, int &tstar, float &o) {
+        constexpr bool FL = decltype(flat_c)::value;
         const bool is_tx = (a == r);
         const unsigned cand = (act && !is_tx) ? (inr_mask & txm) : 0u;
         n_pairs += __popc(cand);
         const unsigned rest = cand & (cand - 1u);
         const int t1 = cand ? (__ffs(cand) - 1) : u;
         const int t2 = rest ? (__ffs(rest) - 1) : t1;
-        double best = dist_uni(flat, sx[t1], sy[t1], x, y);
-        const double d2 = dist_uni(flat, sx[t2], sy[t2], x, y);
+        double best = dist_t<FL>(sx[t1], sy[t1], x, y);
+        const double d2 = dist_t<FL>(sx[t2], sy[t2], x, y);
         tstar = t1;
         if (d2 < best) { best = d2; tstar = t2; }
         for (unsigned m = rest & (rest - 1u); m; m &= m - 1u) {
             const int t = __ffs(m) - 1;
-            const double d = dist_uni(flat, sx[t], sy[t], x, y);
+            const double d = dist_t<FL>(sx[t], sy[t], x, y);
             if (d < best) { best = d; tstar = t; }
         }
         if (!cand || !(best < sentinel)) { tstar = -1; best = sentinel; }              // network.py:385
@@ -289,23 +301,24 @@ step_group_kernel(const Params p)
             ++npass;
         }
     };
-    {
+    auto run_decisions = [&](auto flat_c) {
         int r = 0;
         for (; r + 2 <= R; r += 2) {
             const unsigned m0 = txm_s[r], m1 = txm_s[r + 1];
             int ts0, ts1; float o0, o1;
-            decide(r, m0, ts0, o0);
-            decide(r + 1, m1, ts1, o1);
+            decide(flat_c, r, m0, ts0, o0);
+            decide(flat_c, r + 1, m1, ts1, o1);
             commit(r, m0, ts0, o0);
             commit(r + 1, m1, ts1, o1);
         }
         if (r < R) {
             const unsigned m0 = txm_s[r];
             int ts0; float o0;
-            decide(r, m0, ts0, o0);
+            decide(flat_c, r, m0, ts0, o0);
             commit(r, m0, ts0, o0);
         }
-    }
+    };
+    if (flat) run_decisions(std::true_type{}); else run_decisions(std::false_type{});
 
     // rewards (test_env.py:159-199 / :294-302 / :408-429), all lane-local
     if (MODE == MODE_STEP) {
@@ -408,29 +421,35 @@ step_group_kernel(const Params p)
             // Straight-line per column; the histogram update is a fire-and-forget shared-memory
             // reduction (lane-private column => conflict-free), so columns do not serialise on it.
             unsigned fix = 0u;
+            auto vpd_cols = [&](auto flat_c) {
+                constexpr bool FL0 = decltype(flat_c)::value;
 #pragma unroll
-            for (int q = 0; q < SL; ++q) {
-                const int j = jbase + q;
-                bool in = (FULL || (j < N && act)) && j != u && lb[q] < age_thr;       // network.py:547
-                double sv;
-                if (flat0) {           // dy == 0: signed distance is exactly xpos - own x
-                    sv = __dsub_rn(xb[q], x_new);
-                    in = in && fabs(sv) < W;                                    // network.py:487
-                } else {
-                    const double y1 = sb[q] > 0 ? sy[j] : 0.0;
-                    const double d = dist_uni(false, xb[q], y1, x_new, y);
-                    in = in && d < W;
-                    sv = (__dsub_rn(xb[q], x_new) > 0.0) ? d : -d;
+                for (int q = 0; q < SL; ++q) {
+                    const int j = jbase + q;
+                    bool in = (FULL || (j < N && act)) && j != u && lb[q] < age_thr;   // network.py:547
+                    double sv;
+                    if (FL0) {             // dy == 0: signed distance is exactly xpos - own x
+                        sv = __dsub_rn(xb[q], x_new);
+                        in = in && fabs(sv) < W;                                // network.py:487
+                    } else {
+                        const double y1 = sb[q] > 0 ? sy[j] : 0.0;
+                        const double d = dist_t<false>(xb[q], y1, x_new, y);
+                        in = in && d < W;
+                        sv = (__dsub_rn(xb[q], x_new) > 0.0) ? d : -d;
+                    }
+                    const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
+                    const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
+                    const bool near = fabs(__dsub_rn(t, rt)) < 1e-6;
+                    // samples that do not count (or wait for the exact re-binning) go to a dummy row, so
+                    // the reduction is unconditional and the column code stays branch-free
+                    const int kb = (in && !near) ? min(max((int)t, 0), B - 1) : B;
+                    smem_red_inc(&hist[kb * G + u]);
+                    if (in && near) fix |= 1u << q;
+                    m_cnt += in ? 1 : 0;
+                    xb[q] = sv;                                // keep the sample for the exact re-binning
                 }
-                const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
-                const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
-                const bool near = fabs(__dsub_rn(t, rt)) < 1e-6;
-                const int kb = min(max((int)t, 0), B - 1);
-                if (in && !near) smem_red_inc(&hist[kb * G + u]);
-                if (in && near) fix |= 1u << q;
-                m_cnt += in ? 1 : 0;
-                xb[q] = sv;                                    // keep the sample for the exact re-binning
-            }
+            };
+            if (flat0) vpd_cols(std::true_type{}); else vpd_cols(std::false_type{});
             if (fix) {
 #pragma unroll
                 for (int q = 0; q < SL; ++q)
