@@ -36,6 +36,7 @@ struct Params {
     int fast_nearest;         // C <= sentinel: a lone in-range transmitter is the nearest without comparing
     // per-call
     int mode, track_lat, build_state, gen_actions;
+    int prefetch_ahead;       // envs between this CTA's env and the one that will reuse its SM slot
     long long timestep;
     double episode, epsilon;
     unsigned long long seed;

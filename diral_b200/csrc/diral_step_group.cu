@@ -179,6 +179,22 @@ step_group_kernel(const Params p)
     int s_next[SL];                          // seq column of the upcoming slab (loaded one slab ahead)
 #pragma unroll
     for (int q = 0; q < SL; ++q) s_next[q] = (p.piggy && (FULL || (q < N && act))) ? seqp[q * N] : 0;
+    {
+        // the CTA that will take over this slot most likely handles env e + (resident CTAs); start its
+        // per-vehicle inputs towards L2 now so that its first dependent instruction does not wait on HBM
+        const long long en = e + (long long)p.prefetch_ahead;
+        if (u == 0 && en < p.E) {
+            if (!p.gen_actions) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + en * N));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pos_x + en * N));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pos_y + en * N));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.vel + en * N));
+            if (N * 8 > 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pos_x + en * N + 16));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pos_y + en * N + 16));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.vel + en * N + 16));
+            }
+        }
+    }
     if (p.piggy) {
         // pull this environment's whole table (16 * N * N bytes, contiguous per array) from HBM into L2
         // now; the decision phase below runs while it arrives and the slab loads then hit L2
@@ -262,8 +278,8 @@ step_group_kernel(const Params p)
         const unsigned cand = (act && !is_tx) ? (inr_mask & txm) : 0u;
         n_pairs += __popc(cand);
         const unsigned rest = cand & (cand - 1u);
-        const int t1 = cand ? (__ffs(cand) - 1) : u;
-        const int t2 = rest ? (__ffs(rest) - 1) : t1;
+        const int t1 = (__ffs(cand) - 1) & (G - 1);      // cand == 0: any valid lane, the result is discarded
+        const int t2 = (__ffs(rest | (1u << t1)) - 1) & (G - 1);   // rest == 0: t1 again (all rest bits lie above t1)
         double best = dist_t<FL>(sx[t1], sy[t1], x, y);
         const double d2 = dist_t<FL>(sx[t2], sy[t2], x, y);
         tstar = t1;
@@ -554,6 +570,22 @@ cudaError_t prepare_k(const Params &p)
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+// CTAs of this instantiation the whole device holds at once (cached per instantiation and smem size)
+template <int G, bool FULL, int W, int MODE, bool LAT>
+long long resident_ctas(size_t smem)
+{
+    static size_t cached_smem = ~(size_t)0; static long long cached = 0;
+    if (smem != cached_smem) {
+        int dev = 0, sms = 148, per_sm = 16;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_group_kernel<G, FULL, W, MODE, LAT>, W * 32, smem) != cudaSuccess)
+            per_sm = 16;
+        cached = (long long)sms * per_sm; cached_smem = smem;
+    }
+    return cached;
+}
+
 template <int G, bool FULL, int MODE, bool LAT>
 cudaError_t launch_k(const Params &p, cudaStream_t stream)
 {
@@ -561,8 +593,10 @@ cudaError_t launch_k(const Params &p, cudaStream_t stream)
     const long long envs_per_cta = (long long)W * (32 / G);
     const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
     size_t smem = smem_bytes<G>(p, W);
+    Params q = p;
+    q.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT>(smem) * envs_per_cta);
     if (const char *pad = getenv("DIRAL_SMEM_PER_CTA")) smem = std::max(smem, (size_t)atoll(pad));   // tuning knob
-    step_group_kernel<G, FULL, W, MODE, LAT><<<(unsigned)grid, W * 32, smem, stream>>>(p);
+    step_group_kernel<G, FULL, W, MODE, LAT><<<(unsigned)grid, W * 32, smem, stream>>>(q);
     return cudaGetLastError();
 }
 
