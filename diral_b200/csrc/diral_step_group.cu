@@ -519,14 +519,19 @@ step_group_kernel(const Params p)
             // counts / len with one correctly rounded reciprocal and two FMAs per bin: exact
             // (== RN(c / m)) for all 0 <= c <= m < 1024, checked exhaustively (tests/test_host.py)
             const float den = (float)m_cnt, rcp = __frcp_rn(den);
-            for (int b = 0; b < B; ++b) {
-                float q = 0.0f;
-                if (vpd && m_cnt > 0) {
-                    const float c = (float)hist[b * G + u];
-                    const float q0 = __fmul_rn(c, rcp);
-                    q = __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0);
+            const bool have = vpd && m_cnt > 0;
+            for (int b0 = 0; b0 < B; b0 += 8) {      // loads first: the row stores below may alias them
+                unsigned hv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hv[i] = (have && b0 + i < B) ? hist[(b0 + i) * G + u] : 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (b0 + i < B) {
+                        const float c = (float)hv[i];
+                        const float q0 = __fmul_rn(c, rcp);
+                        *wp++ = have ? __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0) : 0.0f;
+                    }
                 }
-                *wp++ = q;
             }
         }
         if (p.add_reward) *wp++ = (float)rew;
