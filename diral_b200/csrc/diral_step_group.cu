@@ -279,7 +279,8 @@ step_group_kernel(const Params p)
         n_pairs += __popc(cand);
         const unsigned rest = cand & (cand - 1u);
         const int t1 = (__ffs(cand) - 1) & (G - 1);      // cand == 0: any valid lane, the result is discarded
-        const int t2 = (__ffs(rest | (1u << t1)) - 1) & (G - 1);   // rest == 0: t1 again (all rest bits lie above t1)
+        const int f2 = __ffs(rest) - 1;
+        const int t2 = f2 < 0 ? t1 : f2;                 // no second candidate: compare t1 with itself
         double best = dist_t<FL>(sx[t1], sy[t1], x, y);
         const double d2 = dist_t<FL>(sx[t2], sy[t2], x, y);
         tstar = t1;
