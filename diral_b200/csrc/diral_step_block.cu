@@ -33,20 +33,21 @@ namespace diral {
 
 namespace {
 
-constexpr int CB = 4;                        // table columns per epilogue barrier
+constexpr int CB = 2;                        // table columns per thread per epilogue barrier
 constexpr unsigned short PAIR_NONE = 0xFFFFu;
 
 __host__ __device__ inline size_t align16z(size_t x) { return (x + 15) & ~(size_t)15; }
 
 struct BlockSmem {
-    size_t off_sx, off_sy, off_edges, off_txm, off_pairs, off_misc, off_recv, off_red, off_union, off_keys, bytes;
+    size_t off_sx, off_sy, off_sxn, off_edges, off_txm, off_pairs, off_misc, off_recv, off_red, off_union, off_keys, bytes;
     size_t union_bytes, keys_bytes;
-    __host__ __device__ BlockSmem(int N, int R, int B, int T, bool vpd_state, bool keys_in_smem)
+    __host__ __device__ BlockSmem(int N, int R, int B, int TN, int H, bool vpd_state, bool keys_in_smem)
     {
-        const int NW = T / 32;
+        const int NW = TN / 32, T = TN;
         size_t o = 0;
         off_sx = o;    o += align16z(8 * (size_t)N);
         off_sy = o;    o += align16z(8 * (size_t)N);
+        off_sxn = o;   o += align16z(8 * (size_t)N);          // post-mobility x, for the helper threads
         off_edges = o; o += align16z(8 * (size_t)(B + 1));
         off_txm = o;   o += align16z(4 * (size_t)R * NW);
         off_pairs = o; o += align16z(2 * 2 * (size_t)N);         // two pass lists of (rx << 8 | tx)
@@ -55,7 +56,7 @@ struct BlockSmem {
         off_red = o;   o += align16z(8 * 4 * 32);
         // phase-disjoint: the obs transpose tiles (phase C) share space with histogram + column buffer (E)
         const size_t tiles = 4 * (size_t)NW * 32 * 33;
-        const size_t epi = (vpd_state ? align16z(4 * (size_t)(B + 1) * T) : 0) + 2 * CB * 8 * (size_t)N;
+        const size_t epi = (vpd_state ? align16z(4 * (size_t)(B + 1) * T) : 0) + 2 * (size_t)H * CB * 8 * (size_t)N;
         union_bytes = align16z(tiles > epi ? tiles : epi);
         off_union = o; o += union_bytes;
         keys_bytes = keys_in_smem ? align16z(4 * (size_t)N * (N + 1)) : 0;
@@ -87,13 +88,21 @@ __device__ __noinline__ int block_reward_weight(const Params &p, const double *s
     return p.toy ? (mean == norm) : (mean > p.C);
 }
 
+// H helper copies of the N-thread team: thread (h, u).  Team 0 makes the decisions; all teams share the
+// column merges (receptions k = h, h+H, .. of a pass), the key loads and the epilogue column blocks.
+template <int NW> struct Helpers { static constexpr int v = NW <= 4 ? 4 : 2; };
+
 template <int NW>
-__global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, const int SB, const int keys_in_smem)
+__global__ void __launch_bounds__(NW * 32 * Helpers<NW>::v, (NW * 32 * Helpers<NW>::v <= 512 ? 2 : 1))
+step_block_kernel(const Params p, const int SB, const int keys_in_smem)
 {
-    constexpr int T = NW * 32;
+    constexpr int T = NW * 32;               // team size (threads that map to vehicles / columns)
+    constexpr int H = Helpers<NW>::v;
+    constexpr int TT = T * H;                // CTA size
     const int N = p.N, R = p.R, B = p.B, S = p.S;
-    const int u = threadIdx.x, lane = u & 31, warp = u >> 5;
-    const bool act = u < N;
+    const int tid = threadIdx.x, h = tid / T, u = tid - h * T, lane = tid & 31, warp = u >> 5;
+    const bool col = u < N;                  // a valid vehicle / column index
+    const bool act = col && h == 0;          // ... and the thread that decides for it
     const long long e = blockIdx.x;
     const long long vbase = e * N, tbase = e * (long long)N * N;
     const bool want_state = p.build_state != 0;
@@ -102,9 +111,10 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
     const int mode = p.mode;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const BlockSmem lay(N, R, B, T, p.vpd_enabled != 0, keys_in_smem != 0);
+    const BlockSmem lay(N, R, B, T, H, p.vpd_enabled != 0, keys_in_smem != 0);
     double *sx = reinterpret_cast<double *>(smem_raw + lay.off_sx);
     double *sy = reinterpret_cast<double *>(smem_raw + lay.off_sy);
+    double *sxn = reinterpret_cast<double *>(smem_raw + lay.off_sxn);
     double *s_edges = reinterpret_cast<double *>(smem_raw + lay.off_edges);
     unsigned *txm_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_txm);         // [R][NW]
     unsigned short *pairs = reinterpret_cast<unsigned short *>(smem_raw + lay.off_pairs);   // [2][N]
@@ -129,16 +139,16 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
         const char *b1 = reinterpret_cast<const char *>(p.tab_lu + tbase);
         const char *b2 = reinterpret_cast<const char *>(p.tab_x + tbase);
         const int bytes4 = N * N * 4;
-        for (int o = u * 128; o < bytes4; o += T * 128) {
+        for (int o = tid * 128; o < bytes4; o += TT * 128) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + o));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + bytes4 + o));
         }
         (void)b0;     // the seq columns are read right below
     }
-    for (int i = u; i <= B; i += T) s_edges[i] = p.edges[i];
-    for (int i = u; i < R * NW; i += T) txm_s[i] = 0u;
-    if (u < 4) npairs[u] = 0;
+    for (int i = tid; i <= B; i += TT) s_edges[i] = p.edges[i];
+    for (int i = tid; i < R * NW; i += TT) txm_s[i] = 0u;
+    if (tid < 4) npairs[tid] = 0;
     if (act) {
         if (p.gen_actions) a = philox_action(p.seed, u, p.env0 + e, p.timestep, R);
         if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
@@ -147,10 +157,10 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
     }
     __syncthreads();
     if (act) atomicOr(&txm_s[a * NW + warp], 1u << lane);            // test_env.py:149-157
-    if (p.piggy && act) {
+    if (p.piggy && col) {
         const int32_t *seqp = p.tab_seq + tbase + u;
 #pragma unroll 8
-        for (int j = 0; j < N; ++j) {
+        for (int j = h; j < N; j += H) {
             int s = seqp[j * N];
             if (j == u) s += 1;                                      // vehicle.py:58 (tick)
             K[u * ld + j] = ((unsigned)s << SB) | (unsigned)u;
@@ -201,6 +211,7 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
     float *og = p.obs + vbase * R;
     int pc = 0;                               // non-empty passes so far (uniform)
     auto flush_tile = [&](int r_end) {       // rows of the 32x32 tile -> coalesced 128 B segments of obs
+        if (h != 0) return;
         const int r0 = (r_end - 1) & ~31, nr = r_end - r0;
         __syncwarp();
         for (int i = 0; i < 32; ++i) {
@@ -253,15 +264,15 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
                 if (has) pairs[parity * N + basep + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)((u << 8) | tstar);
                 // the counter of pass pc+2: its last readers (pass pc-2) are all past barrier pc-1, and its
                 // next writers come after barrier pc+1
-                if (u == 0) npairs[(pc + 2) & 3] = 0;
+                if (tid == 0) npairs[(pc + 2) & 3] = 0;
                 __syncthreads();
                 const int np = npairs[slot];
-                if (act) {           // thread j = u owns column j
+                if (col) {           // team h applies receptions h, h+H, .. of this pass to column j = u
                     const unsigned short *pl = pairs + parity * N;
                     unsigned *Kj = K + u;
-                    int k = 0;
-                    for (; k + 4 <= np; k += 4) {        // receptions of one pass are independent
-                        const unsigned p0 = pl[k], p1 = pl[k + 1], p2 = pl[k + 2], p3 = pl[k + 3];
+                    int k = h;
+                    for (; k + 3 * H < np; k += 4 * H) {     // receptions of one pass are independent
+                        const unsigned p0 = pl[k], p1 = pl[k + H], p2 = pl[k + 2 * H], p3 = pl[k + 3 * H];
                         const unsigned a0 = Kj[(p0 >> 8) * ld], b0 = Kj[(p0 & 255u) * ld];
                         const unsigned a1 = Kj[(p1 >> 8) * ld], b1 = Kj[(p1 & 255u) * ld];
                         const unsigned a2 = Kj[(p2 >> 8) * ld], b2 = Kj[(p2 & 255u) * ld];
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
                         Kj[(p0 >> 8) * ld] = max(a0, b0); Kj[(p1 >> 8) * ld] = max(a1, b1);
                         Kj[(p2 >> 8) * ld] = max(a2, b2); Kj[(p3 >> 8) * ld] = max(a3, b3);
                     }
-                    for (; k < np; ++k) {
+                    for (; k < np; k += H) {
                         const unsigned p0 = pl[k];
                         Kj[(p0 >> 8) * ld] = max(Kj[(p0 >> 8) * ld], Kj[(p0 & 255u) * ld]);
                     }
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
                 ++pc;
             }
         }
-        tile[lane * 33 + (r & 31)] = o;
+        if (h == 0) tile[lane * 33 + (r & 31)] = o;
         if ((r & 31) == 31 || r == R - 1) flush_tile(r + 1);
     }
     __syncthreads();                          // keys final; recv_s complete; tiles free for the epilogue
@@ -319,25 +330,29 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
     }
 
     // ---- D: mobility -------------------------------------------------------------------------------
-    const double x_new = act ? mobility_step(p, x, v, u) : 0.0;
-    if (act && p.mobility) p.pos_x[vbase + u] = x_new;
+    double x_new = act ? mobility_step(p, x, v, u) : 0.0;
+    if (act) { if (p.mobility) p.pos_x[vbase + u] = x_new; sxn[u] = x_new; recv_s[u] = 0u; }   // recv_s now sums m_cnt
+    __syncthreads();
+    if (col && h != 0) { x = sx[u]; y = sy[u]; x_new = sxn[u]; }
 
     // ---- E: stream the columns (thread u = observer) -----------------------------------------------
     int m_cnt = 0;
-    if (vpd) { for (int k = 0; k <= B; ++k) hist[k * T + u] = 0u; }
+    if (vpd && h == 0) { for (int k = 0; k <= B; ++k) hist[k * T + u] = 0u; }
+    __syncthreads();
     if (p.piggy) {
         int32_t *seqp = p.tab_seq + tbase + u, *lup = p.tab_lu + tbase + u;
         double *xp = p.tab_x + tbase + u;
         const double W = p.W, inv_binw = p.inv_binw;
         int buf = 0;
-        for (int jb = 0; jb < N; jb += CB) {
+        for (int jb0 = 0; jb0 < N; jb0 += H * CB) {
+            const int jb = jb0 + h * CB;         // this team's columns of the block
             int s0[CB], lu[CB], sn[CB]; double xo[CB]; unsigned key[CB];
-            double *cb = colbuf + (size_t)buf * CB * N;
+            double *cb = colbuf + ((size_t)buf * H + h) * CB * N;
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
                 const int j = jb + c;
                 s0[c] = 0; lu[c] = 0; xo[c] = 0.0; key[c] = 0u;
-                if (act && j < N) {
+                if (col && j < N) {
                     s0[c] = seqp[j * N]; lu[c] = lup[j * N]; xo[c] = xp[j * N];
                     if (j == u) { s0[c] += 1; lu[c] = 0; xo[c] = x; } else lu[c] += 1;     // vehicle.py:58-70
                     key[c] = K[u * ld + j];
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
                 const int j = jb + c;
-                if (act && j < N) {
+                if (col && j < N) {
                     sn[c] = (int)(key[c] >> SB);
                     double xn = xo[c];
                     if (sn[c] != s0[c]) { xn = cb[c * N + (int)(key[c] & srcmask)]; lu[c] = 0; }   // vehicle.py:41-47
@@ -377,7 +392,9 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
             buf ^= 1;
         }
     }
+    if (col && m_cnt) atomicAdd(&recv_s[u], (unsigned)m_cnt);
     __syncthreads();                          // every thread is done with the keys: the region becomes staging
+    if (act) m_cnt = (int)recv_s[u];
 
     // ---- F: state rows (TestEnv.obtain_state, test_env.py:527-583) ---------------------------------
     if (want_state) {
@@ -411,9 +428,9 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
             float *sg = p.state + vbase * S;
             const int n = N * S;
             if ((n & 3) == 0) {
-                for (int i = u; i < n / 4; i += T) reinterpret_cast<float4 *>(sg)[i] = reinterpret_cast<const float4 *>(st)[i];
+                for (int i = tid; i < n / 4; i += TT) reinterpret_cast<float4 *>(sg)[i] = reinterpret_cast<const float4 *>(st)[i];
             } else {
-                for (int i = u; i < n; i += T) sg[i] = st[i];
+                for (int i = tid; i < n; i += TT) sg[i] = st[i];
             }
         }
     }
@@ -428,9 +445,9 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
             np += __shfl_xor_sync(0xffffffffu, np, o);
             nb += __shfl_xor_sync(0xffffffffu, nb, o);
         }
-        if (lane == 0) { s_red[warp * 4 + 0] = rs; s_red[warp * 4 + 1] = nr; s_red[warp * 4 + 2] = np; s_red[warp * 4 + 3] = nb; }
+        if (lane == 0 && h == 0) { s_red[warp * 4 + 0] = rs; s_red[warp * 4 + 1] = nr; s_red[warp * 4 + 2] = np; s_red[warp * 4 + 3] = nb; }
         __syncthreads();
-        if (u == 0) {
+        if (tid == 0) {
             double trs = 0.0, tnr = 0.0, tnp = 0.0, tnb = 0.0;
             for (int i = 0; i < NW; ++i) { trs += s_red[i * 4]; tnr += s_red[i * 4 + 1]; tnp += s_red[i * 4 + 2]; tnb += s_red[i * 4 + 3]; }
             atomicAdd(p.acc_reward + e, trs);
@@ -442,6 +459,7 @@ __global__ void __launch_bounds__(NW * 32) step_block_kernel(const Params p, con
 }
 
 int block_threads(int N) { return ((N + 31) / 32) * 32; }
+int helpers_for(int N) { return block_threads(N) / 32 <= 4 ? 4 : 2; }
 
 template <int NW>
 cudaError_t prepare_nw(const Params &p, size_t smem)
@@ -453,7 +471,7 @@ cudaError_t prepare_nw(const Params &p, size_t smem)
 template <int NW>
 cudaError_t launch_nw(const Params &p, size_t smem, int SB, int fit, cudaStream_t stream)
 {
-    step_block_kernel<NW><<<(unsigned)p.E, NW * 32, smem, stream>>>(p, SB, fit);
+    step_block_kernel<NW><<<(unsigned)p.E, NW * 32 * Helpers<NW>::v, smem, stream>>>(p, SB, fit);
     return cudaGetLastError();
 }
 
@@ -468,13 +486,13 @@ int key_src_bits(int N)
 
 bool step_block_keys_fit_smem(const Params &p)
 {
-    const BlockSmem lay(p.N, p.R, p.B, block_threads(p.N), p.vpd_enabled != 0, true);
+    const BlockSmem lay(p.N, p.R, p.B, block_threads(p.N), helpers_for(p.N), p.vpd_enabled != 0, true);
     return lay.bytes <= SMEM_BUDGET;
 }
 
 size_t step_block_smem_bytes(const Params &p, bool keys_in_smem)
 {
-    const BlockSmem lay(p.N, p.R, p.B, block_threads(p.N), p.vpd_enabled != 0, keys_in_smem);
+    const BlockSmem lay(p.N, p.R, p.B, block_threads(p.N), helpers_for(p.N), p.vpd_enabled != 0, keys_in_smem);
     return lay.bytes;
 }
 
