@@ -39,6 +39,12 @@ class DiralBuffers(C.Structure):
                 ("trace", C.c_void_p), ("trace_len", C.c_int64)]
 
 
+class DiralShaping(C.Structure):
+    """POD mirror of ``diral_shaping`` (include/diral_env.h)."""
+    _fields_ = [("ia_averaging", C.c_int32), ("ia_penalty_enable", C.c_int32), ("ia_penalty_threshold", C.c_int32),
+                ("global_reward_avg", C.c_int32), ("ia_penalty_value", C.c_double)]
+
+
 # every symbol include/diral_env.h declares: name -> (restype, argtypes)
 _P, _I64, _U64, _I32, _D = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_double
 SYMBOLS = {
@@ -59,6 +65,7 @@ SYMBOLS = {
     "diral_update_velocity": (C.c_int, [_P, _P, _U64, _I64, _P]),
     "diral_information_age": (C.c_int, [_P, _I64, _P, _P]),
     "diral_episode_metrics": (C.c_int, [_P, _I64, _P, _P]),
+    "diral_shape_rewards": (C.c_int, [_P, C.POINTER(DiralShaping), _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "diral_step_host": (C.c_int, [_P, C.c_int, _P, _I64, _D, _D, _P, _P, _P, _P]),
     "diral_launch_count": (C.c_int64, [_P]),
 }

@@ -423,6 +423,31 @@ int diral_episode_metrics(void *handle, int64_t timestep, double *out110, void *
     return DIRAL_OK;
 }
 
+int diral_shape_rewards(void *handle, const diral_shaping *cfg, const int32_t *actions, int64_t timestep, float *rewards,
+                        int64_t *sum_ia_prev, int32_t *ia_counter, int32_t *prev_actions, double *slot_sums,
+                        int32_t *ia_out, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!cfg || !rewards) return fail(DIRAL_ERR_ARG, "cfg/rewards must not be NULL");
+    if (cfg->ia_averaging && !sum_ia_prev) return fail(DIRAL_ERR_ARG, "ia_averaging needs sum_ia_prev");
+    if (cfg->ia_penalty_enable && (!actions || !ia_counter || !prev_actions))
+        return fail(DIRAL_ERR_ARG, "ia_penalty_enable needs actions, ia_counter and prev_actions");
+    DeviceGuard g(h->device);
+    diral::Params p = h->base;
+    p.timestep = timestep;
+    p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;
+    diral::ShapingArgs a{};
+    a.ia_averaging = cfg->ia_averaging != 0; a.ia_penalty_enable = cfg->ia_penalty_enable != 0;
+    a.ia_penalty_threshold = cfg->ia_penalty_threshold; a.global_reward_avg = cfg->global_reward_avg != 0;
+    a.ia_penalty_value = cfg->ia_penalty_value;
+    a.actions = actions; a.rewards = rewards; a.sum_ia_prev = reinterpret_cast<long long *>(sum_ia_prev);
+    a.ia_counter = ia_counter; a.prev_actions = prev_actions; a.slot_sums = slot_sums; a.ia_out = ia_out;
+    DIRAL_CUDA(diral::launch_shape_rewards(p, a, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return DIRAL_OK;
+}
+
 int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
                     float *h_state, float *h_rews, float *h_obs, void *stream)
 {

@@ -276,3 +276,86 @@ cudaError_t launch_episode_metrics(const Params &p, double *out110, cudaStream_t
 }
 
 }  // namespace diral
+
+// ---- per-slot caller epilogue (reference main_test.py:150-206, utils/misc.py:1-12) -------------------
+namespace diral {
+
+namespace {
+
+// One CTA per environment: information-age histogram of this slot (Network.get_information_age,
+// network.py:560-574), its weighted sum (calculate_ia_penalty, utils/misc.py:1-12), then the reward
+// shaping of main_test.py:153-206 in place.  Rewards arrive as the float32 the slot kernel wrote; all
+// arithmetic here is float64 like the reference's, rounded to float32 once at the store.
+__global__ void shape_rewards_kernel(const Params p, const ShapingArgs s)
+{
+    __shared__ int h[IA_BINS];
+    __shared__ double s_sum[32];
+    __shared__ long long s_ia;
+    __shared__ int s_penalty;
+    const long long e = blockIdx.x;
+    const int N = p.N, T = blockDim.x, tid = threadIdx.x;
+    for (int i = tid; i < IA_BINS; i += T) h[i] = 0;
+    __syncthreads();
+    if (p.lat && p.track_lat) {
+        const int32_t *lat = p.lat + e * (long long)N * N;
+        for (int i = tid; i < N * N; i += T) {
+            const int t = i / N, r = i - t * N;
+            if (t != r) ia_accumulate(h, lat[i], p.timestep);
+        }
+    }
+    // sum of the raw rewards (main_test.py:174), fixed order: lane-strided partials, then a tree
+    double part = 0.0;
+    for (int i = tid; i < N; i += T) part += (double)s.rewards[e * N + i];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) s_sum[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double sum_r = 0.0;
+        for (int w = 0; w < (T + 31) / 32; ++w) sum_r += s_sum[w];
+        s_sum[0] = sum_r;
+        long long ia_sum = 0;                                      // utils/misc.py:7-10
+        for (int i = 0; i < IA_BINS; ++i) if (h[i] > 0) ia_sum += (long long)(i + 1) * h[i];
+        s_ia = ia_sum;
+        int penalty = 0;
+        if (s.ia_averaging) {                                      // main_test.py:153-160
+            const long long prev = s.sum_ia_prev[e];
+            penalty = ia_sum > prev ? -1 : (ia_sum < prev ? 1 : 0);
+            s.sum_ia_prev[e] = ia_sum;
+        }
+        s_penalty = penalty;
+        if (s.slot_sums) {
+            s.slot_sums[e * 3 + 0] = sum_r;
+            s.slot_sums[e * 3 + 1] = (double)p.R - sum_r;          // collision, main_test.py:178
+            s.slot_sums[e * 3 + 2] = (double)ia_sum;
+        }
+    }
+    __syncthreads();
+    if (s.ia_out) for (int i = tid; i < IA_BINS; i += T) s.ia_out[e * IA_BINS + i] = h[i];
+    const double sum_r = s_sum[0];
+    for (int i = tid; i < N; i += T) {                             // main_test.py:188-206
+        const long long k = e * N + i;
+        double r = (double)s.rewards[k];
+        if (s.ia_averaging) r += (double)s_penalty;
+        if (s.ia_penalty_enable) {
+            const int a = s.actions[k];
+            int c = s.ia_counter[k];
+            c = (r < 1.0 && a == s.prev_actions[k]) ? c + 1 : 0;
+            if (c > s.ia_penalty_threshold) r = s.ia_penalty_value;
+            s.ia_counter[k] = c;
+            s.prev_actions[k] = a;
+        }
+        if (s.global_reward_avg) r = r + sum_r / (double)N;
+        s.rewards[k] = (float)r;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_shape_rewards(const Params &p, const ShapingArgs &s, cudaStream_t stream)
+{
+    const int threads = p.N <= 32 ? 32 : (p.N <= 128 ? 128 : 256);
+    shape_rewards_kernel<<<(unsigned)p.E, threads, 0, stream>>>(p, s);
+    return cudaGetLastError();
+}
+
+}  // namespace diral

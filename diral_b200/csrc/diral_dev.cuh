@@ -53,6 +53,19 @@ struct Params {
     const double *edges;      // [B+1] numpy.linspace(-W, W, B+1), computed on the host in float64
 };
 
+// per-slot caller epilogue (main_test.py:150-206): device pointers and switches of one call
+struct ShapingArgs {
+    int ia_averaging, ia_penalty_enable, ia_penalty_threshold, global_reward_avg;
+    double ia_penalty_value;
+    const int32_t *actions;       // [E][N]
+    float *rewards;               // [E][N] in/out
+    long long *sum_ia_prev;       // [E]      (ia_averaging)
+    int32_t *ia_counter;          // [E][N]   (ia_penalty_enable)
+    int32_t *prev_actions;        // [E][N]   (ia_penalty_enable)
+    double *slot_sums;            // [E][3] = {sum of raw rewards, collisions, weighted information age} or NULL
+    int32_t *ia_out;              // [E][100] or NULL
+};
+
 // ---- Philox4x32-10 (Salmon et al., SC'11; published round constants) -------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
 {

@@ -6,6 +6,7 @@
 namespace diral {
 
 struct Params;
+struct ShapingArgs;
 
 // N <= 32: one lane group per environment, table keys in registers (diral_step_group.cu)
 constexpr int GROUP_MAX_N = 32;
@@ -32,5 +33,6 @@ cudaError_t launch_update_velocity(const Params &p, double *vel, const int8_t *d
                                    cudaStream_t stream);
 cudaError_t launch_information_age(const Params &p, int32_t *out, cudaStream_t stream);
 cudaError_t launch_episode_metrics(const Params &p, double *out110, cudaStream_t stream);
+cudaError_t launch_shape_rewards(const Params &p, const ShapingArgs &s, cudaStream_t stream);
 
 }  // namespace diral

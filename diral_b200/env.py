@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DiralBuffers, DiralCfg, MODES, check
+from ._lib import DiralBuffers, DiralCfg, DiralShaping, MODES, check
 
 IA_BINS = 100          # Network.get_information_age (network.py:566)
 METRIC_LEN = 110       # layout documented at diral_episode_metrics in include/diral_env.h
@@ -226,6 +226,8 @@ class TestEnv:
         self.t = 0
         self.episode = 0
         self._obs.zero_(); self._rews.zero_()
+        if hasattr(self, "_shape_sums"):          # shaping state of main_test.py:48-56,73 starts over too
+            self._sum_ia_prev.zero_(); self._ia_counter.zero_(); self._prev_actions.fill_(-1)
         return self
 
     def sample(self, t=None):
@@ -363,6 +365,32 @@ class TestEnv:
             check(self.lib.diral_episode_metrics(self._handle, C.c_int64(self.t if timestep is None else int(timestep)),
                                                  self._metrics.data_ptr(), self._stream()))
         return self._metrics
+
+    def shape_rewards(self, actions, rewards, timestep, ia_averaging=False, ia_penalty_enable=False,
+                      ia_penalty_threshold=5, ia_penalty_value=-10, global_reward_avg=False):
+        """The per-slot caller epilogue of the reference's driver (main_test.py:150-206, utils/misc.py):
+        information age of this slot, its weighted sum, and the reward shaping options, applied IN PLACE
+        to ``rewards`` ([E, N] float32, e.g. the tensor ``my_step*`` returned).  Call it after
+        ``obtain_state`` -- the reference builds the state from the unshaped rewards (main_test.py:164).
+        Returns ``(rewards, slot_sums [E, 3] = (sum_r, collisions, weighted IA), ia [E, 100])``."""
+        if not hasattr(self, "_shape_sums"):
+            dev = self.device
+            self._shape_sums = torch.zeros((self.E, 3), dtype=torch.float64, device=dev)
+            self._sum_ia_prev = torch.zeros((self.E,), dtype=torch.int64, device=dev)        # main_test.py:73
+            self._ia_counter = torch.zeros((self.E, self.N), dtype=torch.int32, device=dev)  # main_test.py:55
+            self._prev_actions = torch.full((self.E, self.N), -1, dtype=torch.int32, device=dev)   # :56
+        a = self._as_actions(actions)
+        if not (isinstance(rewards, torch.Tensor) and rewards.dtype == torch.float32 and rewards.is_contiguous()
+                and rewards.device == self.device and rewards.numel() == self.E * self.N):
+            raise ValueError("rewards must be a contiguous float32 tensor of num_envs*num_users entries on %s" % self.device)
+        cfg = DiralShaping(int(bool(ia_averaging)), int(bool(ia_penalty_enable)), int(ia_penalty_threshold),
+                           int(bool(global_reward_avg)), float(ia_penalty_value))
+        with torch.cuda.device(self.device):
+            check(self.lib.diral_shape_rewards(self._handle, C.byref(cfg), a.data_ptr(), C.c_int64(int(timestep)),
+                                               rewards.data_ptr(), self._sum_ia_prev.data_ptr(), self._ia_counter.data_ptr(),
+                                               self._prev_actions.data_ptr(), self._shape_sums.data_ptr(),
+                                               self._ia.data_ptr(), self._stream()))
+        return rewards, self._shape_sums, self._ia
 
     def launch_count(self):
         return int(self.lib.diral_launch_count(self._handle))

@@ -138,6 +138,22 @@ int diral_information_age(void *handle, int64_t timestep, int32_t *out, void *st
  * this device's envs; clears the per-env accumulators.  out110: device, float64[110]. */
 int diral_episode_metrics(void *handle, int64_t timestep, double *out110, void *stream);
 
+/* Per-slot caller epilogue of the reference's driver loop (main_test.py:150-206 + utils/misc.py:1-12),
+ * the first "next" row of SURVEY.md 8(f): information age of this slot, its weighted sum
+ * (calculate_ia_penalty), and the reward shaping -- ia_averaging (+-1 by the direction of the weighted
+ * sum), ia_penalty_enable (stuck-on-a-bad-resource penalty), global_reward_avg (+ sum_r / N) -- applied in
+ * place to rewards [E][N] (float32, device).  The caller owns the shaping state: sum_ia_prev [E] int64
+ * (initially 0), ia_counter [E][N] int32 (0), prev_actions [E][N] int32 (-1); arrays of disabled options
+ * may be NULL.  slot_sums [E][3] float64 = {sum of raw rewards, collisions = R - sum, weighted information
+ * age} and ia_out [E][100] int32 are optional outputs. */
+typedef struct diral_shaping {
+    int32_t ia_averaging, ia_penalty_enable, ia_penalty_threshold, global_reward_avg;   /* main_test.py:34-50 */
+    double  ia_penalty_value;
+} diral_shaping;
+int diral_shape_rewards(void *handle, const diral_shaping *cfg, const int32_t *actions, int64_t timestep,
+                        float *rewards, int64_t *sum_ia_prev, int32_t *ia_counter, int32_t *prev_actions,
+                        double *slot_sums, int32_t *ia_out, void *stream);
+
 /* Host-buffer convenience for callers that keep data on the CPU (the reference's learners do):
  * copies h_actions in, runs diral_step(build_state=1), copies state/rews (and obs if not NULL) out,
  * synchronises the stream.  Host pointers should be pinned for full PCIe bandwidth. */

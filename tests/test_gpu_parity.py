@@ -264,3 +264,42 @@ def test_rollout_and_velocity_draws_follow_the_philox_specification():
         env.update_velocity()
         orc.update_velocity(orc.philox_draws(seed, episode))
         assert (_np(env.vel) == orc.vel).all(), "velocity jitter, episode %d" % episode
+
+
+@pytest.mark.parametrize("opts", [
+    dict(global_reward_avg=True),                                             # the shipped YAML (:22)
+    dict(ia_averaging=True, global_reward_avg=True),
+    dict(ia_penalty_enable=True, ia_penalty_threshold=2, ia_penalty_value=-10),
+    dict(ia_averaging=True, ia_penalty_enable=True, ia_penalty_threshold=1, ia_penalty_value=-7.5, global_reward_avg=True),
+])
+def test_reward_shaping_epilogue(opts):
+    """diral_shape_rewards against the restated caller epilogue (main_test.py:150-206), PRR mode so that
+    the information age is live; few resources so that vehicles get stuck on bad ones."""
+    from oracle.c_oracle import COracle
+    from oracle.shaping import ShapingState, shape_slot
+    kw = dict(num_users=12, num_channels=3, highway_length=700, reward_design=2, communication_range=250,
+              mobility=True, bin_range=500, State=_shipped_state())
+    E, T, seed = 24, 40, 3
+    orc = COracle(num_envs=E, **kw)
+    orc.reset_philox(seed)
+    env = _env(E, seed=seed, **kw)
+    states = [ShapingState(12) for _ in range(E)]
+    rs = np.random.RandomState(4)
+    for t in range(T):
+        # sticky actions: most vehicles repeat their previous choice
+        a = orc.philox_actions(seed, t)
+        if t:
+            keep = rs.rand(E, 12) < 0.8
+            a = np.where(keep, prev_a, a).astype(np.int32)
+        prev_a = a
+        o_ref, r_ref = orc.step("my_step_ch", a, t)
+        ia_ref = orc.information_age(t)
+        obs, rews = env.my_step_ch(a, t)
+        shaped, sums, ia = env.shape_rewards(a, rews, t, **opts)
+        assert (_np(ia) == ia_ref).all()
+        for e in range(E):
+            r64 = r_ref[e].astype(np.float32).astype(np.float64)      # the epilogue starts from the float32 rewards
+            sum_r, coll, ia_sum = shape_slot(states[e], ia_ref[e], a[e], r64, 3, **opts)
+            assert np.allclose(_np(shaped)[e], r64.astype(np.float32), rtol=1e-6, atol=1e-6), (t, e)
+            assert np.allclose(_np(sums)[e], [sum_r, coll, ia_sum], rtol=1e-12, atol=1e-9), (t, e)
+    env.close()

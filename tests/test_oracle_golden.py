@@ -59,3 +59,15 @@ def test_survey_known_answers():
     g, _ = load_golden("kat4_toy_fixed")
     assert g["rews"][:3].tolist() == [[-2, 1, 1, -2], [0, 1, 1, 0], [-4] * 4]
     assert g["pos_x"][4].tolist() == [5.5, 10.0, 9.25, 12.5]
+
+
+def test_ia_penalty_sum_matches_reference():
+    """oracle/shaping.py::ia_penalty_sum against outputs of the reference's utils/misc.py function."""
+    import json
+    import os
+    from golden_util import GOLDEN_DIR
+    from oracle.shaping import ia_penalty_sum
+    cases = json.load(open(os.path.join(GOLDEN_DIR, "shaping_ia_sums.json")))
+    assert len(cases) > 60
+    for c in cases:
+        assert ia_penalty_sum(c["ia"]) == c["sum"]
