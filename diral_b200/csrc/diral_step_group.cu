@@ -57,7 +57,7 @@ struct GroupSmem {
     __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd)
     {
         int o = 0;
-        off_script = o; o += align16i(G * R);          // merge script: one byte per (pass, lane)
+        off_script = o; o += align16i(G * (R + 1));    // merge script: one byte per (pass, lane), + 1 spare row
         off_txm = o;    o += align16i(4 * R);          // transmitter mask of every resource
         off_recv = o;   o += align16i(4 * G);          // packets received per transmitter (my_step_ch)
         off_sx = o;   o += align16i(8 * G);
@@ -272,7 +272,7 @@ step_group_kernel(const Params p)
     // transmitters, visited in ascending id with strict '<' (first wins ties): the two lowest are
     // compared branch-free, a third and later ones are rare.  Pure (no stores), so two resources can be
     // in flight at once.
-    auto decide = [&](auto flat_c, int r, unsigned txm, int &tstar, float &o) {
+    auto decide = [&](auto flat_c, int r, unsigned txm, int &tstar, float &o, unsigned &more) {
         constexpr bool FL = decltype(flat_c)::value;
         const bool is_tx = (a == r);
         const unsigned cand = (act && !is_tx) ? (inr_mask & txm) : 0u;
@@ -285,53 +285,58 @@ step_group_kernel(const Params p)
         const double d2 = dist_t<FL>(sx[t2], sy[t2], x, y);
         tstar = t1;
         if (d2 < best) { best = d2; tstar = t2; }
-        for (unsigned m = rest & (rest - 1u); m; m &= m - 1u) {
-            const int t = __ffs(m) - 1;
-            const double d = dist_t<FL>(sx[t], sy[t], x, y);
-            if (d < best) { best = d; tstar = t; }
+        more = rest & (rest - 1u);                       // a third, fourth .. candidate: finished by the caller
+        if (more) {                                      // (rare; kept out of line of the two-resource schedule)
+            for (unsigned m = more; m; m &= m - 1u) {
+                const int t = __ffs(m) - 1;
+                const double d = dist_t<FL>(sx[t], sy[t], x, y);
+                if (d < best) { best = d; tstar = t; }
+            }
         }
         if (!cand || !(best < sentinel)) { tstar = -1; best = sentinel; }              // network.py:385
-        if (tstar >= 0) ++n_recv;
+        n_recv += tstar >= 0 ? 1 : 0;
         // channel observation (test_env.py:203-240 / :305-306 / :431)
-        o = 0.0f;
-        if (!is_tx && txm) {
-            if (MODE == MODE_STEP) o = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
-            else o = 1.0f;
-        }
+        float ov = 1.0f;
+        if (MODE == MODE_STEP) ov = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
+        o = (!is_tx && txm) ? ov : 0.0f;
     };
     // side effects of one resource, in resource order
     auto commit = [&](int r, unsigned txm, int tstar, float o) {
         obs_row[r] = o;
-        if (txm == 0u) return;
-        if (LAT) {                                                                    // network.py:394
-            const bool is_rx = act && a != r;
-            for (unsigned m = txm; m; m &= m - 1) {
-                const int t = __ffs(m) - 1;
-                if (is_rx && !((inr_mask >> t) & 1u)) latp[t * N] = -1;
+        if (LAT || MODE == MODE_CH) {
+            if (txm != 0u) {
+                if (LAT) {                                                            // network.py:394
+                    const bool is_rx = act && a != r;
+                    for (unsigned m = txm; m; m &= m - 1) {
+                        const int t = __ffs(m) - 1;
+                        if (is_rx && !((inr_mask >> t) & 1u)) latp[t * N] = -1;
+                    }
+                    if (MODE == MODE_CH && tstar >= 0) latp[tstar * N] = (int32_t)p.timestep;    // test_env.py:436
+                }
+                if (MODE == MODE_CH && tstar >= 0) smem_red_inc(&recv_s[tstar]);      // test_env.py:396-397
             }
-            if (MODE == MODE_CH && tstar >= 0) latp[tstar * N] = (int32_t)p.timestep;    // test_env.py:436
         }
-        if (MODE == MODE_CH && tstar >= 0) smem_red_inc(&recv_s[tstar]);              // test_env.py:396-397
-        // table merge (vehicle.py:35-47) is deferred: log which row this lane merges in this pass
+        // table merge (vehicle.py:35-47) is deferred: log which row this lane merges in this pass.  The row
+        // of an empty pass is written too but not counted, so the next pass overwrites it.
         if (merge_mode) {
             script[npass * G + u] = (unsigned char)(tstar >= 0 ? tstar : u);
-            ++npass;
+            npass += txm != 0u ? 1 : 0;
         }
     };
     auto run_decisions = [&](auto flat_c) {
         int r = 0;
         for (; r + 2 <= R; r += 2) {
             const unsigned m0 = txm_s[r], m1 = txm_s[r + 1];
-            int ts0, ts1; float o0, o1;
-            decide(flat_c, r, m0, ts0, o0);
-            decide(flat_c, r + 1, m1, ts1, o1);
+            int ts0, ts1; float o0, o1; unsigned mo0, mo1;
+            decide(flat_c, r, m0, ts0, o0, mo0);
+            decide(flat_c, r + 1, m1, ts1, o1, mo1);
             commit(r, m0, ts0, o0);
             commit(r + 1, m1, ts1, o1);
         }
         if (r < R) {
             const unsigned m0 = txm_s[r];
-            int ts0; float o0;
-            decide(flat_c, r, m0, ts0, o0);
+            int ts0; float o0; unsigned mo0;
+            decide(flat_c, r, m0, ts0, o0, mo0);
             commit(r, m0, ts0, o0);
         }
     };
