@@ -356,6 +356,7 @@ int diral_step(void *handle, int mode, const int32_t *actions, int64_t timestep,
     const bool fused = build_state && fused_state_ok(h->cfg);
     diral::Params p = h->base;
     p.mode = mode; p.timestep = timestep; p.episode = episode; p.epsilon = epsilon; p.seed = seed;
+    p.tick = (int)(h->ticks + 1);
     p.build_state = fused ? 1 : 0;
     p.actions = actions; p.gen_actions = actions == nullptr; p.actions_out = actions_out;
     if (mode == DIRAL_MY_STEP_CH && h->bufs.lat) h->lat_live = true;
@@ -480,6 +481,7 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
     for (auto &ev : h->pipe_ev) if (!ev) DIRAL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     diral::Params p = h->base;
     p.mode = mode; p.timestep = timestep; p.episode = episode; p.epsilon = epsilon; p.seed = 0;
+    p.tick = (int)(h->ticks + 1);
     p.build_state = 1; p.actions = h->d_actions; p.gen_actions = 0; p.actions_out = nullptr;
     if (mode == DIRAL_MY_STEP_CH && h->bufs.lat) h->lat_live = true;
     p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;

@@ -38,6 +38,7 @@ struct Params {
     int mode, track_lat, build_state, gen_actions;
     int prefetch_ahead;       // envs between this CTA's env and the one that will reuse its SM slot
     long long timestep;
+    int tick;                 // table ticks since the reset including this slot (= every vehicle's own seq)
     double episode, epsilon;
     unsigned long long seed;
     // device memory

@@ -409,16 +409,46 @@ step_group_kernel(const Params p)
             }
         }
         unsigned key[SL];
+        // Two columns per register when every sequence number of the slab is either 0 (never heard) or
+        // within FMAX slots of the newest possible one: then  fresh = seq - base  fits 16 - SB bits, the
+        // order of the packed halves equals the order of the 32-bit keys, and one shuffle + one
+        // VIMNMX.U16x2 merge two entries.  Slabs holding older information take the 32-bit path.
+        constexpr int FMAX = (1 << (16 - SB)) - 1;
+        const int base = p.tick - FMAX;
+        bool narrow = true;
 #pragma unroll
         for (int q = 0; q < SL; ++q) {
             if (jbase + q == u) sb[q] += 1;                                       // vehicle.py:58 (tick)
-            key[q] = ((unsigned)sb[q] << SB) | (unsigned)u;
+            narrow = narrow && (sb[q] == 0 || (unsigned)(sb[q] - base - 1) < (unsigned)FMAX);
         }
-        // replay the passes in order on this slab's columns
-        for (int pp = 0; pp < npass; ++pp) {
-            const int srcl = script[pp * G + u];
+        if ((SL & 1) == 0 && (__ballot_sync(gmask, !narrow) & gmask) == 0u) {
+            unsigned k2[SL / 2 > 0 ? SL / 2 : 1];
 #pragma unroll
-            for (int q = 0; q < SL; ++q) key[q] = max(key[q], __shfl_sync(gmask, key[q], srcl, G));
+            for (int i = 0; i < SL / 2; ++i) {
+                const unsigned f0 = sb[2 * i] ? (unsigned)(sb[2 * i] - base) : 0u;
+                const unsigned f1 = sb[2 * i + 1] ? (unsigned)(sb[2 * i + 1] - base) : 0u;
+                k2[i] = ((f0 << SB) | (unsigned)u) | (((f1 << SB) | (unsigned)u) << 16);
+            }
+            for (int pp = 0; pp < npass; ++pp) {
+                const int srcl = script[pp * G + u];
+#pragma unroll
+                for (int i = 0; i < SL / 2; ++i) k2[i] = __vmaxu2(k2[i], __shfl_sync(gmask, k2[i], srcl, G));
+            }
+#pragma unroll
+            for (int q = 0; q < SL; ++q) {
+                const unsigned hk = (k2[q / 2] >> (16 * (q & 1))) & 0xffffu;
+                const unsigned f = hk >> SB;
+                key[q] = ((f ? f + (unsigned)base : 0u) << SB) | (hk & (unsigned)(G - 1));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < SL; ++q) key[q] = ((unsigned)sb[q] << SB) | (unsigned)u;
+            // replay the passes in order on this slab's columns
+            for (int pp = 0; pp < npass; ++pp) {
+                const int srcl = script[pp * G + u];
+#pragma unroll
+                for (int q = 0; q < SL; ++q) key[q] = max(key[q], __shfl_sync(gmask, key[q], srcl, G));
+            }
         }
         // gather xpos from the origin row, age, write back (independent per column => ILP)
 #pragma unroll

@@ -303,3 +303,28 @@ def test_reward_shaping_epilogue(opts):
             assert np.allclose(_np(shaped)[e], r64.astype(np.float32), rtol=1e-6, atol=1e-6), (t, e)
             assert np.allclose(_np(sums)[e], [sum_r, coll, ia_sum], rtol=1e-12, atol=1e-9), (t, e)
     env.close()
+
+
+def test_long_run_with_stale_entries():
+    """2 300 slots on a sparse highway: table entries older than 2 047 slots appear, so slabs fall back
+    from the packed 16-bit replay to the 32-bit one (and mix both within one table).  Integer state must
+    stay bit-exact against the oracle throughout."""
+    from oracle.c_oracle import COracle
+    kw = dict(num_users=24, num_channels=6, highway_length=6000, reward_design=2, communication_range=250,
+              mobility=True, bin_range=500, State=_shipped_state())
+    E, T, seed = 6, 2300, 21
+    orc = COracle(num_envs=E, **kw)
+    orc.reset_philox(seed)
+    env = _env(E, seed=seed, **kw)
+    for t in range(T):
+        a = orc.philox_actions(seed, t)
+        o_ref, r_ref = orc.step("my_step", a, t)
+        env._step("my_step", a, t, True)
+        if t % 100 == 99 or t > T - 40:
+            s_ref = orc.obtain_state(o_ref, a, r_ref)
+            _close32(_np(env._state), s_ref, "state", t, exact=True)
+            assert (_np(env.tab_seq) == orc.tab_seq).all(), "seq table, slot %d" % t
+            assert (_np(env.tab_lu) == orc.tab_lu).all(), "last_updated table, slot %d" % t
+            assert (_np(env.tab_x) == orc.tab_x).all(), "xpos table, slot %d" % t
+    stale = (orc.tab_seq > 0) & (orc.tab_seq <= T - 2047)
+    assert stale.any(), "the scenario must contain entries older than the packed key range"
