@@ -4,31 +4,41 @@
 // vehicle u both as a receiver and as the owner of row u of the neighbour table.  The slot splits
 // into a DECISION phase that never touches the table and a TABLE phase that streams it once:
 //
-//   A  load actions / kinematics and kick off the loads of the first table slab
-//   C1 for r = 0..R-1 in order (reference envs/test_env.py:147): ballot the transmitters on r (the
-//      per-resource collision histogram, test_env.py:149-157), what their reward needs, the nearest
-//      in-range transmitter of every other lane (Network.find_closest_tx, network.py:378-398), channel
-//      observation, last_arrival_time; every pass in which somebody receives appends one row
-//      ts[pass][u] = "lane whose row u merges" to a small shared-memory script
+//   A  load actions / kinematics; prefetch this env's whole table (and the next env's inputs) to L2
+//   C1 decisions.  __match_any_sync on the actions gives every lane its collision set (the
+//      per-resource collision histogram, reference envs/test_env.py:149-157) in one instruction, so all
+//      three reward models are lane-local.  An in-range bitmask over all G candidates is built once; then
+//      for r = 0..R-1 in order (test_env.py:147), two resources in flight: nearest in-range transmitter
+//      (Network.find_closest_tx, network.py:378-398) = lowest candidate bit, second lowest compared
+//      branch-free, further ones in a rare loop; channel observation; last_arrival_time; every
+//      non-empty pass appends one byte per lane ("which row does lane u merge") to a shared-memory script
 //   D  mobility (Network.update_positions, network.py:189-206)
 //   C2/E per slab of 8 table columns (subject-major storage => every access is one coalesced G*4 or
-//      G*8 byte segment; the next slab's loads are in flight while this one computes):
+//      G*8 byte segment; the next slab's seq column and this slab's last_updated / xpos are requested
+//      before the replay loop, so their latency hides behind it):
 //        tick (Vehicle.periodic_update, vehicle.py:56-70) and pack  key = seq << log2 G | origin-row
-//        replay the script IN PASS ORDER -- the passes are a true sequential dependency (SURVEY.md
-//        2b), but table COLUMNS are independent, so a slab can run all passes by itself:
-//            key[q] = max(key[q], shfl(key[q], ts[pass][u]))            (Vehicle.received_update,
-//        vehicle.py:35-47: one shuffle + one integer max per entry).  (xpos, ypos) of an entry is a
-//        pure function of (subject, seq), so the max-by-seq join never moves positions: the key's low
-//        bits remember which row held that version when the slot began.
-//        then gather xpos from the origin row by shuffle, last_updated bookkeeping, write
+//        (two columns per register -- 16-bit "freshness" keys -- unless the slab holds entries older
+//        than 2^(16 - log2 G) slots), replay the script IN PASS ORDER -- the passes are a true
+//        sequential dependency, but table COLUMNS are independent, so a slab can run all
+//        passes by itself:   key[q] = max(key[q], shfl(key[q], script[pass][u]))
+//        (Vehicle.received_update, vehicle.py:35-47: one shuffle + one integer max per entry or entry
+//        pair).  (xpos, ypos) of an entry is a pure function of (subject, seq), so the max-by-seq join
+//        never moves positions: the key's low bits remember which row held that version when the slot
+//        began.  Then gather xpos from the origin row by shuffle, last_updated bookkeeping, write
 //        seq / last_updated / xpos back, and bin the view-based positional distribution
-//        (Network.get_positional_dist_2_piggy + dist_piggy, network.py:473-513,538-558)
+//        (Network.get_positional_dist_2_piggy + dist_piggy, network.py:473-513,538-558) with
+//        fire-and-forget shared-memory reductions
 //   F  TestEnv.obtain_state (test_env.py:527-583): assemble [E][N][S] float32 rows in shared memory
 //      and write obs / rewards / state with coalesced float4 stores.
 //
+// Every hot loop is written as ONE basic block (compile-time FLAT variants for the "all vehicles on one
+// lane" case, unconditional reductions into a dummy histogram row, predicated selects instead of
+// branches): the kernel is bound by instruction latency, and ptxas only interleaves independent
+// columns / resources inside a basic block.
+//
 // HBM traffic per env-slot is the algorithmic minimum SURVEY.md 8(d) states: the table is read once
 // and written once (16 B per entry each way), everything else is O(N).  Only one slab of keys lives
-// in registers at a time, which is what lets ~20 warps stay resident per SM.
+// in registers at a time (16 warps resident per SM at ~118 registers).
 //
 // FULL (N == G) instantiations drop every "is this lane / column live" predicate and turn all
 // table addresses into compile-time offsets from one base pointer.
