@@ -50,7 +50,7 @@ struct BlockSmem {
         off_sxn = o;   o += align16z(8 * (size_t)N);          // post-mobility x, for the helper threads
         off_edges = o; o += align16z(8 * (size_t)(B + 1));
         off_txm = o;   o += align16z(4 * (size_t)R * NW);
-        off_pairs = o; o += align16z(2 * 2 * (size_t)N);         // two pass lists of (rx << 8 | tx)
+        off_pairs = o; o += align16z(2 * 8 * (size_t)N);         // two pass lists of (rx row offset, tx row offset)
         off_misc = o;  o += 16;                                  // list lengths of passes pc, pc+1, pc+2, pc+3
         off_recv = o;  o += align16z(4 * (size_t)N);
         off_red = o;   o += align16z(8 * 4 * 32);
@@ -90,7 +90,12 @@ __device__ __noinline__ int block_reward_weight(const Params &p, const double *s
 
 // H helper copies of the N-thread team: thread (h, u).  Team 0 makes the decisions; all teams share the
 // column merges (receptions k = h, h+H, .. of a pass), the key loads and the epilogue column blocks.
-template <int NW> struct Helpers { static constexpr int v = NW <= 4 ? 4 : 2; };
+#ifndef DIRAL_BLOCK_HELPERS
+// measured on B200 (profiles/README.md): no helpers up to 64 vehicles, 4 teams up to 128, 2 beyond
+template <int NW> struct Helpers { static constexpr int v = NW <= 2 ? 1 : (NW <= 4 ? 4 : 2); };
+#else
+template <int NW> struct Helpers { static constexpr int v = (NW * 32 * DIRAL_BLOCK_HELPERS <= 1024) ? DIRAL_BLOCK_HELPERS : 1024 / (NW * 32); };
+#endif
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32 * Helpers<NW>::v, (NW * 32 * Helpers<NW>::v <= 512 ? 2 : 1))
@@ -117,7 +122,7 @@ step_block_kernel(const Params p, const int SB, const int keys_in_smem)
     double *sxn = reinterpret_cast<double *>(smem_raw + lay.off_sxn);
     double *s_edges = reinterpret_cast<double *>(smem_raw + lay.off_edges);
     unsigned *txm_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_txm);         // [R][NW]
-    unsigned short *pairs = reinterpret_cast<unsigned short *>(smem_raw + lay.off_pairs);   // [2][N]
+    uint2 *pairs = reinterpret_cast<uint2 *>(smem_raw + lay.off_pairs);               // [2][N] byte offsets of (rx row, tx row)
     int *npairs = reinterpret_cast<int *>(smem_raw + lay.off_misc);                 // [4], indexed by pass & 3
     unsigned *recv_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_recv);
     double *s_red = reinterpret_cast<double *>(smem_raw + lay.off_red);
@@ -261,28 +266,27 @@ step_block_kernel(const Params p, const int SB, const int keys_in_smem)
                 int basep = 0;
                 if (lane == 0 && bm) basep = atomicAdd(&npairs[slot], __popc(bm));
                 basep = __shfl_sync(0xffffffffu, basep, 0);
-                if (has) pairs[parity * N + basep + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)((u << 8) | tstar);
+                if (has) pairs[parity * N + basep + __popc(bm & ((1u << lane) - 1u))] = make_uint2((unsigned)(u * ld * 4), (unsigned)(tstar * ld * 4));
                 // the counter of pass pc+2: its last readers (pass pc-2) are all past barrier pc-1, and its
                 // next writers come after barrier pc+1
                 if (tid == 0) npairs[(pc + 2) & 3] = 0;
                 __syncthreads();
                 const int np = npairs[slot];
                 if (col) {           // team h applies receptions h, h+H, .. of this pass to column j = u
-                    const unsigned short *pl = pairs + parity * N;
-                    unsigned *Kj = K + u;
+                    const uint2 *pl = pairs + parity * N;
+                    char *Kj = reinterpret_cast<char *>(K + u);
+                    auto at = [&](unsigned off) -> unsigned & { return *reinterpret_cast<unsigned *>(Kj + off); };
                     int k = h;
                     for (; k + 3 * H < np; k += 4 * H) {     // receptions of one pass are independent
-                        const unsigned p0 = pl[k], p1 = pl[k + H], p2 = pl[k + 2 * H], p3 = pl[k + 3 * H];
-                        const unsigned a0 = Kj[(p0 >> 8) * ld], b0 = Kj[(p0 & 255u) * ld];
-                        const unsigned a1 = Kj[(p1 >> 8) * ld], b1 = Kj[(p1 & 255u) * ld];
-                        const unsigned a2 = Kj[(p2 >> 8) * ld], b2 = Kj[(p2 & 255u) * ld];
-                        const unsigned a3 = Kj[(p3 >> 8) * ld], b3 = Kj[(p3 & 255u) * ld];
-                        Kj[(p0 >> 8) * ld] = max(a0, b0); Kj[(p1 >> 8) * ld] = max(a1, b1);
-                        Kj[(p2 >> 8) * ld] = max(a2, b2); Kj[(p3 >> 8) * ld] = max(a3, b3);
+                        const uint2 p0 = pl[k], p1 = pl[k + H], p2 = pl[k + 2 * H], p3 = pl[k + 3 * H];
+                        const unsigned a0 = at(p0.x), b0 = at(p0.y), a1 = at(p1.x), b1 = at(p1.y);
+                        const unsigned a2 = at(p2.x), b2 = at(p2.y), a3 = at(p3.x), b3 = at(p3.y);
+                        at(p0.x) = max(a0, b0); at(p1.x) = max(a1, b1);
+                        at(p2.x) = max(a2, b2); at(p3.x) = max(a3, b3);
                     }
                     for (; k < np; k += H) {
-                        const unsigned p0 = pl[k];
-                        Kj[(p0 >> 8) * ld] = max(Kj[(p0 >> 8) * ld], Kj[(p0 & 255u) * ld]);
+                        const uint2 p0 = pl[k];
+                        at(p0.x) = max(at(p0.x), at(p0.y));
                     }
                 }
                 ++pc;
@@ -459,7 +463,13 @@ step_block_kernel(const Params p, const int SB, const int keys_in_smem)
 }
 
 int block_threads(int N) { return ((N + 31) / 32) * 32; }
-int helpers_for(int N) { return block_threads(N) / 32 <= 4 ? 4 : 2; }
+int helpers_for(int N)
+{
+    switch (block_threads(N) / 32) {
+    case 1: return Helpers<1>::v; case 2: return Helpers<2>::v; case 3: return Helpers<3>::v; case 4: return Helpers<4>::v;
+    case 5: return Helpers<5>::v; case 6: return Helpers<6>::v; case 7: return Helpers<7>::v; default: return Helpers<8>::v;
+    }
+}
 
 template <int NW>
 cudaError_t prepare_nw(const Params &p, size_t smem)
