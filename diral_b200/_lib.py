@@ -66,6 +66,7 @@ SYMBOLS = {
     "diral_information_age": (C.c_int, [_P, _I64, _P, _P]),
     "diral_episode_metrics": (C.c_int, [_P, _I64, _P, _P]),
     "diral_shape_rewards": (C.c_int, [_P, C.POINTER(DiralShaping), _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "diral_ring_gather": (C.c_int, [_P, _I64, _I64, _I64, _I32, _P, _I32, _I32, _P, _P]),
     "diral_step_host": (C.c_int, [_P, C.c_int, _P, _I64, _D, _D, _P, _P, _P, _P]),
     "diral_launch_count": (C.c_int64, [_P]),
 }

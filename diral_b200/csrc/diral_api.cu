@@ -449,6 +449,17 @@ int diral_shape_rewards(void *handle, const diral_shaping *cfg, const int32_t *a
     return DIRAL_OK;
 }
 
+int diral_ring_gather(const void *ring, int64_t capacity, int64_t agents, int64_t width, int32_t elem_bytes,
+                      const int64_t *start, int32_t batch, int32_t step, void *out, void *stream)
+{
+    if (!ring || !start || !out) return fail(DIRAL_ERR_ARG, "ring/start/out must not be NULL");
+    if (capacity < 1 || agents < 1 || width < 1 || batch < 1 || step < 1 || elem_bytes < 1)
+        return fail(DIRAL_ERR_ARG, "capacity/agents/width/batch/step/elem_bytes must be >= 1");
+    DIRAL_CUDA(diral::launch_ring_gather(ring, capacity, agents, width, elem_bytes, reinterpret_cast<const long long *>(start),
+                                         batch, step, out, static_cast<cudaStream_t>(stream)));
+    return DIRAL_OK;
+}
+
 int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
                     float *h_state, float *h_rews, float *h_obs, void *stream)
 {

@@ -3,6 +3,9 @@
 #include "diral_dev.cuh"
 #include "diral_launch.h"
 
+#include <algorithm>
+#include <cstdint>
+
 namespace diral {
 
 namespace {
@@ -355,6 +358,58 @@ cudaError_t launch_shape_rewards(const Params &p, const ShapingArgs &s, cudaStre
 {
     const int threads = p.N <= 32 ? 32 : (p.N <= 128 ? 128 : 256);
     shape_rewards_kernel<<<(unsigned)p.E, threads, 0, stream>>>(p, s);
+    return cudaGetLastError();
+}
+
+}  // namespace diral
+
+// ---- device-resident replay ring (reference utils/memory.py:162-194 + drl_drqn.py:294-377) ------------
+namespace diral {
+
+namespace {
+
+// out[(a * batch + b) * step + k][0..width) = ring[(start[b] + k) mod capacity][a][0..width)
+// One warp per (a, b, k) row group; `width` elements of `VEC` bytes move as coalesced vectors.
+template <typename V>
+__global__ void ring_gather_kernel(const V *__restrict__ ring, long long capacity, long long agents, int width,
+                                   const long long *__restrict__ start, int batch, int step, V *__restrict__ out)
+{
+    const long long rows = agents * batch * step;
+    const int lane = threadIdx.x & 31;
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const int k = (int)(row % step);
+        const long long ab = row / step;
+        const int b = (int)(ab % batch);
+        const long long a = ab / batch;
+        long long slot = (start[b] + k) % capacity;
+        if (slot < 0) slot += capacity;
+        const V *src = ring + (slot * agents + a) * width;
+        V *dst = out + row * width;
+        for (int i = lane; i < width; i += 32) dst[i] = src[i];
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_ring_gather(const void *ring, long long capacity, long long agents, long long width, int elem_bytes,
+                               const long long *start, int batch, int step, void *out, cudaStream_t stream)
+{
+    const long long rows = agents * batch * step;
+    if (rows <= 0 || width <= 0) return cudaSuccess;
+    const long long row_bytes = width * elem_bytes;
+    const int threads = 256;
+    const unsigned grid = (unsigned)std::min<long long>((rows + 7) / 8, 148LL * 32);
+    const bool a16 = (row_bytes % 16 == 0) && ((uintptr_t)ring % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    if (a16)
+        ring_gather_kernel<uint4><<<grid, threads, 0, stream>>>(static_cast<const uint4 *>(ring), capacity, agents,
+                                                                (int)(row_bytes / 16), start, batch, step, static_cast<uint4 *>(out));
+    else if (row_bytes % 4 == 0)
+        ring_gather_kernel<uint32_t><<<grid, threads, 0, stream>>>(static_cast<const uint32_t *>(ring), capacity, agents,
+                                                                   (int)(row_bytes / 4), start, batch, step, static_cast<uint32_t *>(out));
+    else
+        ring_gather_kernel<uint8_t><<<grid, threads, 0, stream>>>(static_cast<const uint8_t *>(ring), capacity, agents,
+                                                                  (int)row_bytes, start, batch, step, static_cast<uint8_t *>(out));
     return cudaGetLastError();
 }
 

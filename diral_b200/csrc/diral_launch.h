@@ -34,5 +34,7 @@ cudaError_t launch_update_velocity(const Params &p, double *vel, const int8_t *d
 cudaError_t launch_information_age(const Params &p, int32_t *out, cudaStream_t stream);
 cudaError_t launch_episode_metrics(const Params &p, double *out110, cudaStream_t stream);
 cudaError_t launch_shape_rewards(const Params &p, const ShapingArgs &s, cudaStream_t stream);
+cudaError_t launch_ring_gather(const void *ring, long long capacity, long long agents, long long width, int elem_bytes,
+                               const long long *start, int batch, int step, void *out, cudaStream_t stream);
 
 }  // namespace diral

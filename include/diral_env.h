@@ -154,6 +154,17 @@ int diral_shape_rewards(void *handle, const diral_shaping *cfg, const int32_t *a
                         float *rewards, int64_t *sum_ia_prev, int32_t *ia_counter, int32_t *prev_actions,
                         double *slot_sums, int32_t *ia_out, void *stream);
 
+/* Device-resident replay ring, the second "next" row of SURVEY.md 8(f): the window gather behind
+ * Memory.sample (utils/memory.py:177-194) fused with the learners' regrouping loops
+ * (algorithms/drl_drqn.py:294-377, which turn batch x step x user tuples into [user][batch][step][...]).
+ * ring:  [capacity][agents][width] elements of elem_bytes (states: width = S float32; actions / rewards:
+ *        width = 1); a batched env folds its env axis into the agent axis (agents = E * N).
+ * start: device int64 [batch], first ring slot of every sampled window (np.random.choice(len - step) on the host).
+ * out:   [agents * batch][step][width], row (a * batch + b) = agent a in window b -- the layout
+ *        drl_drqn.py:235-238 reshapes to.  No handle: it touches no environment state. */
+int diral_ring_gather(const void *ring, int64_t capacity, int64_t agents, int64_t width, int32_t elem_bytes,
+                      const int64_t *start, int32_t batch, int32_t step, void *out, void *stream);
+
 /* Host-buffer convenience for callers that keep data on the CPU (the reference's learners do):
  * copies h_actions in, runs diral_step(build_state=1), copies state/rews (and obs if not NULL) out,
  * synchronises the stream.  Host pointers should be pinned for full PCIe bandwidth. */

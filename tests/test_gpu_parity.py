@@ -328,3 +328,35 @@ def test_long_run_with_stale_entries():
             assert (_np(env.tab_x) == orc.tab_x).all(), "xpos table, slot %d" % t
     stale = (orc.tab_seq > 0) & (orc.tab_seq <= T - 2047)
     assert stale.any(), "the scenario must contain entries older than the packed key range"
+
+
+@pytest.mark.parametrize("share", [True, False])
+def test_replay_ring_matches_reference_memory(share):
+    """diral_b200.replay.Memory (ring tensors + diral_ring_gather) against the restated reference Memory
+    + regrouping loops, fed by a real env rollout; the ring wraps several times."""
+    from diral_b200.replay import Memory
+    from oracle.replay import Memory as RefMemory, regroup
+    kw = dict(num_users=6, num_channels=5, highway_length=1170, reward_design=2, communication_range=250,
+              mobility=True, bin_range=500, State=_shipped_state())
+    E, CAP, T, BATCH, STEP = 3, 16, 70, 5, 4
+    env = _env(E, seed=2, **kw)
+    A, S = E * 6, env.S
+    mem = Memory(CAP, agents=A, state_space=S, device="cuda", share_next_state=share)
+    ref = RefMemory(CAP)
+    state = env.obtain_state(env._obs, env.sample(0), env._rews).clone()
+    rs = np.random.RandomState(8)
+    for t in range(T):
+        a = env.sample(t)
+        nxt, rew, _ = env.step(a)
+        nxt, rew = nxt.clone(), rew.clone()
+        mem.add((state, a, rew, nxt))
+        ref.add((_np(state).reshape(A, S), _np(a).reshape(A), _np(rew).reshape(A), _np(nxt).reshape(A, S)))
+        state = nxt
+        if t > BATCH + STEP and t % 7 == 0:
+            batch, idx = ref.sample(BATCH, STEP, rng=rs)
+            got = mem.sample(BATCH, STEP, idx=idx)
+            for field, name in enumerate(("states", "actions", "rewards", "next_states")):
+                want = regroup(batch, field, A)                          # [A][batch][step][...]
+                want = want.reshape((A * BATCH, STEP) + want.shape[3:])
+                assert (_np(got[name]) == want).all(), (name, t)
+    assert len(mem) == CAP and mem.count == T

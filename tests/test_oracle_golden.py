@@ -71,3 +71,27 @@ def test_ia_penalty_sum_matches_reference():
     assert len(cases) > 60
     for c in cases:
         assert ia_penalty_sum(c["ia"]) == c["sum"]
+
+
+def test_replay_memory_matches_reference():
+    """oracle/replay.py::Memory against windows sampled by the reference's utils/memory.py::Memory."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from oracle.replay import Memory, regroup
+    g = np.load(os.path.join(GOLDEN_DIR, "replay_memory.npz"))
+    N, S, CAP, T, BATCH, STEP = (int(v) for v in g["shape"])
+    mem = Memory(max_size=CAP)
+    k = 0
+    for t in range(T):
+        mem.add((g["states"][t], g["actions"][t], g["rewards"][t], g["states"][t + 1]))
+        if k < len(g["at"]) and t == int(g["at"][k]):
+            rs = np.random.RandomState(100 + t)
+            batch, idx = mem.sample(BATCH, STEP, rng=rs)
+            assert (idx == g["idx"][k]).all()
+            flat = np.array([[np.concatenate([e[0].ravel(), e[1].ravel(), e[2].ravel(), e[3].ravel()]) for e in w]
+                             for w in batch])
+            assert (flat == g["samples"][k]).all()
+            st = regroup(batch, 0, N)
+            assert st.shape == (N, BATCH, STEP, S) and (st[2, 1, 0] == batch[1][0][0][2]).all()
+            k += 1
+    assert k == len(g["at"]) and k > 3
