@@ -360,3 +360,63 @@ def test_replay_ring_matches_reference_memory(share):
                 want = want.reshape((A * BATCH, STEP) + want.shape[3:])
                 assert (_np(got[name]) == want).all(), (name, t)
     assert len(mem) == CAP and mem.count == T
+
+
+def _random_config(rs):
+    n = int(rs.choice([1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 23, 31, 32, 33, 40, 64, 65, 96]))
+    r = int(rs.choice([1, 2, 3, 5, 8, 13, 20, 33]))
+    st = _shipped_state(add_action=bool(rs.rand() < 0.8), action_index=["binary", "real"][int(rs.rand() < 0.3)],
+                        add_channel_obs=bool(rs.rand() < 0.5), add_reward=bool(rs.rand() < 0.5),
+                        add_index=bool(rs.rand() < 0.3), add_velocity=bool(rs.rand() < 0.3),
+                        add_position=bool(rs.rand() < 0.3), add_positional_dist=bool(rs.rand() < 0.2) and n > 1,
+                        add_positional_dist_piggy=bool(rs.rand() < 0.85),
+                        add_positional_dist_type=int(rs.choice([1, 2, 2, 2])), num_bins=int(rs.choice([1, 3, 10, 20, 37])))
+    if not any(st[k] for k in ("add_action", "add_channel_obs", "add_reward", "add_index", "add_velocity", "add_position",
+                               "add_positional_dist", "add_positional_dist_piggy")):
+        st["add_action"] = True
+    kw = dict(num_users=n, num_channels=r, highway_length=float(rs.choice([60, 400, 1500, 5000])),
+              reward_design=int(rs.choice([1, 2, 2, 3, 4, 5])), communication_range=float(rs.choice([80, 250, 900])),
+              bin_range=float(rs.choice([150, 500])), mobility=bool(rs.rand() < 0.9),
+              congestion_test=bool(rs.rand() < 0.25), enable_fingerprint=bool(rs.rand() < 0.2), State=st)
+    mode = str(rs.choice(["my_step", "my_step", "my_step_ch", "my_step_design"]))
+    if mode == "my_step_ch" and kw["reward_design"] not in (2, 3, 4):
+        kw["reward_design"] = 2
+    return kw, mode
+
+
+@pytest.mark.parametrize("case", range(36))
+def test_random_configurations_against_oracle(case):
+    """Random small configurations (vehicle counts around every kernel boundary, every State flag, all
+    reward designs and modes, static and mobile, toy and non-toy), every output compared every slot."""
+    from oracle.c_oracle import COracle
+    rs = np.random.RandomState(1000 + case)
+    kw, mode = _random_config(rs)
+    E, T, seed = int(rs.choice([1, 3, 10])), 22, 40 + case
+    orc = COracle(num_envs=E, **kw)
+    x0, y0, v0 = orc.reset_philox(seed)
+    if rs.rand() < 0.3:                     # two-lane topologies exercise the general (sqrt) distance path
+        y0 = rs.randint(0, 3, size=y0.shape).astype(np.float64)
+        orc.reset(x0, y0, v0)
+    variants = _variants(kw["num_users"])
+    envs = [_env(E, variant=v, seed=seed, **kw) for v in variants]
+    for env in envs:
+        env.reset(init=(x0, y0, v0))
+    exact_rewards = kw["reward_design"] in (1, 2, 5) or mode == "my_step_design"
+    piggy = kw["State"]["add_positional_dist_piggy"]
+    for t in range(T):
+        a = orc.philox_actions(seed, t)
+        o_ref, r_ref = orc.step(mode, a, t)
+        s_ref = orc.obtain_state(o_ref, a, r_ref, t // 5, 0.9 ** t)
+        for env in envs:
+            env._step(mode, a, t, True, t // 5, 0.9 ** t)
+            _close32(_np(env._obs), o_ref, "obs", t)
+            _close32(_np(env._rews), r_ref, "rews", t, exact=exact_rewards)
+            _close32(_np(env._state), s_ref, "state", t)
+            assert (_np(env.pos_x) == orc.pos_x).all(), "pos_x, slot %d" % t
+            if piggy:
+                assert (_np(env.tab_seq) == orc.tab_seq).all(), "seq table, slot %d" % t
+                assert (_np(env.tab_lu) == orc.tab_lu).all(), "last_updated table, slot %d" % t
+                assert (_np(env.tab_x) == orc.tab_x).all(), "xpos table, slot %d" % t
+            assert (_np(env.lat) == orc.lat).all(), "last_arrival_time, slot %d" % t
+    for env in envs:
+        env.close()
