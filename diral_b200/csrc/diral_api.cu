@@ -168,7 +168,7 @@ diral::Params env_range(const diral::Params &p, long long e0, long long n)
     if (q.lat) q.lat += e0 * NN;
     q.obs += e0 * N * p.R; q.rews += e0 * N; q.state += e0 * N * p.S;
     q.acc_reward += e0; q.acc_count += e0 * diral::ACC_COUNTS;
-    if (q.scratch) q.scratch += e0 * N * (N + 1);
+    if (q.scratch) q.scratch += e0 * (long long)diral::step_block_scratch_words_per_env(p.N);
     return q;
 }
 

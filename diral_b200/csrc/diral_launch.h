@@ -15,12 +15,13 @@ size_t step_group_smem_bytes(const Params &p);
 cudaError_t prepare_step_group(const Params &p);
 cudaError_t launch_step_group(const Params &p, cudaStream_t stream);
 
-// any N <= 256: one CTA per environment, table keys in shared memory or scratch (diral_step_block.cu)
+// any N <= 256: persistent CTAs, one environment at a time, table keys in shared memory or scratch (diral_step_block.cu)
 constexpr int BLOCK_MAX_N = 256;
 int key_src_bits(int N);
 size_t step_block_smem_bytes(const Params &p, bool keys_in_smem);
 bool step_block_keys_fit_smem(const Params &p);
 size_t step_block_scratch_bytes(long long E, int N);
+size_t step_block_scratch_words_per_env(int N);
 cudaError_t prepare_step_block(const Params &p);
 cudaError_t launch_step_block(const Params &p, cudaStream_t stream);
 

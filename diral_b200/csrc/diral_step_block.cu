@@ -1,71 +1,85 @@
-// diral_step_block.cu -- fused time-slot kernel for 32 < N <= 256 vehicles (one CTA per environment).
+// diral_step_block.cu -- fused time-slot kernel for 32 < N <= 256 vehicles (one CTA per environment,
+// persistent CTAs that walk the environments of the launch).
 //
-// Same slot semantics and the same ideas as diral_step_group.cu, re-mapped for rows that no longer
-// fit one warp.  Thread u is vehicle u; the packed table keys  seq << SB | origin-row  live in shared
-// memory as K[u][j] with an odd row stride (or in the scratch buffer when 4*N*(N+1) bytes do not fit).
+// Same slot semantics as diral_step_group.cu, re-mapped for rows that no longer fit one warp.  The packed
+// table keys  seq << SB | origin-row  live in shared memory as K[observer i][subject j] (row stride LD,
+// rows 16 B aligned), or in an L2-resident scratch slice per CTA when they do not fit.
 //
-//   A   inputs, whole-table L2 prefetch, transmitter masks per resource (the per-resource collision
-//       histogram, reference envs/test_env.py:149-157) by shared-memory atomicOr, keys from the seq
-//       columns (coalesced), in-range bitmask of every vehicle (NW = N/32 words per thread)
-//   C   for r = 0..R-1 in order:
-//         every thread finds its nearest in-range transmitter on r (Network.find_closest_tx,
-//         network.py:378-398) from  inr & txm[r]  and appends (receiver, transmitter) to the pass list;
-//         ONE barrier; then the CTA turns around -- thread j owns table COLUMN j and applies the
-//         pass's merges to it sequentially (Vehicle.received_update, vehicle.py:35-47):
-//             K[rx][j] = max(K[rx][j], K[tx][j])
-//         Columns are independent and a pass never modifies a transmitter's row, so no second barrier
-//         is needed (the pass list is double-buffered) and the accesses are conflict-free.
-//       channel observations leave through a per-warp 32x32 transpose tile as coalesced 128 B rows
-//   D   mobility
-//   E   thread u = observer again: stream the columns CB at a time -- gather xpos from the origin row
-//       through a double-buffered shared-memory column buffer (one barrier per CB columns), age, write
-//       back, bin the positional distribution (network.py:473-513) with shared-memory reductions
-//   F   state rows are staged in the (now free) key region and written as contiguous float4s
-//
-// Reward models are lane-local exactly as in the group kernel: a thread's collision set is txm[a].
+//   A   inputs -> shared memory; keys from the seq columns (one warp per subject column, coalesced);
+//       in-range bit mask of every vehicle (Network.check_communicaiton_range, network.py:595-607), thread
+//       (u, w) forms word w of vehicle u against warp-uniform candidate positions
+//   B   DECISIONS, no table access.  Resources are taken RC at a time.  Transmitter masks per resource (the
+//       per-resource collision histogram, envs/test_env.py:149-157) by shared-memory atomicOr, copied to a
+//       per-vehicle "who shares my resource" mask.  Channel observations start as coalesced rows of the
+//       no-reception value.  Then thread (u, w) walks the in-range vehicles t of word w: every t transmits
+//       on exactly one resource, so t is u's nearest in-range transmitter there (Network.find_closest_tx,
+//       network.py:378-398) unless another in-range vehicle shares t's resource -- the common case costs a
+//       few mask words, no search.  Winners store the distance and append (u, t) to the list of pass a[t]
+//   C   MERGES, resource passes in ascending order (they are a true dependency: Vehicle.periodic_update
+//       aliases the transmitted table, vehicle.py:61).  One warp per reception applies
+//       Vehicle.received_update (vehicle.py:35-47) to the whole row with vector accesses:
+//           K[rx][:] = max(K[rx][:], K[tx][:])
+//       conflict-free, exactly the merges that happen; one barrier per non-empty pass (a pass never modifies
+//       a transmitter's row and a receiver appears once per pass)
+//   D   rewards (lane-local: a vehicle's collision set is txm[a]) and mobility
+//   E   one warp per subject column: xpos is gathered from the origin row through a per-warp column buffer
+//       (an entry's position is a pure function of (subject, seq)), ages, write-back, and the positional
+//       distribution (network.py:473-513) binned with shared-memory reductions -- no CTA barrier inside
+//   F   state rows (TestEnv.obtain_state, test_env.py:527-583): one warp per row, coalesced stores
 #include "diral_dev.cuh"
 #include "diral_launch.h"
 
 #include <algorithm>
-#include <type_traits>
 
 namespace diral {
 
 namespace {
 
-constexpr int CB = 2;                        // table columns per thread per epilogue barrier
-constexpr unsigned short PAIR_NONE = 0xFFFFu;
+// compile-time geometry of the NW-warp instantiation (N <= 32 NW vehicles)
+__host__ __device__ constexpr int geo_lpr(int nw) { return nw <= 1 ? 4 : nw <= 2 ? 8 : nw <= 4 ? 16 : 32; }  // lanes per reception in a row merge (8 key words each)
+__host__ __device__ constexpr int geo_ld(int nw) { return 8 * geo_lpr(nw) + 4; }                              // key row stride (words)
+__host__ __device__ constexpr int geo_threads(int nw) { return nw <= 1 ? 128 : nw <= 2 ? 256 : 512; }
+__host__ __device__ constexpr int geo_nwp(int nw) { return nw | 1; }                                         // odd stride of the bit-mask rows
+__host__ __device__ constexpr int geo_rc(int nw) { return ((256 / nw) & ~31) < 32 ? 32 : ((256 / nw) & ~31); } // resources per decision chunk
 
-__host__ __device__ inline size_t align16z(size_t x) { return (x + 15) & ~(size_t)15; }
-
+// Shared-memory carve-up.  Everything the hot loops touch sits at an offset that depends on the
+// instantiation only (a compile-time constant inside the kernel: addresses fold into the instructions
+// instead of being recomputed under register pressure); the arrays sized by the runtime bin count follow.
+__host__ __device__ constexpr size_t align16c(size_t x) { return (x + 15) & ~(size_t)15; }
 struct BlockSmem {
-    size_t off_sx, off_sy, off_sxn, off_edges, off_txm, off_pairs, off_misc, off_recv, off_red, off_union, off_keys, bytes;
-    size_t union_bytes, keys_bytes;
-    __host__ __device__ BlockSmem(int N, int R, int B, int TN, int H, bool vpd_state, bool keys_in_smem)
+    size_t off_sx, off_sy, off_sxn, off_sa, off_rew, off_recv, off_txm, off_cnt, off_inr, off_own, off_red, off_union,
+        off_keys, off_edges, off_hist, bytes;
+    size_t keys_bytes, list_bytes;
+    __host__ __device__ constexpr BlockSmem(int B, int nw, bool vpd_state, bool keys_in_smem)
+        : off_sx(0), off_sy(0), off_sxn(0), off_sa(0), off_rew(0), off_recv(0), off_txm(0), off_cnt(0), off_inr(0), off_own(0),
+          off_red(0), off_union(0), off_keys(0), off_edges(0), off_hist(0), bytes(0), keys_bytes(0), list_bytes(0)
     {
-        const int NW = TN / 32, T = TN;
+        const int T = nw * 32, NWP = geo_nwp(nw), RC = geo_rc(nw), NWARPS = geo_threads(nw) / 32;
         size_t o = 0;
-        off_sx = o;    o += align16z(8 * (size_t)N);
-        off_sy = o;    o += align16z(8 * (size_t)N);
-        off_sxn = o;   o += align16z(8 * (size_t)N);          // post-mobility x, for the helper threads
-        off_edges = o; o += align16z(8 * (size_t)(B + 1));
-        off_txm = o;   o += align16z(4 * (size_t)R * NW);
-        off_pairs = o; o += align16z(2 * 8 * (size_t)N);         // two pass lists of (rx row offset, tx row offset)
-        off_misc = o;  o += 16;                                  // list lengths of passes pc, pc+1, pc+2, pc+3
-        off_recv = o;  o += align16z(4 * (size_t)N);
-        off_red = o;   o += align16z(8 * 4 * 32);
-        // phase-disjoint: the obs transpose tiles (phase C) share space with histogram + column buffer (E)
-        const size_t tiles = 4 * (size_t)NW * 32 * 33;
-        const size_t epi = (vpd_state ? align16z(4 * (size_t)(B + 1) * T) : 0) + 2 * (size_t)H * CB * 8 * (size_t)N;
-        union_bytes = align16z(tiles > epi ? tiles : epi);
-        off_union = o; o += union_bytes;
-        keys_bytes = keys_in_smem ? align16z(4 * (size_t)N * (N + 1)) : 0;
+        off_sx = o;    o += align16c(8 * (size_t)T);
+        off_sy = o;    o += align16c(8 * (size_t)T);
+        off_sxn = o;   o += align16c(8 * (size_t)T);          // post-mobility x
+        off_sa = o;    o += align16c(4 * (size_t)T);          // actions
+        off_rew = o;   o += align16c(4 * (size_t)T);          // rewards (float)
+        off_recv = o;  o += align16c(4 * (size_t)T);          // receptions per transmitter, later VPD sample counts
+        off_txm = o;   o += align16c(4 * (size_t)RC * NWP);
+        off_cnt = o;   o += align16c(4 * (size_t)RC);
+        off_inr = o;   o += align16c(4 * (size_t)T * NWP);
+        off_own = o;   o += align16c(4 * (size_t)T * NWP);    // txm[a[t]] per vehicle t
+        off_red = o;   o += align16c(8 * 4 * 16 + 16);
+        // phase-disjoint: reception lists (B, C) and per-warp column buffers (E)
+        list_bytes = align16c(2 * (size_t)RC * T);
+        const size_t colx = 8 * (size_t)NWARPS * T;
+        off_union = o; o += align16c(list_bytes > colx ? list_bytes : colx);
+        keys_bytes = keys_in_smem ? align16c(4 * (size_t)T * geo_ld(nw)) : 0;      // sized by the padded vehicle count
         off_keys = o;  o += keys_bytes;
+        off_edges = o; o += align16c(8 * (size_t)(B + 1));
+        off_hist = o;  o += vpd_state ? align16c(4 * (size_t)B * T) : 0;
         bytes = o;
     }
 };
 
-constexpr size_t SMEM_BUDGET = 220 * 1024;
+constexpr size_t SMEM_BUDGET = 226 * 1024;
 
 // Network.calculate_reward_weights / calculate_avg_distance (network.py:273-316) over the
 // transmitters whose bits are set in m[0..NW), ascending ids, Python sum() semantics
@@ -88,401 +102,476 @@ __device__ __noinline__ int block_reward_weight(const Params &p, const double *s
     return p.toy ? (mean == norm) : (mean > p.C);
 }
 
-// H helper copies of the N-thread team: thread (h, u).  Team 0 makes the decisions; all teams share the
-// column merges (receptions k = h, h+H, .. of a pass), the key loads and the epilogue column blocks.
-#ifndef DIRAL_BLOCK_HELPERS
-// measured on B200 (profiles/README.md): no helpers up to 64 vehicles, 4 teams up to 128, 2 beyond
-template <int NW> struct Helpers { static constexpr int v = NW <= 2 ? 1 : (NW <= 4 ? 4 : 2); };
-#else
-template <int NW> struct Helpers { static constexpr int v = (NW * 32 * DIRAL_BLOCK_HELPERS <= 1024) ? DIRAL_BLOCK_HELPERS : 1024 / (NW * 32); };
-#endif
-
-template <int NW>
-__global__ void __launch_bounds__(NW * 32 * Helpers<NW>::v, (NW * 32 * Helpers<NW>::v <= 512 ? 2 : 1))
-step_block_kernel(const Params p, const int SB, const int keys_in_smem)
+// one lane's share of a key row: two 16 B pieces, LPR * 16 B apart (sub = lane within its reception group)
+template <int LPR, bool KS>
+__device__ __forceinline__ void row_load(const unsigned *row, int sub, uint4 &lo, uint4 &hi)
 {
-    constexpr int T = NW * 32;               // team size (threads that map to vehicles / columns)
-    constexpr int H = Helpers<NW>::v;
-    constexpr int TT = T * H;                // CTA size
+    const uint4 *q = reinterpret_cast<const uint4 *>(row) + sub;
+    if (KS) { lo = q[0]; hi = q[LPR]; } else { lo = __ldcg(q); hi = __ldcg(q + LPR); }
+}
+template <int LPR, bool KS>
+__device__ __forceinline__ void row_store(unsigned *row, int sub, const uint4 &lo, const uint4 &hi)
+{
+    uint4 *q = reinterpret_cast<uint4 *>(row) + sub;
+    if (KS) { q[0] = lo; q[LPR] = hi; } else { __stcg(q, lo); __stcg(q + LPR, hi); }
+}
+__device__ __forceinline__ uint4 max4(const uint4 &a, const uint4 &b)
+{
+    return make_uint4(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
+}
+
+template <int NW, bool KS>
+__global__ void __launch_bounds__(geo_threads(NW), 1024 / geo_threads(NW))
+step_block_kernel(const Params p, const int SB)
+{
+    constexpr int T = NW * 32;                    // padded vehicle count
+    constexpr int LPR = geo_lpr(NW), LD = geo_ld(NW), TT = geo_threads(NW), NWARPS = TT / 32;
+    constexpr int G = 32 / LPR;                   // receptions per warp and merge round
+    constexpr int NWP = geo_nwp(NW), RC = geo_rc(NW);
     const int N = p.N, R = p.R, B = p.B, S = p.S;
-    const int tid = threadIdx.x, h = tid / T, u = tid - h * T, lane = tid & 31, warp = u >> 5;
-    const bool col = u < N;                  // a valid vehicle / column index
-    const bool act = col && h == 0;          // ... and the thread that decides for it
-    const long long e = blockIdx.x;
-    const long long vbase = e * N, tbase = e * (long long)N * N;
+    int tid;      // read once through an opaque asm: ptxas otherwise re-reads SR_TID.X inside the hot loops
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool act = tid < N;                     // thread u = vehicle u for the per-vehicle work
     const bool want_state = p.build_state != 0;
     const bool vpd = want_state && p.vpd_enabled;
-    const int ld = N + 1;
     const int mode = p.mode;
+    const bool merge_mode = p.piggy && (mode != MODE_STEP || p.state_type == 1 || p.state_type == 2);
+    const double Cr = p.C, sentinel = p.sentinel;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const BlockSmem lay(N, R, B, T, H, p.vpd_enabled != 0, keys_in_smem != 0);
-    double *sx = reinterpret_cast<double *>(smem_raw + lay.off_sx);
-    double *sy = reinterpret_cast<double *>(smem_raw + lay.off_sy);
-    double *sxn = reinterpret_cast<double *>(smem_raw + lay.off_sxn);
-    double *s_edges = reinterpret_cast<double *>(smem_raw + lay.off_edges);
-    unsigned *txm_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_txm);         // [R][NW]
-    uint2 *pairs = reinterpret_cast<uint2 *>(smem_raw + lay.off_pairs);               // [2][N] byte offsets of (rx row, tx row)
-    int *npairs = reinterpret_cast<int *>(smem_raw + lay.off_misc);                 // [4], indexed by pass & 3
-    unsigned *recv_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_recv);
-    double *s_red = reinterpret_cast<double *>(smem_raw + lay.off_red);
-    float *tile = reinterpret_cast<float *>(smem_raw + lay.off_union) + warp * 32 * 33;     // phase C
-    unsigned *hist = reinterpret_cast<unsigned *>(smem_raw + lay.off_union);                // phase E
-    double *colbuf = reinterpret_cast<double *>(smem_raw + lay.off_union + (p.vpd_enabled ? align16z(4 * (size_t)(B + 1) * T) : 0));
-    unsigned *K = keys_in_smem ? reinterpret_cast<unsigned *>(smem_raw + lay.off_keys)
-                               : p.scratch + (size_t)e * N * ld;
+    constexpr BlockSmem fix(0, NW, false, KS);    // offsets up to the keys do not depend on the bin count
+    const BlockSmem lay(B, NW, p.vpd_enabled != 0, KS);
+    double *sx = reinterpret_cast<double *>(smem_raw + fix.off_sx);
+    double *sy = reinterpret_cast<double *>(smem_raw + fix.off_sy);
+    double *sxn = reinterpret_cast<double *>(smem_raw + fix.off_sxn);
+    double *s_edges = reinterpret_cast<double *>(smem_raw + fix.off_edges);
+    int *sa = reinterpret_cast<int *>(smem_raw + fix.off_sa);
+    float *s_rew = reinterpret_cast<float *>(smem_raw + fix.off_rew);
+    unsigned *recv_s = reinterpret_cast<unsigned *>(smem_raw + fix.off_recv);
+    unsigned *txm_s = reinterpret_cast<unsigned *>(smem_raw + fix.off_txm);            // [RC][NWP]
+    int *cnt_s = reinterpret_cast<int *>(smem_raw + fix.off_cnt);                      // [RC] receptions of a pass
+    unsigned *inr_s = reinterpret_cast<unsigned *>(smem_raw + fix.off_inr);            // [N][NWP]
+    unsigned *own_s = reinterpret_cast<unsigned *>(smem_raw + fix.off_own);            // [N][NWP]
+    double *s_red = reinterpret_cast<double *>(smem_raw + fix.off_red);                // [16][4]
+    unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + fix.off_red + 8 * 4 * 16); // received, pairs, bad
+    unsigned *hist = reinterpret_cast<unsigned *>(smem_raw + lay.off_hist);            // [B][T]
+    unsigned short *list = reinterpret_cast<unsigned short *>(smem_raw + fix.off_union);   // [RC][T]  rx << 8 | tx
+    double *colx = reinterpret_cast<double *>(smem_raw + fix.off_union) + warp * T;    // phase E
+    unsigned *K;
+    if constexpr (KS) K = reinterpret_cast<unsigned *>(smem_raw + fix.off_keys);
+    else K = p.scratch + (size_t)blockIdx.x * N * LD;
     const unsigned srcmask = (1u << SB) - 1u;
 
-    // ---- A: inputs ---------------------------------------------------------------------------------
-    int a = -1; double x = 0.0, y = 0.0, v = 0.0; int bad = 0;
-    if (act) {
-        if (!p.gen_actions) a = p.actions[vbase + u];
-        x = p.pos_x[vbase + u]; y = p.pos_y[vbase + u]; v = p.vel[vbase + u];
-    }
-    if (p.piggy) {    // this environment's whole table towards L2 while the decisions run
-        const char *b0 = reinterpret_cast<const char *>(p.tab_seq + tbase);
-        const char *b1 = reinterpret_cast<const char *>(p.tab_lu + tbase);
-        const char *b2 = reinterpret_cast<const char *>(p.tab_x + tbase);
+    for (int i = tid; i <= B; i += TT) s_edges[i] = p.edges[i];
+
+    // HBM -> L2 ahead of use: an environment's ages and positions while its decisions and merges run
+    // (they are first touched in phase E), the NEXT environment's sequence numbers during phase E
+    auto prefetch_rest = [&](long long ee) {
+        const char *b1 = reinterpret_cast<const char *>(p.tab_lu + ee * N * N);
+        const char *b2 = reinterpret_cast<const char *>(p.tab_x + ee * N * N);
         const int bytes4 = N * N * 4;
         for (int o = tid * 128; o < bytes4; o += TT * 128) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + o));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + bytes4 + o));
         }
-        (void)b0;     // the seq columns are read right below
-    }
-    for (int i = tid; i <= B; i += TT) s_edges[i] = p.edges[i];
-    for (int i = tid; i < R * NW; i += TT) txm_s[i] = 0u;
-    if (tid < 4) npairs[tid] = 0;
-    if (act) {
-        if (p.gen_actions) a = philox_action(p.seed, u, p.env0 + e, p.timestep, R);
-        if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
-        if (p.gen_actions && p.actions_out) p.actions_out[vbase + u] = a;
-        sx[u] = x; sy[u] = y; recv_s[u] = 0u;
-    }
-    __syncthreads();
-    if (act) atomicOr(&txm_s[a * NW + warp], 1u << lane);            // test_env.py:149-157
-    if (p.piggy && col) {
-        const int32_t *seqp = p.tab_seq + tbase + u;
-#pragma unroll 8
-        for (int j = h; j < N; j += H) {
-            int s = seqp[j * N];
-            if (j == u) s += 1;                                      // vehicle.py:58 (tick)
-            K[u * ld + j] = ((unsigned)s << SB) | (unsigned)u;
-        }
-    }
-    // every vehicle on the same lane of the highway?  (dy == 0 for every pair => dist == |dx| exactly)
-    const double y0 = sy[0];
-    const bool flat = __syncthreads_and(!act || y == y0) != 0;       // also publishes txm_s and K
-    const bool flat0 = flat && y0 == 0.0;
-
-    // who is within communication range of this vehicle (network.py:595-607)
-    unsigned inr[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) inr[w] = 0u;
-    const double Cr = p.C, sentinel = p.sentinel;
-    if (act) {
-        if (flat) {
-#pragma unroll
-            for (int w = 0; w < NW; ++w)
-                for (int b = 0; b < 32 && w * 32 + b < N; ++b)
-                    if (fabs(__dsub_rn(x, sx[w * 32 + b])) < Cr) inr[w] |= 1u << b;
-        } else {
-#pragma unroll
-            for (int w = 0; w < NW; ++w)
-                for (int b = 0; b < 32 && w * 32 + b < N; ++b)
-                    if (dist2d(sx[w * 32 + b], sy[w * 32 + b], x, y) < Cr) inr[w] |= 1u << b;
-        }
-    }
-    unsigned own[NW]; int my_tot = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) { own[w] = act ? txm_s[a * NW + w] : 0u; my_tot += __popc(own[w]); }
-
-    // toy reward: first-min-x / first-max-x vehicle (network.py:225-246)
-    double norm = 0.0;
-    if (p.toy && mode == MODE_STEP && act && my_tot > 1 && design_needs_weight(p.reward_design, my_tot)) {
-        double xmin = p.L + 1.0, xmax = -p.L - 1.0; int imin = 0, imax = 0;
-        for (int t = 0; t < N; ++t) {
-            if (sx[t] < xmin) { xmin = sx[t]; imin = t; }
-            if (sx[t] > xmax) { xmax = sx[t]; imax = t; }
-        }
-        norm = dist2d(sx[imin], sy[imin], sx[imax], sy[imax]);
-    }
-
-    // ---- C: resources in ascending order -----------------------------------------------------------
-    int n_recv = 0, n_pairs = 0;
-    int32_t *latp = p.track_lat ? p.lat + tbase + u : nullptr;       // lat[t][u] = latp[t * N]
-    const bool merge_mode = p.piggy && (mode != MODE_STEP || p.state_type == 1 || p.state_type == 2);
-    float *og = p.obs + vbase * R;
-    int pc = 0;                               // non-empty passes so far (uniform)
-    auto flush_tile = [&](int r_end) {       // rows of the 32x32 tile -> coalesced 128 B segments of obs
-        if (h != 0) return;
-        const int r0 = (r_end - 1) & ~31, nr = r_end - r0;
-        __syncwarp();
-        for (int i = 0; i < 32; ++i) {
-            const int uu = warp * 32 + i;
-            if (uu < N && lane < nr) og[(long long)uu * R + r0 + lane] = tile[i * 33 + lane];
-        }
-        __syncwarp();
     };
-    for (int r = 0; r < R; ++r) {
-        unsigned txm[NW]; unsigned any = 0u;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) { txm[w] = txm_s[r * NW + w]; any |= txm[w]; }
-        float o = 0.0f;
-        if (any != 0u) {
-            const bool is_rx = act && a != r;
-            // candidates = in-range transmitters; nearest in ascending id with strict '<' (first wins)
-            double best = sentinel; int tstar = -1;
-            if (is_rx) {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    unsigned c = inr[w] & txm[w];
-                    n_pairs += __popc(c);
-                    for (; c; c &= c - 1) {
-                        const int t = w * 32 + __ffs(c) - 1;
-                        const double d = flat ? fabs(__dsub_rn(x, sx[t])) : dist2d(sx[t], sy[t], x, y);
-                        if (d < best) { best = d; tstar = t; }
-                    }
-                }
-                if (latp) {                                                          // network.py:394
-#pragma unroll
-                    for (int w = 0; w < NW; ++w)
-                        for (unsigned c = txm[w] & ~inr[w]; c; c &= c - 1) latp[(w * 32 + __ffs(c) - 1) * N] = -1;
-                    if (mode == MODE_CH && tstar >= 0) latp[tstar * N] = (int32_t)p.timestep;   // test_env.py:436
-                }
-                if (tstar >= 0) {
-                    ++n_recv;
-                    if (mode == MODE_CH) atomicAdd(&recv_s[tstar], 1u);             // test_env.py:396-397
-                }
-                if (mode == MODE_STEP) o = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
-                else o = 1.0f;
-            }
-            // pass list, warp-aggregated append (order inside a pass is irrelevant)
-            if (merge_mode) {
-                const bool has = tstar >= 0;
-                const int parity = pc & 1, slot = pc & 3;
-                const unsigned bm = __ballot_sync(0xffffffffu, has);
-                int basep = 0;
-                if (lane == 0 && bm) basep = atomicAdd(&npairs[slot], __popc(bm));
-                basep = __shfl_sync(0xffffffffu, basep, 0);
-                if (has) pairs[parity * N + basep + __popc(bm & ((1u << lane) - 1u))] = make_uint2((unsigned)(u * ld * 4), (unsigned)(tstar * ld * 4));
-                // the counter of pass pc+2: its last readers (pass pc-2) are all past barrier pc-1, and its
-                // next writers come after barrier pc+1
-                if (tid == 0) npairs[(pc + 2) & 3] = 0;
-                __syncthreads();
-                const int np = npairs[slot];
-                if (col) {           // team h applies receptions h, h+H, .. of this pass to column j = u
-                    const uint2 *pl = pairs + parity * N;
-                    char *Kj = reinterpret_cast<char *>(K + u);
-                    auto at = [&](unsigned off) -> unsigned & { return *reinterpret_cast<unsigned *>(Kj + off); };
-                    int k = h;
-                    for (; k + 3 * H < np; k += 4 * H) {     // receptions of one pass are independent
-                        const uint2 p0 = pl[k], p1 = pl[k + H], p2 = pl[k + 2 * H], p3 = pl[k + 3 * H];
-                        const unsigned a0 = at(p0.x), b0 = at(p0.y), a1 = at(p1.x), b1 = at(p1.y);
-                        const unsigned a2 = at(p2.x), b2 = at(p2.y), a3 = at(p3.x), b3 = at(p3.y);
-                        at(p0.x) = max(a0, b0); at(p1.x) = max(a1, b1);
-                        at(p2.x) = max(a2, b2); at(p3.x) = max(a3, b3);
-                    }
-                    for (; k < np; k += H) {
-                        const uint2 p0 = pl[k];
-                        at(p0.x) = max(at(p0.x), at(p0.y));
-                    }
-                }
-                ++pc;
-            }
-        }
-        if (h == 0) tile[lane * 33 + (r & 31)] = o;
-        if ((r & 31) == 31 || r == R - 1) flush_tile(r + 1);
-    }
-    __syncthreads();                          // keys final; recv_s complete; tiles free for the epilogue
+    auto prefetch_seq = [&](long long ee) {
+        const char *b0 = reinterpret_cast<const char *>(p.tab_seq + ee * N * N);
+        for (int o = tid * 128; o < N * N * 4; o += TT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + o));
+    };
 
-    // rewards (test_env.py:159-199 / :294-302 / :408-429), all lane-local
-    double rew = 0.0;
-    if (act) {
-        if (mode == MODE_STEP) {
-            if (my_tot <= 1) rew = 1.0;
-            else {
-                int w = 0;
-                if (design_needs_weight(p.reward_design, my_tot)) w = block_reward_weight<NW>(p, sx, sy, own, norm);
-                rew = collision_reward_step(p.reward_design, my_tot, w);
-            }
-        } else if (mode == MODE_DESIGN) {
-            if (my_tot <= 1) rew = 1.0;
-            else {   // TestEnv.calculate_reward_design (test_env.py:319-349)
-                int k = 1, last = u;
-                for (int w = 0; w < NW; ++w)
-                    for (unsigned m = own[w]; m; m &= m - 1) {
-                        const int t = w * 32 + __ffs(m) - 1;
-                        if (t != u && dist2d(x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
-                    }
-                if (k == 1) rew = 1.0;
-                else if (k == 2) rew = (dist2d(x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
-                else rew = -(double)k;
-            }
-        } else {
-            // PRR (test_env.py:384-405): receivers in range = own in-range bits outside the collision set
-            int in_range = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const unsigned livew = (w * 32 + 32 <= N) ? 0xffffffffu : ((w * 32 < N) ? ((1u << (N - w * 32)) - 1u) : 0u);
-                in_range += __popc(inr[w] & ~own[w] & livew);
-            }
-            rew = channel_reward(p.reward_design, max(my_tot, 1), (int)recv_s[u], in_range);
-        }
-        p.rews[vbase + u] = (float)rew;
-    }
+    for (long long e = blockIdx.x; e < p.E; e += gridDim.x) {
+        const long long vbase = e * N, tbase = e * (long long)N * N;
 
-    // ---- D: mobility -------------------------------------------------------------------------------
-    double x_new = act ? mobility_step(p, x, v, u) : 0.0;
-    if (act) { if (p.mobility) p.pos_x[vbase + u] = x_new; sxn[u] = x_new; recv_s[u] = 0u; }   // recv_s now sums m_cnt
-    __syncthreads();
-    if (col && h != 0) { x = sx[u]; y = sy[u]; x_new = sxn[u]; }
-
-    // ---- E: stream the columns (thread u = observer) -----------------------------------------------
-    int m_cnt = 0;
-    if (vpd && h == 0) { for (int k = 0; k <= B; ++k) hist[k * T + u] = 0u; }
-    __syncthreads();
-    if (p.piggy) {
-        int32_t *seqp = p.tab_seq + tbase + u, *lup = p.tab_lu + tbase + u;
-        double *xp = p.tab_x + tbase + u;
-        const double W = p.W, inv_binw = p.inv_binw;
-        int buf = 0;
-        for (int jb0 = 0; jb0 < N; jb0 += H * CB) {
-            const int jb = jb0 + h * CB;         // this team's columns of the block
-            int s0[CB], lu[CB], sn[CB]; double xo[CB]; unsigned key[CB];
-            double *cb = colbuf + ((size_t)buf * H + h) * CB * N;
-#pragma unroll
-            for (int c = 0; c < CB; ++c) {
-                const int j = jb + c;
-                s0[c] = 0; lu[c] = 0; xo[c] = 0.0; key[c] = 0u;
-                if (col && j < N) {
-                    s0[c] = seqp[j * N]; lu[c] = lup[j * N]; xo[c] = xp[j * N];
-                    if (j == u) { s0[c] += 1; lu[c] = 0; xo[c] = x; } else lu[c] += 1;     // vehicle.py:58-70
-                    key[c] = K[u * ld + j];
-                    cb[c * N + u] = xo[c];
-                }
-            }
-            __syncthreads();                  // column buffer complete (double-buffered: one barrier per CB)
-#pragma unroll
-            for (int c = 0; c < CB; ++c) {
-                const int j = jb + c;
-                if (col && j < N) {
-                    sn[c] = (int)(key[c] >> SB);
-                    double xn = xo[c];
-                    if (sn[c] != s0[c]) { xn = cb[c * N + (int)(key[c] & srcmask)]; lu[c] = 0; }   // vehicle.py:41-47
-                    seqp[j * N] = sn[c]; lup[j * N] = lu[c]; xp[j * N] = xn;
-                    if (vpd) {
-                        bool in = j != u && lu[c] < p.age_threshold;                      // network.py:547
-                        double sv;
-                        if (flat0) { sv = __dsub_rn(xn, x_new); in = in && fabs(sv) < W; }
-                        else {
-                            const double d = dist2d(xn, sn[c] > 0 ? sy[j] : 0.0, x_new, y);
-                            in = in && d < W;                                             // network.py:487
-                            sv = (__dsub_rn(xn, x_new) > 0.0) ? d : -d;
-                        }
-                        if (in) {
-                            // trunc(t) is NumPy's edge-corrected bin unless t is within 1e-6 of an edge
-                            const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
-                            const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
-                            const int kb = (fabs(__dsub_rn(t, rt)) < 1e-6) ? vpd_bin(sv, W, inv_binw, B, s_edges)
-                                                                           : min(max((int)t, 0), B - 1);
-                            atomicAdd(&hist[kb * T + u], 1u);
-                            ++m_cnt;
-                        }
-                    }
-                }
-            }
-            buf ^= 1;
-        }
-    }
-    if (col && m_cnt) atomicAdd(&recv_s[u], (unsigned)m_cnt);
-    __syncthreads();                          // every thread is done with the keys: the region becomes staging
-    if (act) m_cnt = (int)recv_s[u];
-
-    // ---- F: state rows (TestEnv.obtain_state, test_env.py:527-583) ---------------------------------
-    if (want_state) {
-        const bool staged = keys_in_smem && (size_t)N * S * 4 <= lay.keys_bytes;
-        float *st = reinterpret_cast<float *>(smem_raw + lay.off_keys);
-        float *wp = staged ? st + u * S : p.state + (vbase + u) * S;
+        // ---- A: inputs -----------------------------------------------------------------------------
+        int a = 0; double x = 0.0, y = 0.0, v = 0.0; int bad = 0;
         if (act) {
-            const float *orow = og + (long long)u * R;   // written by this thread's own warp; visible after the barriers
-            if (p.add_action) {
-                if (p.action_binary) { for (int r = 0; r < R; ++r) *wp++ = (a == r) ? 1.0f : 0.0f; }
-                else *wp++ = (float)a;
-            }
-            if (p.add_channel_obs) { for (int r = 0; r < R; ++r) *wp++ = __ldcg(orow + r); }
-            if (p.piggy) {
-                const float den = (float)m_cnt, rcp = __frcp_rn(den);
-                const bool have = vpd && m_cnt > 0;
-                for (int b = 0; b < B; ++b) {
-                    const float c = have ? (float)hist[b * T + u] : 0.0f;
-                    const float q0 = __fmul_rn(c, rcp);
-                    *wp++ = have ? __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0) : 0.0f;
+            if (p.gen_actions) a = philox_action(p.seed, tid, p.env0 + e, p.timestep, R);
+            else a = p.actions[vbase + tid];
+            x = p.pos_x[vbase + tid]; y = p.pos_y[vbase + tid]; v = p.vel[vbase + tid];
+            if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
+            if (p.gen_actions && p.actions_out) p.actions_out[vbase + tid] = a;
+            sx[tid] = x; sy[tid] = y; sa[tid] = a; recv_s[tid] = 0u;
+        }
+        if (p.piggy) prefetch_rest(e);
+        if (vpd) for (int i = tid; i < B * T; i += TT) hist[i] = 0u;
+        if (tid < 3) s_tot[tid] = 0u;
+        // every vehicle on the same lane of the highway?  (dy == 0 for every pair => dist == |dx| exactly)
+        const double y0 = p.pos_y[vbase];
+        const bool flat = __syncthreads_and(!act || y == y0) != 0;     // also publishes sx, sy, sa
+        const bool flat0 = flat && y0 == 0.0;
+
+        // keys: K[i][j] = (seq[i][j] (+1 on the diagonal: the tick, vehicle.py:58)) << SB | i
+        if (p.piggy) {
+            const int32_t *seqg = p.tab_seq + tbase;
+#pragma unroll 2
+            for (int j = warp; j < N; j += NWARPS) {
+#pragma unroll
+                for (int q = 0; q < NW; ++q) {
+                    const int i = q * 32 + lane;
+                    if (i < N) {
+                        int s = seqg[j * N + i];
+                        if (i == j) s += 1;
+                        const unsigned key = ((unsigned)s << SB) | (unsigned)i;
+                        if (KS) K[i * LD + j] = key; else __stcg(K + i * LD + j, key);
+                    }
                 }
             }
-            if (p.add_reward) *wp++ = (float)rew;
-            if (p.add_index) *wp++ = (float)(u + 1);
-            if (p.add_position) { *wp++ = (float)__ddiv_rn(x_new, p.L); *wp++ = (float)__ddiv_rn(y, 2.0); }
-            if (p.add_velocity) *wp++ = (float)v;
-            if (p.fingerprint) { *wp++ = (float)p.episode; *wp++ = (float)p.epsilon; }
         }
-        if (staged) {
-            __syncthreads();
-            float *sg = p.state + vbase * S;
-            const int n = N * S;
-            if ((n & 3) == 0) {
-                for (int i = tid; i < n / 4; i += TT) reinterpret_cast<float4 *>(sg)[i] = reinterpret_cast<const float4 *>(st)[i];
-            } else {
-                for (int i = tid; i < n; i += TT) sg[i] = st[i];
+        // who is within communication range of whom (self included; it never counts as a candidate):
+        // thread (u, w) forms word w of vehicle u, the candidate positions are warp-uniform broadcasts
+        for (int it = tid; it < T * NW; it += TT) {
+            const int w = it / T, u = it - w * T;
+            if (u < N) {
+                const double xu = sx[u], yu = sy[u];
+                const int nb = min(32, N - w * 32);
+                unsigned m = 0u;
+                if (flat) {
+#pragma unroll 8
+                    for (int b = 0; b < nb; ++b) m |= (fabs(__dsub_rn(xu, sx[w * 32 + b])) < Cr ? 1u : 0u) << b;
+                } else {
+                    for (int b = 0; b < nb; ++b) m |= (dist2d(sx[w * 32 + b], sy[w * 32 + b], xu, yu) < Cr ? 1u : 0u) << b;
+                }
+                inr_s[u * NWP + w] = m;
             }
         }
-    }
 
-    // ---- per-env metric accumulators (fixed-order block reduction) ----------------------------------
-    {
-        double rs = act ? rew : 0.0; int nr = n_recv, np = n_pairs, nb = bad;
+        // ---- B + C: resources, RC at a time --------------------------------------------------------
+        int my_tot = 0, in_range = 0; double rew = 0.0;
+        int n_recv = 0, n_pairs = 0;
+        float *og = p.obs + vbase * R;
+        for (int r0 = 0; r0 < R; r0 += RC) {
+            const int rend = min(R, r0 + RC), nres = rend - r0;
+            for (int i = tid; i < nres * NWP; i += TT) txm_s[i] = 0u;
+            for (int i = tid; i < nres; i += TT) cnt_s[i] = 0;
+            __syncthreads();
+            const bool mine = act && a >= r0 && a < rend;
+            if (mine) atomicOr(&txm_s[(a - r0) * NWP + warp], 1u << lane);             // test_env.py:149-157
+            __syncthreads();
+
+            // rewards that need nothing but the collision set (test_env.py:159-199 / :294-302)
+            if (mine) {
+                unsigned own[NW], inr[NW];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            rs += __shfl_xor_sync(0xffffffffu, rs, o);
-            nr += __shfl_xor_sync(0xffffffffu, nr, o);
-            np += __shfl_xor_sync(0xffffffffu, np, o);
-            nb += __shfl_xor_sync(0xffffffffu, nb, o);
+                for (int w = 0; w < NW; ++w) { own[w] = txm_s[(a - r0) * NWP + w]; inr[w] = inr_s[tid * NWP + w]; my_tot += __popc(own[w]); }
+                if (mode == MODE_STEP) {
+                    if (my_tot <= 1) rew = 1.0;
+                    else {
+                        int wgt = 0;
+                        if (design_needs_weight(p.reward_design, my_tot)) {
+                            double norm = 0.0;
+                            if (p.toy) {   // first-min-x / first-max-x vehicle (network.py:225-246)
+                                double xmin = p.L + 1.0, xmax = -p.L - 1.0; int imin = 0, imax = 0;
+                                for (int t = 0; t < N; ++t) {
+                                    if (sx[t] < xmin) { xmin = sx[t]; imin = t; }
+                                    if (sx[t] > xmax) { xmax = sx[t]; imax = t; }
+                                }
+                                norm = dist2d(sx[imin], sy[imin], sx[imax], sy[imax]);
+                            }
+                            wgt = block_reward_weight<NW>(p, sx, sy, own, norm);
+                        }
+                        rew = collision_reward_step(p.reward_design, my_tot, wgt);
+                    }
+                } else if (mode == MODE_DESIGN) {
+                    if (my_tot <= 1) rew = 1.0;
+                    else {   // TestEnv.calculate_reward_design (test_env.py:319-349)
+                        int k = 1, last = tid;
+                        for (int w = 0; w < NW; ++w)
+                            for (unsigned m = own[w]; m; m &= m - 1) {
+                                const int t = w * 32 + __ffs(m) - 1;
+                                if (t != tid && dist2d(x, y, sx[t], sy[t]) < p.C2) { ++k; last = t; }
+                            }
+                        if (k == 1) rew = 1.0;
+                        else if (k == 2) rew = (dist2d(x, y, sx[last], sy[last]) > p.C2) ? 0.0 : -2.0;
+                        else rew = -(double)k;
+                    }
+                } else {
+                    // PRR (test_env.py:384-405): receivers in range = own in-range bits outside the collision set
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) in_range += __popc(inr[w] & ~own[w]);
+                }
+            }
+
+            // per-vehicle collision set; channel observations before any reception (coalesced rows)
+            if (mine) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) own_s[tid * NWP + w] = txm_s[(a - r0) * NWP + w];
+            }
+            {
+                const float basev = (mode != MODE_STEP || p.state_type == 1) ? 1.0f : (p.state_type == 2 ? (float)sentinel : 0.0f);
+                const int rcw = (nres + 31) >> 5;
+                for (int g = 0; g < rcw; ++g) {
+                    const int rl = g * 32 + lane, r = r0 + rl;
+                    unsigned any = 0u;
+                    if (rl < nres) {
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) any |= txm_s[rl * NWP + w];
+                    }
+                    if (rl < nres)
+                        for (int u = warp; u < N; u += NWARPS)
+                            og[(long long)u * R + r] = (any != 0u && sa[u] != r) ? basev : 0.0f;
+                }
+            }
+            __syncthreads();
+
+            // decisions: thread (u, w) walks the in-range vehicles t of word w
+            for (int it = tid; it < T * NW; it += TT) {
+                const int w = it / T, u = it - w * T;
+                if (u >= N) continue;
+                const int au = sa[u];
+                const double xu = sx[u], yu = sy[u];
+                unsigned inr[NW];
+#pragma unroll
+                for (int w2 = 0; w2 < NW; ++w2) inr[w2] = inr_s[u * NWP + w2];
+                unsigned mine_w = 0u;
+#pragma unroll
+                for (int w2 = 0; w2 < NW; ++w2) if (w2 == w) mine_w = inr[w2];
+                for (unsigned c = mine_w; c; c &= c - 1) {
+                    const int t = w * 32 + __ffs(c) - 1;
+                    const int at = sa[t];
+                    if (at == au || at < r0 || at >= rend) continue;          // u transmits there itself (half duplex)
+                    // in-range vehicles that share t's resource: candidates of find_closest_tx
+                    int ncand = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < NW; ++w2) ncand += __popc(inr[w2] & own_s[t * NWP + w2]);
+                    const double d = flat ? fabs(__dsub_rn(xu, sx[t])) : dist2d(sx[t], sy[t], xu, yu);
+                    bool win = d < sentinel;          // best starts at the sentinel (network.py:380)
+                    if (ncand > 1) {        // ascending ids, strict '<': the first minimum wins (network.py:384-391)
+                        for (int w2 = 0; w2 < NW; ++w2)
+                            for (unsigned c2 = inr_s[u * NWP + w2] & own_s[t * NWP + w2]; c2; c2 &= c2 - 1) {
+                                const int t2 = w2 * 32 + __ffs(c2) - 1;
+                                const double d2 = flat ? fabs(__dsub_rn(xu, sx[t2])) : dist2d(sx[t2], sy[t2], xu, yu);
+                                if (d2 < d || (d2 == d && t2 < t)) win = false;
+                            }
+                    }
+                    n_pairs += 1;
+                    if (win) {
+                        ++n_recv;
+                        const int rl = at - r0;
+                        if (mode == MODE_CH) {
+                            atomicAdd(&recv_s[t], 1u);                                     // test_env.py:396-397
+                            if (p.track_lat) p.lat[tbase + (long long)t * N + u] = (int32_t)p.timestep;   // test_env.py:436
+                        }
+                        if (mode == MODE_STEP && p.state_type == 2) og[(long long)u * R + at] = (float)d;
+                        if (merge_mode) {
+                            const int slot = atomicAdd(&cnt_s[rl], 1);
+                            list[rl * T + slot] = (unsigned short)((u << 8) | t);
+                        }
+                    }
+                }
+                if (p.track_lat) {                                                       // network.py:394
+                    const unsigned live = (w * 32 + 32 <= N) ? 0xffffffffu : ((1u << (N - w * 32)) - 1u);
+                    for (unsigned c = ~mine_w & live; c; c &= c - 1) {
+                        const int t = w * 32 + __ffs(c) - 1;
+                        const int at = sa[t];
+                        if (at != au && at >= r0 && at < rend) p.lat[tbase + (long long)t * N + u] = -1;
+                    }
+                }
+            }
+            __syncthreads();
+
+            // merges, pass by pass: G receptions per warp and round, LPR lanes per row
+            if (merge_mode) {
+                const int grp = lane / LPR, sub = lane - grp * LPR;
+                for (int rl = 0; rl < nres; ++rl) {
+                    const int np = cnt_s[rl];
+                    if (np == 0) continue;
+                    const unsigned short *pl = list + rl * T;
+                    for (int k0 = warp * G; k0 < np; k0 += NWARPS * G) {   // receptions of one pass are independent
+                        const int k = k0 + grp;
+                        if (k < np) {
+                            const unsigned en = pl[k];
+                            unsigned *ra = K + (en >> 8) * LD, *rb = K + (en & 255u) * LD;
+                            uint4 alo, ahi, blo, bhi;
+                            row_load<LPR, KS>(ra, sub, alo, ahi); row_load<LPR, KS>(rb, sub, blo, bhi);
+                            row_store<LPR, KS>(ra, sub, max4(alo, blo), max4(ahi, bhi));
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
         }
-        if (lane == 0 && h == 0) { s_red[warp * 4 + 0] = rs; s_red[warp * 4 + 1] = nr; s_red[warp * 4 + 2] = np; s_red[warp * 4 + 3] = nb; }
+        __syncthreads();                          // recv_s complete; txm/cnt/list free
+
+        // ---- D: rewards out, mobility ----------------------------------------------------------------
+        double x_new = 0.0;
+        if (act) {
+            if (mode == MODE_CH) rew = channel_reward(p.reward_design, max(my_tot, 1), (int)recv_s[tid], in_range);
+            p.rews[vbase + tid] = (float)rew;
+            s_rew[tid] = (float)rew;
+            x_new = mobility_step(p, x, v, tid);
+            if (p.mobility) p.pos_x[vbase + tid] = x_new;
+            sxn[tid] = x_new;
+        }
+        if (p.piggy && e + gridDim.x < p.E) prefetch_seq(e + gridDim.x);
         __syncthreads();
-        if (tid == 0) {
-            double trs = 0.0, tnr = 0.0, tnp = 0.0, tnb = 0.0;
-            for (int i = 0; i < NW; ++i) { trs += s_red[i * 4]; tnr += s_red[i * 4 + 1]; tnp += s_red[i * 4 + 2]; tnb += s_red[i * 4 + 3]; }
-            atomicAdd(p.acc_reward + e, trs);
-            unsigned long long *c = reinterpret_cast<unsigned long long *>(p.acc_count + e * ACC_COUNTS);
-            atomicAdd(c + 0, (unsigned long long)tnr); atomicAdd(c + 1, (unsigned long long)tnp);
-            atomicAdd(c + 2, (unsigned long long)tnb); atomicAdd(c + 3, 1ull);
+
+        // ---- E: one warp per subject column ------------------------------------------------------------
+        if (p.piggy) {
+            int32_t *seqg = p.tab_seq + tbase, *lug = p.tab_lu + tbase;
+            double *xg = p.tab_x + tbase;
+            const double W = p.W, inv_binw = p.inv_binw;
+            for (int j = warp; j < N; j += NWARPS) {
+                int s0[NW], lu[NW]; double xo[NW];
+                const double xj = sx[j], yj = sy[j];
+#pragma unroll
+                for (int q = 0; q < NW; ++q) {
+                    const int i = q * 32 + lane;
+                    s0[q] = 0; lu[q] = 0; xo[q] = 0.0;
+                    if (i < N) { s0[q] = __ldcs(seqg + j * N + i); lu[q] = __ldcs(lug + j * N + i); xo[q] = __ldcs(xg + j * N + i); }
+                }
+#pragma unroll
+                for (int q = 0; q < NW; ++q) {
+                    const int i = q * 32 + lane;
+                    if (i == j) { s0[q] += 1; lu[q] = 0; xo[q] = xj; } else lu[q] += 1;       // vehicle.py:58-70
+                    colx[i] = xo[q];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < NW; ++q) {
+                    const int i = q * 32 + lane;
+                    if (i < N) {
+                        const unsigned key = KS ? K[i * LD + j] : __ldcg(K + i * LD + j);
+                        const int sn = (int)(key >> SB);
+                        double xn = xo[q];
+                        if (sn != s0[q]) { xn = colx[key & srcmask]; lu[q] = 0; }              // vehicle.py:41-47
+                        __stcs(seqg + j * N + i, sn); __stcs(lug + j * N + i, lu[q]); __stcs(xg + j * N + i, xn);
+                        if (vpd) {
+                            bool in = j != i && lu[q] < p.age_threshold;                        // network.py:547
+                            const double xi = sxn[i];
+                            double sv;
+                            if (flat0) { sv = __dsub_rn(xn, xi); in = in && fabs(sv) < W; }
+                            else {
+                                const double d = dist2d(xn, sn > 0 ? yj : 0.0, xi, sy[i]);
+                                in = in && d < W;                                               // network.py:487
+                                sv = (__dsub_rn(xn, xi) > 0.0) ? d : -d;
+                            }
+                            if (in) {
+                                // trunc(t) is NumPy's edge-corrected bin unless t is within 1e-6 of an edge
+                                const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
+                                const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
+                                const int kb = (fabs(__dsub_rn(t, rt)) < 1e-6) ? vpd_bin(sv, W, inv_binw, B, s_edges)
+                                                                               : min(max((int)t, 0), B - 1);
+                                atomicAdd(&hist[kb * T + i], 1u);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (vpd && act) {     // samples per observer (the divisor of network.py:501)
+            unsigned m = 0u;
+            for (int b = 0; b < B; ++b) m += hist[b * T + tid];
+            recv_s[tid] = m;
+        }
+
+        // ---- F: state rows (TestEnv.obtain_state, test_env.py:527-583), one warp per row ---------------
+        if (want_state) {
+            __syncthreads();
+            const int n_act = p.add_action ? (p.action_binary ? R : 1) : 0;
+            const int o_vpd = n_act + (p.add_channel_obs ? R : 0);
+            const int o_tail = o_vpd + (p.piggy ? B : 0);
+            for (int u = warp; u < N; u += NWARPS) {
+                const int au = sa[u];
+                const float den = vpd ? (float)recv_s[u] : 0.0f, rcp = __frcp_rn(den);
+                const bool have = vpd && den > 0.0f;
+                const float *orow = og + (long long)u * R;     // written by this CTA before the barriers above
+                float *srow = p.state + (vbase + u) * S;
+                for (int s = lane; s < S; s += 32) {
+                    float val = 0.0f;
+                    if (s < n_act) val = p.action_binary ? ((au == s) ? 1.0f : 0.0f) : (float)au;
+                    else if (s < o_vpd) val = __ldcg(orow + (s - n_act));
+                    else if (s < o_tail) {
+                        if (have) {
+                            const float c = (float)hist[(s - o_vpd) * T + u];
+                            const float q0 = __fmul_rn(c, rcp);
+                            val = __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0);
+                        }
+                    } else {
+                        int k = s - o_tail;
+                        if (p.add_reward)   { if (k == 0) val = s_rew[u]; --k; }
+                        if (p.add_index)    { if (k == 0) val = (float)(u + 1); --k; }
+                        if (p.add_position) { if (k == 0) val = (float)__ddiv_rn(sxn[u], p.L); if (k == 1) val = (float)__ddiv_rn(sy[u], 2.0); k -= 2; }
+                        if (p.add_velocity) { if (k == 0) val = (float)p.vel[vbase + u]; --k; }
+                        if (p.fingerprint)  { if (k == 0) val = (float)p.episode; if (k == 1) val = (float)p.epsilon; k -= 2; }
+                    }
+                    srow[s] = val;
+                }
+            }
+        }
+
+        // ---- per-env metric accumulators (fixed-order block reduction for the reward sum) ---------------
+        {
+            double rs = act ? rew : 0.0; int nr = n_recv, np = n_pairs, nb = bad;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                nr += __shfl_xor_sync(0xffffffffu, nr, o);
+                np += __shfl_xor_sync(0xffffffffu, np, o);
+                nb += __shfl_xor_sync(0xffffffffu, nb, o);
+            }
+            if (lane == 0) {
+                if (warp < NW) s_red[warp] = rs;
+                if (nr) atomicAdd(&s_tot[0], (unsigned)nr);
+                if (np) atomicAdd(&s_tot[1], (unsigned)np);
+                if (nb) atomicAdd(&s_tot[2], (unsigned)nb);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double trs = 0.0;
+                for (int i = 0; i < NW; ++i) trs += s_red[i];
+                atomicAdd(p.acc_reward + e, trs);
+                unsigned long long *c = reinterpret_cast<unsigned long long *>(p.acc_count + e * ACC_COUNTS);
+                atomicAdd(c + 0, (unsigned long long)s_tot[0]); atomicAdd(c + 1, (unsigned long long)s_tot[1]);
+                atomicAdd(c + 2, (unsigned long long)s_tot[2]); atomicAdd(c + 3, 1ull);
+            }
+            __syncthreads();                      // shared memory is recycled by the next environment
         }
     }
 }
 
-int block_threads(int N) { return ((N + 31) / 32) * 32; }
-int helpers_for(int N)
-{
-    switch (block_threads(N) / 32) {
-    case 1: return Helpers<1>::v; case 2: return Helpers<2>::v; case 3: return Helpers<3>::v; case 4: return Helpers<4>::v;
-    case 5: return Helpers<5>::v; case 6: return Helpers<6>::v; case 7: return Helpers<7>::v; default: return Helpers<8>::v;
-    }
-}
+int block_warps(int N) { return std::max(1, (N + 31) / 32); }
 
-template <int NW>
-cudaError_t prepare_nw(const Params &p, size_t smem)
+template <int NW, bool KS>
+cudaError_t prepare_nw(size_t smem)
 {
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(step_block_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(step_block_kernel<NW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+template <int NW, bool KS>
+cudaError_t launch_nw(const Params &p, size_t smem, int SB, cudaStream_t stream)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_block_kernel<NW, KS>, geo_threads(NW), smem);
+    if (err != cudaSuccess) return err;
+    const long long resident = (long long)sms * std::max(per_sm, 1);
+    const unsigned grid = (unsigned)std::min<long long>(p.E, resident);
+    step_block_kernel<NW, KS><<<grid, geo_threads(NW), smem, stream>>>(p, SB);
+    return cudaGetLastError();
 }
 
 template <int NW>
-cudaError_t launch_nw(const Params &p, size_t smem, int SB, int fit, cudaStream_t stream)
+cudaError_t prepare_both(const Params &p)
 {
-    step_block_kernel<NW><<<(unsigned)p.E, NW * 32 * Helpers<NW>::v, smem, stream>>>(p, SB, fit);
-    return cudaGetLastError();
+    const bool fit = step_block_keys_fit_smem(p);
+    const size_t smem = step_block_smem_bytes(p, fit);
+    return fit ? prepare_nw<NW, true>(smem) : prepare_nw<NW, false>(smem);
+}
+
+template <int NW>
+cudaError_t launch_both(const Params &p, cudaStream_t stream)
+{
+    const bool fit = step_block_keys_fit_smem(p);
+    const size_t smem = step_block_smem_bytes(p, fit);
+    const int SB = key_src_bits(p.N);
+    return fit ? launch_nw<NW, true>(p, smem, SB, stream) : launch_nw<NW, false>(p, smem, SB, stream);
 }
 
 }  // namespace
@@ -496,50 +585,48 @@ int key_src_bits(int N)
 
 bool step_block_keys_fit_smem(const Params &p)
 {
-    const BlockSmem lay(p.N, p.R, p.B, block_threads(p.N), helpers_for(p.N), p.vpd_enabled != 0, true);
+    const BlockSmem lay(p.B, block_warps(p.N), p.vpd_enabled != 0, true);
     return lay.bytes <= SMEM_BUDGET;
 }
 
 size_t step_block_smem_bytes(const Params &p, bool keys_in_smem)
 {
-    const BlockSmem lay(p.N, p.R, p.B, block_threads(p.N), helpers_for(p.N), p.vpd_enabled != 0, keys_in_smem);
+    const BlockSmem lay(p.B, block_warps(p.N), p.vpd_enabled != 0, keys_in_smem);
     return lay.bytes;
 }
 
+size_t step_block_scratch_words_per_env(int N) { return (size_t)N * geo_ld(block_warps(N)); }
+
 size_t step_block_scratch_bytes(long long E, int N)
 {
-    return (size_t)E * N * (N + 1) * sizeof(unsigned);
+    return (size_t)E * step_block_scratch_words_per_env(N) * sizeof(unsigned);
 }
 
 cudaError_t prepare_step_block(const Params &p)
 {
-    const size_t smem = step_block_smem_bytes(p, step_block_keys_fit_smem(p));
-    switch (block_threads(p.N) / 32) {
-    case 1: return prepare_nw<1>(p, smem);
-    case 2: return prepare_nw<2>(p, smem);
-    case 3: return prepare_nw<3>(p, smem);
-    case 4: return prepare_nw<4>(p, smem);
-    case 5: return prepare_nw<5>(p, smem);
-    case 6: return prepare_nw<6>(p, smem);
-    case 7: return prepare_nw<7>(p, smem);
-    default: return prepare_nw<8>(p, smem);
+    switch (block_warps(p.N)) {
+    case 1: return prepare_both<1>(p);
+    case 2: return prepare_both<2>(p);
+    case 3: return prepare_both<3>(p);
+    case 4: return prepare_both<4>(p);
+    case 5: return prepare_both<5>(p);
+    case 6: return prepare_both<6>(p);
+    case 7: return prepare_both<7>(p);
+    default: return prepare_both<8>(p);
     }
 }
 
 cudaError_t launch_step_block(const Params &p, cudaStream_t stream)
 {
-    const bool fit = step_block_keys_fit_smem(p);
-    const size_t smem = step_block_smem_bytes(p, fit);
-    const int SB = key_src_bits(p.N);
-    switch (block_threads(p.N) / 32) {
-    case 1: return launch_nw<1>(p, smem, SB, fit, stream);
-    case 2: return launch_nw<2>(p, smem, SB, fit, stream);
-    case 3: return launch_nw<3>(p, smem, SB, fit, stream);
-    case 4: return launch_nw<4>(p, smem, SB, fit, stream);
-    case 5: return launch_nw<5>(p, smem, SB, fit, stream);
-    case 6: return launch_nw<6>(p, smem, SB, fit, stream);
-    case 7: return launch_nw<7>(p, smem, SB, fit, stream);
-    default: return launch_nw<8>(p, smem, SB, fit, stream);
+    switch (block_warps(p.N)) {
+    case 1: return launch_both<1>(p, stream);
+    case 2: return launch_both<2>(p, stream);
+    case 3: return launch_both<3>(p, stream);
+    case 4: return launch_both<4>(p, stream);
+    case 5: return launch_both<5>(p, stream);
+    case 6: return launch_both<6>(p, stream);
+    case 7: return launch_both<7>(p, stream);
+    default: return launch_both<8>(p, stream);
     }
 }
 

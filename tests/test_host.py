@@ -128,7 +128,7 @@ def test_size_helpers():
     assert tables < n < tables * 1.6
     assert lib.diral_scratch_bytes(C.byref(cfg)) == 0
     big = cfg_from_kwargs(16, 0, dict(num_users=256, num_channels=128, State=_state()))
-    assert lib.diral_scratch_bytes(C.byref(big)) == 16 * 256 * 257 * 4      # keys no longer fit shared memory
+    assert lib.diral_scratch_bytes(C.byref(big)) == 16 * 256 * 260 * 4      # keys no longer fit shared memory (row stride 260 words)
 
 
 def test_count_over_len_division_is_exact():
