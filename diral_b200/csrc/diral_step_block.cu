@@ -47,11 +47,11 @@ __host__ __device__ constexpr int geo_rc(int nw) { return ((256 / nw) & ~31) < 3
 // instead of being recomputed under register pressure); the arrays sized by the runtime bin count follow.
 __host__ __device__ constexpr size_t align16c(size_t x) { return (x + 15) & ~(size_t)15; }
 struct BlockSmem {
-    size_t off_sx, off_sy, off_sxn, off_sa, off_rew, off_recv, off_txm, off_cnt, off_inr, off_own, off_red, off_union,
+    size_t off_sx, off_sy, off_sxn, off_rewd, off_sa, off_aux, off_rew, off_recv, off_txm, off_cnt, off_inr, off_own, off_red, off_union,
         off_keys, off_edges, off_hist, bytes;
     size_t keys_bytes, list_bytes;
     __host__ __device__ constexpr BlockSmem(int B, int nw, bool vpd_state, bool keys_in_smem)
-        : off_sx(0), off_sy(0), off_sxn(0), off_sa(0), off_rew(0), off_recv(0), off_txm(0), off_cnt(0), off_inr(0), off_own(0),
+        : off_sx(0), off_sy(0), off_sxn(0), off_rewd(0), off_sa(0), off_aux(0), off_rew(0), off_recv(0), off_txm(0), off_cnt(0), off_inr(0), off_own(0),
           off_red(0), off_union(0), off_keys(0), off_edges(0), off_hist(0), bytes(0), keys_bytes(0), list_bytes(0)
     {
         const int T = nw * 32, NWP = geo_nwp(nw), RC = geo_rc(nw), NWARPS = geo_threads(nw) / 32;
@@ -59,7 +59,9 @@ struct BlockSmem {
         off_sx = o;    o += align16c(8 * (size_t)T);
         off_sy = o;    o += align16c(8 * (size_t)T);
         off_sxn = o;   o += align16c(8 * (size_t)T);          // post-mobility x
+        off_rewd = o;  o += align16c(8 * (size_t)T);          // rewards (float64, for the episode sums)
         off_sa = o;    o += align16c(4 * (size_t)T);          // actions
+        off_aux = o;   o += align16c(4 * (size_t)T);          // collision-set size | receivers in range << 16
         off_rew = o;   o += align16c(4 * (size_t)T);          // rewards (float)
         off_recv = o;  o += align16c(4 * (size_t)T);          // receptions per transmitter, later VPD sample counts
         off_txm = o;   o += align16c(4 * (size_t)RC * NWP);
@@ -146,7 +148,9 @@ step_block_kernel(const Params p, const int SB)
     double *sy = reinterpret_cast<double *>(smem_raw + fix.off_sy);
     double *sxn = reinterpret_cast<double *>(smem_raw + fix.off_sxn);
     double *s_edges = reinterpret_cast<double *>(smem_raw + fix.off_edges);
+    double *s_rewd = reinterpret_cast<double *>(smem_raw + fix.off_rewd);
     int *sa = reinterpret_cast<int *>(smem_raw + fix.off_sa);
+    int *s_aux = reinterpret_cast<int *>(smem_raw + fix.off_aux);
     float *s_rew = reinterpret_cast<float *>(smem_raw + fix.off_rew);
     unsigned *recv_s = reinterpret_cast<unsigned *>(smem_raw + fix.off_recv);
     unsigned *txm_s = reinterpret_cast<unsigned *>(smem_raw + fix.off_txm);            // [RC][NWP]
@@ -186,22 +190,26 @@ step_block_kernel(const Params p, const int SB)
         const long long vbase = e * N, tbase = e * (long long)N * N;
 
         // ---- A: inputs -----------------------------------------------------------------------------
-        int a = 0; double x = 0.0, y = 0.0, v = 0.0; int bad = 0;
+        // (per-vehicle values live in shared memory, not in registers, across the long phases)
+        if (tid < 3) s_tot[tid] = 0u;
+        bool y_same = true;
         if (act) {
+            int a;
             if (p.gen_actions) a = philox_action(p.seed, tid, p.env0 + e, p.timestep, R);
             else a = p.actions[vbase + tid];
-            x = p.pos_x[vbase + tid]; y = p.pos_y[vbase + tid]; v = p.vel[vbase + tid];
-            if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
+            const double y = p.pos_y[vbase + tid];
+            sx[tid] = p.pos_x[vbase + tid]; sy[tid] = y;
+            y_same = y == p.pos_y[vbase];
+            if (a < 0 || a >= R) { a = min(max(a, 0), R - 1); s_aux[tid] = -1; } else s_aux[tid] = 0;
             if (p.gen_actions && p.actions_out) p.actions_out[vbase + tid] = a;
-            sx[tid] = x; sy[tid] = y; sa[tid] = a; recv_s[tid] = 0u;
+            sa[tid] = a; recv_s[tid] = 0u; s_rewd[tid] = 0.0;
         }
         if (p.piggy) prefetch_rest(e);
         if (vpd) for (int i = tid; i < B * T; i += TT) hist[i] = 0u;
-        if (tid < 3) s_tot[tid] = 0u;
         // every vehicle on the same lane of the highway?  (dy == 0 for every pair => dist == |dx| exactly)
-        const double y0 = p.pos_y[vbase];
-        const bool flat = __syncthreads_and(!act || y == y0) != 0;     // also publishes sx, sy, sa
-        const bool flat0 = flat && y0 == 0.0;
+        const bool flat = __syncthreads_and(y_same) != 0;              // also publishes sx, sy, sa
+        const bool flat0 = flat && sy[0] == 0.0;
+        if (act && s_aux[tid] < 0) { atomicAdd(&s_tot[2], 1u); s_aux[tid] = 0; }   // out-of-range actions are counted
 
         // keys: K[i][j] = (seq[i][j] (+1 on the diagonal: the tick, vehicle.py:58)) << SB | i
         if (p.piggy) {
@@ -239,14 +247,13 @@ step_block_kernel(const Params p, const int SB)
         }
 
         // ---- B + C: resources, RC at a time --------------------------------------------------------
-        int my_tot = 0, in_range = 0; double rew = 0.0;
-        int n_recv = 0, n_pairs = 0;
         float *og = p.obs + vbase * R;
         for (int r0 = 0; r0 < R; r0 += RC) {
             const int rend = min(R, r0 + RC), nres = rend - r0;
             for (int i = tid; i < nres * NWP; i += TT) txm_s[i] = 0u;
             for (int i = tid; i < nres; i += TT) cnt_s[i] = 0;
             __syncthreads();
+            const int a = act ? sa[tid] : -1;
             const bool mine = act && a >= r0 && a < rend;
             if (mine) atomicOr(&txm_s[(a - r0) * NWP + warp], 1u << lane);             // test_env.py:149-157
             __syncthreads();
@@ -254,6 +261,8 @@ step_block_kernel(const Params p, const int SB)
             // rewards that need nothing but the collision set (test_env.py:159-199 / :294-302)
             if (mine) {
                 unsigned own[NW], inr[NW];
+                int my_tot = 0, in_range = 0; double rew = 0.0;
+                const double x = sx[tid], y = sy[tid];
 #pragma unroll
                 for (int w = 0; w < NW; ++w) { own[w] = txm_s[(a - r0) * NWP + w]; inr[w] = inr_s[tid * NWP + w]; my_tot += __popc(own[w]); }
                 if (mode == MODE_STEP) {
@@ -292,6 +301,7 @@ step_block_kernel(const Params p, const int SB)
 #pragma unroll
                     for (int w = 0; w < NW; ++w) in_range += __popc(inr[w] & ~own[w]);
                 }
+                s_rewd[tid] = rew; s_aux[tid] = my_tot | (in_range << 16);
             }
 
             // per-vehicle collision set; channel observations before any reception (coalesced rows)
@@ -317,6 +327,7 @@ step_block_kernel(const Params p, const int SB)
             __syncthreads();
 
             // decisions: thread (u, w) walks the in-range vehicles t of word w
+            int n_recv = 0, n_pairs = 0;
             for (int it = tid; it < T * NW; it += TT) {
                 const int w = it / T, u = it - w * T;
                 if (u >= N) continue;
@@ -370,6 +381,15 @@ step_block_kernel(const Params p, const int SB)
                     }
                 }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                n_recv += __shfl_xor_sync(0xffffffffu, n_recv, o);
+                n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o);
+            }
+            if (lane == 0) {
+                if (n_recv) atomicAdd(&s_tot[0], (unsigned)n_recv);
+                if (n_pairs) atomicAdd(&s_tot[1], (unsigned)n_pairs);
+            }
             __syncthreads();
 
             // merges, pass by pass: G receptions per warp and round, LPR lanes per row
@@ -396,12 +416,16 @@ step_block_kernel(const Params p, const int SB)
         __syncthreads();                          // recv_s complete; txm/cnt/list free
 
         // ---- D: rewards out, mobility ----------------------------------------------------------------
-        double x_new = 0.0;
         if (act) {
-            if (mode == MODE_CH) rew = channel_reward(p.reward_design, max(my_tot, 1), (int)recv_s[tid], in_range);
+            double rew = s_rewd[tid];
+            if (mode == MODE_CH) {
+                const int aux = s_aux[tid];
+                rew = channel_reward(p.reward_design, max(aux & 0xffff, 1), (int)recv_s[tid], aux >> 16);
+                s_rewd[tid] = rew;
+            }
             p.rews[vbase + tid] = (float)rew;
             s_rew[tid] = (float)rew;
-            x_new = mobility_step(p, x, v, tid);
+            const double x_new = mobility_step(p, sx[tid], p.vel[vbase + tid], tid);
             if (p.mobility) p.pos_x[vbase + tid] = x_new;
             sxn[tid] = x_new;
         }
@@ -506,20 +530,10 @@ step_block_kernel(const Params p, const int SB)
 
         // ---- per-env metric accumulators (fixed-order block reduction for the reward sum) ---------------
         {
-            double rs = act ? rew : 0.0; int nr = n_recv, np = n_pairs, nb = bad;
+            double rs = act ? s_rewd[tid] : 0.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                rs += __shfl_xor_sync(0xffffffffu, rs, o);
-                nr += __shfl_xor_sync(0xffffffffu, nr, o);
-                np += __shfl_xor_sync(0xffffffffu, np, o);
-                nb += __shfl_xor_sync(0xffffffffu, nb, o);
-            }
-            if (lane == 0) {
-                if (warp < NW) s_red[warp] = rs;
-                if (nr) atomicAdd(&s_tot[0], (unsigned)nr);
-                if (np) atomicAdd(&s_tot[1], (unsigned)np);
-                if (nb) atomicAdd(&s_tot[2], (unsigned)nb);
-            }
+            for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            if (lane == 0 && warp < NW) s_red[warp] = rs;
             __syncthreads();
             if (tid == 0) {
                 double trs = 0.0;
