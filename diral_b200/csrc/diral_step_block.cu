@@ -75,8 +75,8 @@ struct BlockSmem {
         off_union = o; o += align16c(list_bytes > colx ? list_bytes : colx);
         keys_bytes = keys_in_smem ? align16c(4 * (size_t)T * geo_ld(nw)) : 0;      // sized by the padded vehicle count
         off_keys = o;  o += keys_bytes;
-        off_edges = o; o += align16c(8 * (size_t)(B + 1));
         off_hist = o;  o += vpd_state ? align16c(4 * (size_t)B * T) : 0;
+        off_edges = o; o += align16c(8 * (size_t)(B + 1));        // (only the near-edge path of the binning reads them)
         bytes = o;
     }
 };
@@ -147,7 +147,7 @@ step_block_kernel(const Params p, const int SB)
     double *sx = reinterpret_cast<double *>(smem_raw + fix.off_sx);
     double *sy = reinterpret_cast<double *>(smem_raw + fix.off_sy);
     double *sxn = reinterpret_cast<double *>(smem_raw + fix.off_sxn);
-    double *s_edges = reinterpret_cast<double *>(smem_raw + fix.off_edges);
+    double *s_edges = reinterpret_cast<double *>(smem_raw + lay.off_edges);
     double *s_rewd = reinterpret_cast<double *>(smem_raw + fix.off_rewd);
     int *sa = reinterpret_cast<int *>(smem_raw + fix.off_sa);
     int *s_aux = reinterpret_cast<int *>(smem_raw + fix.off_aux);
@@ -159,7 +159,7 @@ step_block_kernel(const Params p, const int SB)
     unsigned *own_s = reinterpret_cast<unsigned *>(smem_raw + fix.off_own);            // [N][NWP]
     double *s_red = reinterpret_cast<double *>(smem_raw + fix.off_red);                // [16][4]
     unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + fix.off_red + 8 * 4 * 16); // received, pairs, bad
-    unsigned *hist = reinterpret_cast<unsigned *>(smem_raw + lay.off_hist);            // [B][T]
+    unsigned *hist = reinterpret_cast<unsigned *>(smem_raw + fix.off_hist);            // [B][T]
     unsigned short *list = reinterpret_cast<unsigned short *>(smem_raw + fix.off_union);   // [RC][T]  rx << 8 | tx
     double *colx = reinterpret_cast<double *>(smem_raw + fix.off_union) + warp * T;    // phase E
     unsigned *K;
@@ -437,6 +437,7 @@ step_block_kernel(const Params p, const int SB)
             int32_t *seqg = p.tab_seq + tbase, *lug = p.tab_lu + tbase;
             double *xg = p.tab_x + tbase;
             const double W = p.W, inv_binw = p.inv_binw;
+            const int age_thr = p.age_threshold;
             for (int j = warp; j < N; j += NWARPS) {
                 int s0[NW], lu[NW]; double xo[NW];
                 const double xj = sx[j], yj = sy[j];
@@ -463,7 +464,7 @@ step_block_kernel(const Params p, const int SB)
                         if (sn != s0[q]) { xn = colx[key & srcmask]; lu[q] = 0; }              // vehicle.py:41-47
                         __stcs(seqg + j * N + i, sn); __stcs(lug + j * N + i, lu[q]); __stcs(xg + j * N + i, xn);
                         if (vpd) {
-                            bool in = j != i && lu[q] < p.age_threshold;                        // network.py:547
+                            bool in = j != i && lu[q] < age_thr;                                // network.py:547
                             const double xi = sxn[i];
                             double sv;
                             if (flat0) { sv = __dsub_rn(xn, xi); in = in && fabs(sv) < W; }
@@ -472,14 +473,13 @@ step_block_kernel(const Params p, const int SB)
                                 in = in && d < W;                                               // network.py:487
                                 sv = (__dsub_rn(xn, xi) > 0.0) ? d : -d;
                             }
-                            if (in) {
-                                // trunc(t) is NumPy's edge-corrected bin unless t is within 1e-6 of an edge
-                                const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
-                                const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
-                                const int kb = (fabs(__dsub_rn(t, rt)) < 1e-6) ? vpd_bin(sv, W, inv_binw, B, s_edges)
-                                                                               : min(max((int)t, 0), B - 1);
-                                atomicAdd(&hist[kb * T + i], 1u);
-                            }
+                            // trunc(t) is NumPy's edge-corrected bin unless t is within 1e-6 of an edge; formed
+                            // unconditionally (clamped garbage when !in), only the reduction is predicated
+                            const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
+                            const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
+                            int kb = min(max(__double2int_rz(t), 0), B - 1);
+                            if (in && fabs(__dsub_rn(t, rt)) < 1e-6) kb = vpd_bin(sv, W, inv_binw, B, s_edges);
+                            if (in) atomicAdd(&hist[kb * T + i], 1u);
                         }
                     }
                 }
@@ -505,25 +505,29 @@ step_block_kernel(const Params p, const int SB)
                 const bool have = vpd && den > 0.0f;
                 const float *orow = og + (long long)u * R;     // written by this CTA before the barriers above
                 float *srow = p.state + (vbase + u) * S;
-                for (int s = lane; s < S; s += 32) {
-                    float val = 0.0f;
-                    if (s < n_act) val = p.action_binary ? ((au == s) ? 1.0f : 0.0f) : (float)au;
-                    else if (s < o_vpd) val = __ldcg(orow + (s - n_act));
-                    else if (s < o_tail) {
+                if (p.add_action) {
+                    if (p.action_binary) { for (int s = lane; s < R; s += 32) srow[s] = (au == s) ? 1.0f : 0.0f; }
+                    else if (lane == 0) srow[0] = (float)au;
+                }
+                if (p.add_channel_obs) for (int s = lane; s < R; s += 32) srow[n_act + s] = __ldcg(orow + s);
+                if (p.piggy)
+                    for (int b = lane; b < B; b += 32) {
+                        float val = 0.0f;
                         if (have) {
-                            const float c = (float)hist[(s - o_vpd) * T + u];
+                            const float c = (float)hist[b * T + u];
                             const float q0 = __fmul_rn(c, rcp);
                             val = __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0);
                         }
-                    } else {
-                        int k = s - o_tail;
-                        if (p.add_reward)   { if (k == 0) val = s_rew[u]; --k; }
-                        if (p.add_index)    { if (k == 0) val = (float)(u + 1); --k; }
-                        if (p.add_position) { if (k == 0) val = (float)__ddiv_rn(sxn[u], p.L); if (k == 1) val = (float)__ddiv_rn(sy[u], 2.0); k -= 2; }
-                        if (p.add_velocity) { if (k == 0) val = (float)p.vel[vbase + u]; --k; }
-                        if (p.fingerprint)  { if (k == 0) val = (float)p.episode; if (k == 1) val = (float)p.epsilon; k -= 2; }
+                        srow[o_vpd + b] = val;
                     }
-                    srow[s] = val;
+                if (lane < S - o_tail) {
+                    float val = 0.0f; int k = lane;
+                    if (p.add_reward)   { if (k == 0) val = s_rew[u]; --k; }
+                    if (p.add_index)    { if (k == 0) val = (float)(u + 1); --k; }
+                    if (p.add_position) { if (k == 0) val = (float)__ddiv_rn(sxn[u], p.L); if (k == 1) val = (float)__ddiv_rn(sy[u], 2.0); k -= 2; }
+                    if (p.add_velocity) { if (k == 0) val = (float)p.vel[vbase + u]; --k; }
+                    if (p.fingerprint)  { if (k == 0) val = (float)p.episode; if (k == 1) val = (float)p.epsilon; k -= 2; }
+                    srow[o_tail + lane] = val;
                 }
             }
         }
