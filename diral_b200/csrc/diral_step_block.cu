@@ -40,7 +40,7 @@ __host__ __device__ constexpr int geo_lpr(int nw) { return nw <= 1 ? 4 : nw <= 2
 __host__ __device__ constexpr int geo_ld(int nw) { return 8 * geo_lpr(nw) + 4; }                              // key row stride (words)
 __host__ __device__ constexpr int geo_threads(int nw) { return nw <= 1 ? 128 : nw <= 2 ? 256 : 512; }
 __host__ __device__ constexpr int geo_nwp(int nw) { return nw | 1; }                                         // odd stride of the bit-mask rows
-__host__ __device__ constexpr int geo_rc(int nw) { return ((256 / nw) & ~31) < 32 ? 32 : ((256 / nw) & ~31); } // resources per decision chunk
+__host__ __device__ constexpr int geo_rc(int nw) { return nw <= 4 ? ((256 / nw) & ~31) : 64; }              // resources per decision chunk (lists no larger than the column buffers)
 
 // Shared-memory carve-up.  Everything the hot loops touch sits at an offset that depends on the
 // instantiation only (a compile-time constant inside the kernel: addresses fold into the instructions

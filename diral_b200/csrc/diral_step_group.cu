@@ -62,9 +62,17 @@ template <> struct Log2<32> { static constexpr int v = 5; };
 __host__ __device__ inline int align16i(int x) { return (x + 15) & ~15; }
 
 // shared-memory carve-up of one group (bytes); the host computes the same numbers
+// State rows leave as float4 stores straight from the registers that hold them (no shared-memory staging,
+// which is what lets 28 one-warp CTAs share an SM at C3) when every feature block starts 16 B aligned.
+__host__ __device__ inline bool group_direct_rows(const Params &p)
+{
+    const int n_act = p.add_action ? (p.action_binary ? p.R : 1) : 0;
+    return (p.S & 3) == 0 && (n_act & 3) == 0 && (!p.add_channel_obs || (p.R & 3) == 0) && (!p.piggy || (p.B & 3) == 0);
+}
+
 struct GroupSmem {
     int off_sx, off_sy, off_script, off_txm, off_recv, off_obs, off_hist, off_st, bytes;
-    __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd)
+    __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd, bool direct)
     {
         int o = 0;
         off_script = o; o += align16i(G * (R + 1));    // merge script: one byte per (pass, lane), + 1 spare row
@@ -74,7 +82,7 @@ struct GroupSmem {
         off_sy = o;   o += align16i(8 * G);
         off_obs = o;  o += align16i(4 * G * R);
         off_hist = o; o += (state && vpd) ? align16i(4 * G * (B + 1)) : 0;   // + 1 dummy row
-        off_st = o;   o += state ? align16i(4 * G * S) : 0;
+        off_st = o;   o += (state && !direct) ? align16i(4 * G * S) : 0;
         bytes = o;
     }
 };
@@ -161,7 +169,8 @@ step_group_kernel(const Params p)
 
     const bool want_state = p.build_state != 0;
     const bool vpd = want_state && p.vpd_enabled;
-    const GroupSmem lay(G, R, B, S, want_state, p.vpd_enabled);
+    const bool direct = group_direct_rows(p);
+    const GroupSmem lay(G, R, B, S, want_state, p.vpd_enabled, direct);
     unsigned char *gbase = smem_raw + align16i(8 * (B + 1)) + (size_t)(warp * EPW + sub) * lay.bytes;
     double *sx = reinterpret_cast<double *>(gbase + lay.off_sx);
     double *sy = reinterpret_cast<double *>(gbase + lay.off_sy);
@@ -548,7 +557,7 @@ step_group_kernel(const Params p)
     // contiguous float4 stream.  (The scalar row writes bank-conflict for some S; they are few.)
     __syncwarp(gmask);                       // all histogram reductions of this group have landed
     if (want_state && act) {
-        float *wp = st + u * S;
+        float *wp = direct ? p.state + (vbase + u) * S : st + u * S;
         if (p.add_action) {
             if (p.action_binary) {
                 int r = 0;
@@ -567,16 +576,21 @@ step_group_kernel(const Params p)
             const float den = (float)m_cnt, rcp = __frcp_rn(den);
             const bool have = vpd && m_cnt > 0;
             for (int b0 = 0; b0 < B; b0 += 8) {      // loads first: the row stores below may alias them
-                unsigned hv[8];
+                unsigned hv[8]; float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) hv[i] = (have && b0 + i < B) ? hist[(b0 + i) * G + u] : 0u;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (b0 + i < B) {
-                        const float c = (float)hv[i];
-                        const float q0 = __fmul_rn(c, rcp);
-                        *wp++ = have ? __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0) : 0.0f;
-                    }
+                    const float c = (float)hv[i];
+                    const float q0 = __fmul_rn(c, rcp);
+                    f[i] = have ? __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0) : 0.0f;
+                }
+                if (direct) {                        // B % 4 == 0: whole float4 groups
+                    *reinterpret_cast<float4 *>(wp) = make_float4(f[0], f[1], f[2], f[3]); wp += 4;
+                    if (b0 + 4 < B) { *reinterpret_cast<float4 *>(wp) = make_float4(f[4], f[5], f[6], f[7]); wp += 4; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (b0 + i < B) *wp++ = f[i];
                 }
             }
         }
@@ -597,13 +611,13 @@ step_group_kernel(const Params p)
         }
     };
     copy_out(p.obs + vbase * R, obsS, N * R);
-    if (want_state) copy_out(p.state + vbase * S, st, N * S);
+    if (want_state && !direct) copy_out(p.state + vbase * S, st, N * S);
 }
 
 template <int G>
 size_t smem_bytes(const Params &p, int warps)
 {
-    const GroupSmem lay(G, p.R, p.B, p.S, p.build_state != 0, p.vpd_enabled != 0);
+    const GroupSmem lay(G, p.R, p.B, p.S, p.build_state != 0, p.vpd_enabled != 0, group_direct_rows(p));
     return (size_t)align16i(8 * (p.B + 1)) + (size_t)warps * (32 / G) * lay.bytes;
 }
 
