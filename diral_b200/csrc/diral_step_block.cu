@@ -186,6 +186,8 @@ step_block_kernel(const Params p, const int SB)
         for (int o = tid * 128; o < N * N * 4; o += TT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + o));
     };
 
+    // prefetching pays only while the tables of all resident environments fit the L2 next to everything else
+    const bool pf_ok = p.piggy && (long long)gridDim.x * N * N * 16 <= (80ll << 20);
     for (long long e = blockIdx.x; e < p.E; e += gridDim.x) {
         const long long vbase = e * N, tbase = e * (long long)N * N;
 
@@ -204,7 +206,7 @@ step_block_kernel(const Params p, const int SB)
             if (p.gen_actions && p.actions_out) p.actions_out[vbase + tid] = a;
             sa[tid] = a; recv_s[tid] = 0u; s_rewd[tid] = 0.0;
         }
-        if (p.piggy) prefetch_rest(e);
+        if (pf_ok) prefetch_rest(e);
         if (vpd) for (int i = tid; i < B * T; i += TT) hist[i] = 0u;
         // every vehicle on the same lane of the highway?  (dy == 0 for every pair => dist == |dx| exactly)
         const bool flat = __syncthreads_and(y_same) != 0;              // also publishes sx, sy, sa
@@ -429,7 +431,7 @@ step_block_kernel(const Params p, const int SB)
             if (p.mobility) p.pos_x[vbase + tid] = x_new;
             sxn[tid] = x_new;
         }
-        if (p.piggy && e + gridDim.x < p.E) prefetch_seq(e + gridDim.x);
+        if (pf_ok && e + gridDim.x < p.E) prefetch_seq(e + gridDim.x);
         __syncthreads();
 
         // ---- E: one warp per subject column ------------------------------------------------------------
