@@ -45,6 +45,12 @@ class DiralShaping(C.Structure):
                 ("global_reward_avg", C.c_int32), ("ia_penalty_value", C.c_double)]
 
 
+class DiralSpsCfg(C.Structure):
+    """POD mirror of ``diral_sps_cfg`` (include/diral_env.h)."""
+    _fields_ = [("rssi_threshold", C.c_double), ("inc_db", C.c_double), ("prob_resource_keep", C.c_double),
+                ("min_candidates", C.c_double)]
+
+
 # every symbol include/diral_env.h declares: name -> (restype, argtypes)
 _P, _I64, _U64, _I32, _D = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_double
 SYMBOLS = {
@@ -67,6 +73,8 @@ SYMBOLS = {
     "diral_episode_metrics": (C.c_int, [_P, _I64, _P, _P]),
     "diral_shape_rewards": (C.c_int, [_P, C.POINTER(DiralShaping), _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "diral_ring_gather": (C.c_int, [_P, _I64, _I64, _I64, _I32, _P, _I32, _I32, _P, _P]),
+    "diral_wire_vpd": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _D, _I32, _P, _P]),
+    "diral_sps_step": (C.c_int, [_I64, _I32, _P, C.POINTER(DiralSpsCfg), _P, _U64, _I64, _P, _P, _P, _P, _P]),
     "diral_step_host": (C.c_int, [_P, C.c_int, _P, _I64, _D, _D, _P, _P, _P, _P]),
     "diral_launch_count": (C.c_int64, [_P]),
 }

@@ -460,6 +460,35 @@ int diral_ring_gather(const void *ring, int64_t capacity, int64_t agents, int64_
     return DIRAL_OK;
 }
 
+int diral_wire_vpd(const diral_wire_entry *tables, const int32_t *observer, int64_t M, int32_t N, int32_t pos_dist,
+                   int32_t bins, double range, int32_t age_limit, float *out, void *stream)
+{
+    if (!tables || !observer || !out) return fail(DIRAL_ERR_ARG, "tables/observer/out must not be NULL");
+    if (M < 1 || N < 1 || N > diral::wire_max_entries()) return fail(DIRAL_ERR_ARG, "M must be >= 1 and N in [1, %d]", diral::wire_max_entries());
+    if (bins < 1 || bins > diral::wire_max_bins()) return fail(DIRAL_ERR_ARG, "state_bins must be in [1, %d] (got %d)", diral::wire_max_bins(), bins);
+    if (pos_dist != 1 && pos_dist != 2) return fail(DIRAL_ERR_ARG, "pos_dist must be 1 or 2 (got %d)", pos_dist);
+    if (pos_dist == 2 && !(range > 0.0)) return fail(DIRAL_ERR_ARG, "state_range must be > 0");
+    std::vector<double> edges(bins + 1);
+    if (pos_dist == 2) np_linspace(-range, range, bins + 1, edges.data());     // numpy.histogram(.., bins, range=(-W, W))
+    else np_linspace(-1.0, 1.0, bins + 1, edges.data());                       // realness_env.py:77
+    DIRAL_CUDA(diral::launch_wire_vpd(tables, observer, M, N, pos_dist, bins, range, age_limit, edges.data(), out,
+                                      static_cast<cudaStream_t>(stream)));
+    return DIRAL_OK;
+}
+
+int diral_sps_step(int64_t agents, int32_t window_len, const double *selection_window, const diral_sps_cfg *cfg,
+                   const double *draws, uint64_t seed, int64_t t, int32_t *prev_action, int32_t *reselection_counter,
+                   int32_t *actions, int32_t *flags, void *stream)
+{
+    if (!selection_window || !cfg || !prev_action || !reselection_counter || !actions)
+        return fail(DIRAL_ERR_ARG, "selection_window/cfg/prev_action/reselection_counter/actions must not be NULL");
+    if (agents < 1 || window_len < 1) return fail(DIRAL_ERR_ARG, "agents and window_len must be >= 1");
+    DIRAL_CUDA(diral::launch_sps_step(agents, window_len, selection_window, cfg->rssi_threshold, cfg->inc_db, cfg->prob_resource_keep,
+                                      cfg->min_candidates, draws, seed, t, prev_action, reselection_counter, actions, flags,
+                                      static_cast<cudaStream_t>(stream)));
+    return DIRAL_OK;
+}
+
 int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
                     float *h_state, float *h_rews, float *h_obs, void *stream)
 {

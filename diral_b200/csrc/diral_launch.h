@@ -38,4 +38,14 @@ cudaError_t launch_shape_rewards(const Params &p, const ShapingArgs &s, cudaStre
 cudaError_t launch_ring_gather(const void *ring, long long capacity, long long agents, long long width, int elem_bytes,
                                const long long *start, int batch, int step, void *out, cudaStream_t stream);
 
+
+// RealNeS wire-format positional distribution and the SPS baseline policy (diral_wire.cu)
+int wire_max_entries();
+int wire_max_bins();
+cudaError_t launch_wire_vpd(const void *tables, const int32_t *observer, long long M, int N, int type, int B, double W,
+                            int age_limit, const double *host_edges, float *out, cudaStream_t stream);
+cudaError_t launch_sps_step(long long A, int Wn, const double *window, double rssi_threshold, double inc_db,
+                            double prob_keep, double min_sa, const double *draws, unsigned long long seed, long long t,
+                            int32_t *prev_action, int32_t *counter, int32_t *actions, int32_t *flags, cudaStream_t stream);
+
 }  // namespace diral

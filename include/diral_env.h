@@ -165,6 +165,43 @@ int diral_shape_rewards(void *handle, const diral_shaping *cfg, const int32_t *a
 int diral_ring_gather(const void *ring, int64_t capacity, int64_t agents, int64_t width, int32_t elem_bytes,
                       const int64_t *start, int32_t batch, int32_t step, void *out, void *stream);
 
+/* The last "next" row of SURVEY.md 8(f), part 1: the view-based positional distribution of the RealNeS
+ * environment, RealnessEnv.get_neighbor_dist (pos_dist 1, envs/realness_env.py:52-85) and get_neighbor_dist2
+ * (pos_dist 2, :87-118), on neighbour tables in the wire layout of MA_NeighborTableEntry (envs/ma_messages_pb2.py;
+ * filled by RealNeSZmqBridge.get_observation_syn_dist, envs/realness_bridge.py:168-191).
+ * tables:   device, [M][N] entries; observer: device int32 [M], the 0-based user_id - 1 each table is seen from
+ *           (realness_env.py:371-373); out: device float32 [M][bins].
+ * Entries with last_update > age_limit (20 in the reference) are skipped; pos_dist 2 bins the signed distances
+ * into `bins` equal bins over [-range, range] and divides by the number of fresh entries (out-of-range ones
+ * included, as the reference does); pos_dist 1 is the weighted histogram of the sorted, max-normalised distances.
+ * No handle: it touches no environment state. */
+typedef struct diral_wire_entry {
+    float   pos_x, pos_y;          /* MA_NeighborTableEntry.pos_x / pos_y  (float32 on the wire) */
+    int32_t seq_num, last_update;  /* MA_NeighborTableEntry.seq_num / last_update */
+} diral_wire_entry;
+int diral_wire_vpd(const diral_wire_entry *tables, const int32_t *observer, int64_t M, int32_t N, int32_t pos_dist,
+                   int32_t bins, double range, int32_t age_limit, float *out, void *stream);
+
+/* ... part 2: the 3GPP semi-persistent-scheduling baseline, SemiPersistentScheduling.step and
+ * choose_new_resource (algorithms/v2x_sps.py:76-104, :24-74), one state machine per agent.
+ * selection_window: device float64 [agents][window_len] averaged RSSI per subframe (the reference receives
+ *   them as protobuf doubles, envs/realness_bridge.py:195-208); prev_action / reselection_counter: device
+ *   int32 [agents], the per-agent state (v2x_sps.py:13-18), updated in place; actions: device int32 [agents].
+ * draws: device float64 [agents][3] = {new reselection counter (random.randint(5, 16)), keep-uniform
+ *   (random.random()), choice index (random.choice picks candidates[index mod len])}, consumed only by agents
+ *   whose counter is 0; NULL draws them from the counter-based generator keyed by (seed, agent, t).
+ * flags (optional, device int32 [agents]) is set to 1 where the reference would raise or never return
+ *   (no candidate list can reach cfg.min_candidates); that agent keeps its previous subframe. */
+typedef struct diral_sps_cfg {
+    double rssi_threshold;         /* v2x_sps.py:11 */
+    double inc_db;                 /* 3 dB per widening round, v2x_sps.py:19 */
+    double prob_resource_keep;     /* 0.8, v2x_sps.py:22 */
+    double min_candidates;         /* len(selection_window) / 5 as the host interpreter evaluates it, v2x_sps.py:40 */
+} diral_sps_cfg;
+int diral_sps_step(int64_t agents, int32_t window_len, const double *selection_window, const diral_sps_cfg *cfg,
+                   const double *draws, uint64_t seed, int64_t t, int32_t *prev_action, int32_t *reselection_counter,
+                   int32_t *actions, int32_t *flags, void *stream);
+
 /* Host-buffer convenience for callers that keep data on the CPU (the reference's learners do):
  * copies h_actions in, runs diral_step(build_state=1), copies state/rews (and obs if not NULL) out,
  * synchronises the stream.  Host pointers should be pinned for full PCIe bandwidth. */

@@ -420,3 +420,95 @@ def test_random_configurations_against_oracle(case):
             assert (_np(env.lat) == orc.lat).all(), "last_arrival_time, slot %d" % t
     for env in envs:
         env.close()
+
+
+# ---- RealNeS wire-format positional distribution and the SPS baseline -------------------
+
+def _golden_npz(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+@pytest.mark.parametrize("pos_dist", [1, 2])
+def test_wire_vpd_golden(pos_dist):
+    """diral_wire_vpd against RealnessEnv.get_neighbor_dist / get_neighbor_dist2 outputs recorded from the
+    unmodified reference: float32 rounding of the reference's float64 values, exact (type 2: integer counts
+    over an integer; type 1 within 1e-6, its cumulative sums see sqrt-of-pow last-bit differences)."""
+    from diral_b200 import realness
+    g = _golden_npz("wire_vpd.npz")
+    for i in range(int(g["ncases"])):
+        x, y, seq, lu, obs = (g["c%d_%s" % (i, k)] for k in ("x", "y", "seq", "lu", "obs"))
+        bins, rng = int(g["c%d_bins" % i]), float(g["c%d_rng" % i])
+        tabs = realness.pack_tables(x, y, seq, lu)
+        if pos_dist == 2:
+            got = _np(realness.get_neighbor_dist2(tabs, obs, bins, rng))
+            _close32(got, g["c%d_o2" % i], "wire VPD type 2, case %d" % i, 0, exact=True)
+        else:
+            got = _np(realness.get_neighbor_dist(tabs, obs, bins))
+            _close32(got[1:], g["c%d_o1" % i][1:], "wire VPD type 1, case %d" % i, 0)
+
+
+@pytest.mark.parametrize("M,N,bins,rng", [(4096, 32, 20, 500.0), (777, 257, 10, 250.0), (50, 1024, 256, 3000.0)])
+def test_wire_vpd_random_vs_oracle(M, N, bins, rng):
+    from diral_b200 import realness
+    from oracle import wire
+    rs = np.random.RandomState(M + N)
+    x = rs.uniform(0, 8 * rng, size=(M, N)).astype(np.float32)
+    y = rs.choice(np.array([0.0, 3.5, 7.0], dtype=np.float32), size=(M, N))
+    lu = rs.randint(0, 45, size=(M, N)).astype(np.int32)
+    seq = rs.randint(0, 1000, size=(M, N)).astype(np.int32)
+    obs = rs.randint(0, N, size=M).astype(np.int32)
+    tabs = realness.pack_tables(x, y, seq, lu)
+    got2 = _np(realness.get_neighbor_dist2(tabs, obs, bins, rng))
+    got1 = _np(realness.get_neighbor_dist(tabs, obs, bins))
+    assert got2.min() >= 0.0 and got2.sum(axis=1).max() <= 1.0 + 1e-5      # out-of-range samples stay in the divisor
+    for m in rs.choice(M, size=min(M, 60), replace=False):
+        r2 = np.asarray(wire.neighbor_dist2(int(obs[m]), x[m], y[m], lu[m], bins, rng), dtype=np.float64)
+        _close32(got2[m], r2, "wire VPD type 2, table %d" % m, 0, exact=True)
+        r1 = np.asarray(wire.neighbor_dist(int(obs[m]), x[m], y[m], lu[m], bins), dtype=np.float64)
+        _close32(got1[m], r1, "wire VPD type 1, table %d" % m, 0)
+
+
+def test_sps_golden():
+    """diral_sps_step against SemiPersistentScheduling stepped in the reference with scripted draws: chosen
+    subframes, previous subframe and reselection counter identical at every step."""
+    from diral_b200.realness import SemiPersistentScheduling
+    s = _golden_npz("sps.npz")
+    for i in range(int(s["ncases"])):
+        W, D = s["c%d_windows" % i], s["c%d_draws" % i]
+        A, Wn = W.shape[1], W.shape[2]
+        sps = SemiPersistentScheduling(A, Wn, float(s["c%d_thr" % i]), init=(s["c%d_tx0" % i], s["c%d_c0" % i]))
+        for t in range(W.shape[0]):
+            a = sps.step(torch.from_numpy(W[t]).cuda().contiguous(), torch.from_numpy(D[t]).cuda().contiguous())
+            assert (_np(a) == s["c%d_acts" % i][t]).all(), (i, t)
+            assert (_np(sps.prev_action) == s["c%d_prev" % i][t]).all(), (i, t)
+            assert (_np(sps.reselection_counter) == s["c%d_cnt" % i][t]).all(), (i, t)
+        assert int(sps.flags.sum()) == 0
+
+
+def test_sps_random_vs_oracle_and_flags():
+    from diral_b200.realness import SemiPersistentScheduling
+    from oracle import wire
+    rs = np.random.RandomState(3)
+    A, Wn, T = 4096, 100, 40
+    tx0, c0 = rs.randint(0, Wn + 1, size=A), rs.randint(0, 3, size=A)
+    sps = SemiPersistentScheduling(A, Wn, -100.0, init=(tx0, c0))
+    bank = wire.SpsBank(tx0, c0, -100.0)
+    for t in range(T):
+        W = np.round(rs.uniform(-125.0, -70.0, size=(A, Wn)))              # integer dB values: many ties
+        D = np.stack([rs.randint(0, 4, size=A).astype(np.float64), rs.rand(A), rs.randint(0, 1 << 30, size=A).astype(np.float64)], axis=-1)
+        a = _np(sps.step(torch.from_numpy(W).cuda(), torch.from_numpy(D).cuda()))
+        ra, rf = bank.step(W, D)
+        assert (a == ra).all() and (_np(sps.prev_action) == bank.prev).all() and (_np(sps.reselection_counter) == bank.counter).all(), t
+    # no candidate list can ever reach len/5 entries: the reference would spin; the kernel flags and keeps the subframe
+    sps2 = SemiPersistentScheduling(8, 5, -100.0, init=(np.zeros(8), np.zeros(8)))
+    W = torch.full((8, 5), float("inf"), dtype=torch.float64, device="cuda")
+    D = torch.tensor([[7.0, 0.99, 0.0]] * 8, dtype=torch.float64, device="cuda")
+    a = _np(sps2.step(W, D))
+    assert (a == 0).all() and int(sps2.flags.sum()) == 8
+    # on-device draws: counters end in [5, 16] after a reselection, actions stay inside the window
+    sps3 = SemiPersistentScheduling(1024, 20, -97.0, seed=5)
+    for t in range(30):
+        a = sps3.step(torch.from_numpy(rs.uniform(-125, -70, size=(1024, 20))).cuda())
+        assert int(a.min()) >= 0 and int(a.max()) <= 20
+    assert int(sps3.reselection_counter.min()) >= 0 and int(sps3.reselection_counter.max()) <= 16

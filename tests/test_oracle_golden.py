@@ -95,3 +95,36 @@ def test_replay_memory_matches_reference():
             assert st.shape == (N, BATCH, STEP, S) and (st[2, 1, 0] == batch[1][0][0][2]).all()
             k += 1
     assert k == len(g["at"]) and k > 3
+
+
+def test_wire_vpd_oracle_matches_reference():
+    """oracle/wire.py against RealnessEnv.get_neighbor_dist / get_neighbor_dist2 run unmodified
+    (tests/golden/make_golden_wire.py), bit for bit in float64."""
+    import os
+    from oracle import wire
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wire_vpd.npz"))
+    for i in range(int(g["ncases"])):
+        x, y, lu, obs, o1, o2 = (g["c%d_%s" % (i, k)] for k in ("x", "y", "lu", "obs", "o1", "o2"))
+        bins, rng = int(g["c%d_bins" % i]), float(g["c%d_rng" % i])
+        for m in range(x.shape[0]):
+            r2 = wire.neighbor_dist2(int(obs[m]), x[m], y[m], lu[m], bins, rng)
+            assert (np.asarray(r2, dtype=np.float64) == o2[m]).all(), (i, m)
+            if m > 0:            # table 0 of every case has a zero norm: NaNs in the reference, not compared
+                with np.errstate(all="ignore"):
+                    r1 = wire.neighbor_dist(int(obs[m]), x[m], y[m], lu[m], bins)
+                assert np.array_equal(np.asarray(r1, dtype=np.float64), o1[m], equal_nan=True), (i, m)
+
+
+def test_sps_oracle_matches_reference():
+    """oracle/wire.py::SpsBank against SemiPersistentScheduling (algorithms/v2x_sps.py) stepped with scripted draws."""
+    import os
+    from oracle import wire
+    s = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sps.npz"))
+    for i in range(int(s["ncases"])):
+        bank = wire.SpsBank(s["c%d_tx0" % i], s["c%d_c0" % i], float(s["c%d_thr" % i]))
+        W, D = s["c%d_windows" % i], s["c%d_draws" % i]
+        for t in range(W.shape[0]):
+            a, f = bank.step(W[t], D[t])
+            assert (a == s["c%d_acts" % i][t]).all(), (i, t)
+            assert (bank.prev == s["c%d_prev" % i][t]).all() and (bank.counter == s["c%d_cnt" % i][t]).all(), (i, t)
+            assert not f.any()
