@@ -121,6 +121,20 @@ ORACLE_CASES = [
                                          communication_range=250, mobility=True)),
     ("c5_100x50", 5, 10, "my_step", dict(num_users=100, num_channels=50, highway_length=2500, reward_design=2,
                                          communication_range=250, mobility=True)),
+    # more resources than one decision chunk of the one-CTA-per-env kernel holds (64-256 by vehicle count),
+    # partial last chunks, every key-storage variant (shared memory up to ~190 vehicles, L2 scratch beyond)
+    ("n96x150_ch", 3, 8, "my_step_ch", dict(num_users=96, num_channels=150, highway_length=2400, reward_design=3,
+                                            communication_range=250, mobility=True)),
+    ("n40x300", 4, 8, "my_step", dict(num_users=40, num_channels=300, highway_length=1000, reward_design=2,
+                                      communication_range=250, mobility=True)),
+    ("n20x600_design", 4, 8, "my_step_design", dict(num_users=20, num_channels=600, highway_length=500, reward_design=2,
+                                                    communication_range=250, mobility=True)),
+    ("n160x70", 2, 6, "my_step", dict(num_users=160, num_channels=70, highway_length=4000, reward_design=2,
+                                      communication_range=250, mobility=True)),
+    ("n200x90_ch", 2, 6, "my_step_ch", dict(num_users=200, num_channels=90, highway_length=5000, reward_design=2,
+                                            communication_range=250, mobility=True)),
+    ("n64x5_dense", 6, 10, "my_step", dict(num_users=64, num_channels=5, highway_length=300, reward_design=1,
+                                           communication_range=250, mobility=True)),
 ]
 
 
