@@ -145,11 +145,14 @@ __device__ __noinline__ int vpd_bin_edges(double s, double W, double inv_binw, i
 }
 
 #ifndef DIRAL_MIN_BLOCKS
-#define DIRAL_MIN_BLOCKS 1
+#define DIRAL_MIN_BLOCKS 1       // tuning knob: minimum resident WARPS per SM for the G >= 16 instantiations
+#endif
+#ifndef DIRAL_GROUP_WARPS
+#define DIRAL_GROUP_WARPS 1      // tuning knob: warps (= environments at G == 32) per CTA for G >= 16
 #endif
 
 template <int G, bool FULL, int WARPS, int MODE, bool LAT>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 1 ? DIRAL_MIN_BLOCKS : 1))
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == DIRAL_GROUP_WARPS ? (DIRAL_MIN_BLOCKS + WARPS - 1) / WARPS : 1))
 step_group_kernel(const Params p)
 {
     constexpr int EPW = 32 / G;              // environments per warp
@@ -623,7 +626,7 @@ size_t smem_bytes(const Params &p, int warps)
 
 // one warp per CTA keeps the tail of the last wave short when few groups share a warp (G >= 16);
 // small groups pack 4 warps so that a CTA still carries a useful number of environments
-template <int G> struct WarpsFor { static constexpr int v = G >= 16 ? 1 : 4; };
+template <int G> struct WarpsFor { static constexpr int v = G >= 16 ? DIRAL_GROUP_WARPS : 4; };
 
 template <int G, bool FULL, int MODE, bool LAT>
 cudaError_t prepare_k(const Params &p)
