@@ -199,6 +199,10 @@ def run_gpu(args):
     launches0 = env.launch_count()
     barrier()
     clocks.start()
+    # a short spin kernel lets the host run ahead of the device, so that no timed interval contains the
+    # host's own launch latency (with 8 ranks per box the host loop is the slower one at first)
+    torch.cuda._sleep(int(2.0e7))
+    t_host0 = time.perf_counter()
     for k in range(steps):
         flush()
         ev0[k].record(stream)
@@ -211,6 +215,7 @@ def run_gpu(args):
                     out = vec.clone()
                     pending.append((out, all_reduce_metrics(out, async_op=True)))
         ev1[k].record(stream)
+    host_us_per_step = (time.perf_counter() - t_host0) / steps * 1e6
     for _, work in pending:
         if work is not None:
             work.wait()
@@ -219,7 +224,15 @@ def run_gpu(args):
     gpu_launches = env.launch_count() - launches0
     ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # every rank's own device time and median SM clock travel to rank 0: the headline uses the MAX
+        mine = torch.tensor([ms / steps, float(clk.get("sm_mhz") or 0.0), float(len(clk.get("reasons") or []))],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [float(t[0]) for t in allr], "sm_mhz": [float(t[1]) for t in allr],
+                    "throttle_reasons": [int(t[2]) for t in allr]}
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
     value = world * E_PER_GPU * N_UE * steps / (ms / 1e3)
@@ -280,6 +293,9 @@ def run_gpu(args):
                          "peak_source": peak_src},
             "extra": {"value_l2_resident_no_flush": warm_value,
                       "note": "value_l2_resident_no_flush = same loop without the L2 flush (state fits the 126 MB L2)"}}
+    line["extra"]["host_enqueue_us_per_step"] = host_us_per_step
+    if per_rank is not None:
+        line["extra"]["per_rank"] = per_rank
     if world == 1 and not args.no_cpu:
         v, dt, cores, sample = cpu_port_run(20, 3, target_seconds=15.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
