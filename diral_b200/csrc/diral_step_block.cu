@@ -38,6 +38,7 @@ namespace {
 // compile-time geometry of the NW-warp instantiation (N <= 32 NW vehicles)
 __host__ __device__ constexpr int geo_lpr(int nw) { return nw <= 1 ? 4 : nw <= 2 ? 8 : nw <= 4 ? 16 : 32; }  // lanes per reception in a row merge (8 key words each)
 __host__ __device__ constexpr int geo_ld(int nw) { return 8 * geo_lpr(nw) + 4; }                              // key row stride (words)
+__host__ __device__ constexpr int geo_ld16(int nw) { return 8 * geo_lpr(nw) + 8; }                            // packed (16-bit) key row stride, in keys
 __host__ __device__ constexpr int geo_threads(int nw) { return nw <= 1 ? 128 : nw <= 2 ? 256 : 512; }
 __host__ __device__ constexpr int geo_nwp(int nw) { return nw | 1; }                                         // odd stride of the bit-mask rows
 __host__ __device__ constexpr int geo_rc(int nw) { return nw <= 4 ? ((256 / nw) & ~31) : 64; }              // resources per decision chunk (lists no larger than the column buffers)
@@ -50,7 +51,9 @@ struct BlockSmem {
     size_t off_sx, off_sy, off_sxn, off_rewd, off_sa, off_aux, off_rew, off_recv, off_txm, off_cnt, off_inr, off_own, off_red, off_union,
         off_keys, off_edges, off_hist, bytes;
     size_t keys_bytes, list_bytes;
-    __host__ __device__ constexpr BlockSmem(int B, int nw, bool vpd_state, bool keys_in_smem)
+    // keys_mode: 2 = 32-bit keys in shared memory (the packed layout shares the region), 1 = packed keys only
+    // (32-bit fallback in the scratch slice), 0 = no keys in shared memory at all
+    __host__ __device__ constexpr BlockSmem(int B, int nw, bool vpd_state, int keys_mode)
         : off_sx(0), off_sy(0), off_sxn(0), off_rewd(0), off_sa(0), off_aux(0), off_rew(0), off_recv(0), off_txm(0), off_cnt(0), off_inr(0), off_own(0),
           off_red(0), off_union(0), off_keys(0), off_edges(0), off_hist(0), bytes(0), keys_bytes(0), list_bytes(0)
     {
@@ -73,7 +76,9 @@ struct BlockSmem {
         list_bytes = align16c(2 * (size_t)RC * T);
         const size_t colx = 8 * (size_t)NWARPS * T;
         off_union = o; o += align16c(list_bytes > colx ? list_bytes : colx);
-        keys_bytes = keys_in_smem ? align16c(4 * (size_t)T * geo_ld(nw)) : 0;      // sized by the padded vehicle count
+        // 32-bit keys when they fit (the packed 16-bit layout then uses the first half), else room for the packed
+        // layout only and the 32-bit fallback lives in the L2 scratch slice; sized by the padded vehicle count
+        keys_bytes = keys_mode == 2 ? align16c(4 * (size_t)T * geo_ld(nw)) : keys_mode == 1 ? align16c(2 * (size_t)T * geo_ld16(nw)) : 0;
         off_keys = o;  o += keys_bytes;
         off_hist = o;  o += vpd_state ? align16c(4 * (size_t)B * T) : 0;
         off_edges = o; o += align16c(8 * (size_t)(B + 1));        // (only the near-edge path of the binning reads them)
@@ -122,13 +127,18 @@ __device__ __forceinline__ uint4 max4(const uint4 &a, const uint4 &b)
     return make_uint4(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
 }
 
-template <int NW, bool KS>
+template <int NW, int KM>
 __global__ void __launch_bounds__(geo_threads(NW), 1024 / geo_threads(NW))
 step_block_kernel(const Params p, const int SB)
 {
+    constexpr bool KS = KM == 2;                  // 32-bit keys in shared memory (else in the scratch slice)
+    // packed 16-bit keys in shared memory: whenever there is no room for the 32-bit ones, and from 65 vehicles on
+    // (below that a pass has fewer receptions than one round of 32-bit sub-warps takes: nothing to halve)
+    constexpr bool HAS16 = KM == 1 || (KM == 2 && NW >= 3);
     constexpr int T = NW * 32;                    // padded vehicle count
     constexpr int LPR = geo_lpr(NW), LD = geo_ld(NW), TT = geo_threads(NW), NWARPS = TT / 32;
     constexpr int G = 32 / LPR;                   // receptions per warp and merge round
+    constexpr int LD16 = geo_ld16(NW), LPR16 = LPR / 2, G16 = 32 / LPR16;   // the same for packed 16-bit keys
     constexpr int NWP = geo_nwp(NW), RC = geo_rc(NW);
     const int N = p.N, R = p.R, B = p.B, S = p.S;
     int tid;      // read once through an opaque asm: ptxas otherwise re-reads SR_TID.X inside the hot loops
@@ -142,8 +152,8 @@ step_block_kernel(const Params p, const int SB)
     const double Cr = p.C, sentinel = p.sentinel;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr BlockSmem fix(0, NW, false, KS);    // offsets up to the keys do not depend on the bin count
-    const BlockSmem lay(B, NW, p.vpd_enabled != 0, KS);
+    constexpr BlockSmem fix(0, NW, false, KM);    // offsets up to the histogram do not depend on the bin count
+    const BlockSmem lay(B, NW, p.vpd_enabled != 0, KM);
     double *sx = reinterpret_cast<double *>(smem_raw + fix.off_sx);
     double *sy = reinterpret_cast<double *>(smem_raw + fix.off_sy);
     double *sxn = reinterpret_cast<double *>(smem_raw + fix.off_sxn);
@@ -165,7 +175,12 @@ step_block_kernel(const Params p, const int SB)
     unsigned *K;
     if constexpr (KS) K = reinterpret_cast<unsigned *>(smem_raw + fix.off_keys);
     else K = p.scratch + (size_t)blockIdx.x * N * LD;
+    // Packed keys (always in shared memory): fresh << SB | origin with fresh = seq - (tick - FMAX), 0 for "never
+    // heard".  Their order equals the order of the 32-bit keys whenever every sequence number of the environment is 0
+    // or within FMAX slots of the newest one; environments holding older entries take the 32-bit path.
+    unsigned short *K16 = reinterpret_cast<unsigned short *>(smem_raw + fix.off_keys);
     const unsigned srcmask = (1u << SB) - 1u;
+    const int FMAX = (1 << (16 - SB)) - 1, kbase = p.tick - FMAX;
 
     for (int i = tid; i <= B; i += TT) s_edges[i] = p.edges[i];
 
@@ -213,19 +228,25 @@ step_block_kernel(const Params p, const int SB)
         const bool flat0 = flat && sy[0] == 0.0;
         if (act && s_aux[tid] < 0) { atomicAdd(&s_tot[2], 1u); s_aux[tid] = 0; }   // out-of-range actions are counted
 
-        // keys: K[i][j] = (seq[i][j] (+1 on the diagonal: the tick, vehicle.py:58)) << SB | i
-        if (p.piggy) {
+        // keys: K[i][j] = (seq[i][j] (+1 on the diagonal: the tick, vehicle.py:58)) << SB | i, packed first
+        bool wide_needed = !HAS16;
+        if (HAS16 && p.piggy) {       // two subject columns per warp pass: one 32-bit store carries both packed keys
             const int32_t *seqg = p.tab_seq + tbase;
-#pragma unroll 2
-            for (int j = warp; j < N; j += NWARPS) {
+            for (int j = 2 * warp; j < N; j += 2 * NWARPS) {
+                const bool two = j + 1 < N;
 #pragma unroll
                 for (int q = 0; q < NW; ++q) {
                     const int i = q * 32 + lane;
                     if (i < N) {
-                        int s = seqg[j * N + i];
-                        if (i == j) s += 1;
-                        const unsigned key = ((unsigned)s << SB) | (unsigned)i;
-                        if (KS) K[i * LD + j] = key; else __stcg(K + i * LD + j, key);
+                        int s0 = seqg[j * N + i], s1 = two ? seqg[(j + 1) * N + i] : 0;
+                        if (i == j) s0 += 1;
+                        if (i == j + 1) s1 += 1;
+                        wide_needed = wide_needed || !(s0 == 0 || (unsigned)(s0 - kbase - 1) < (unsigned)FMAX)
+                                                  || !(s1 == 0 || (unsigned)(s1 - kbase - 1) < (unsigned)FMAX);
+                        const unsigned f0 = s0 ? (unsigned)(s0 - kbase) : 0u, f1 = s1 ? (unsigned)(s1 - kbase) : 0u;   // (garbage when
+                        const unsigned k0 = ((f0 << SB) | (unsigned)i) & 0xffffu, k1 = ((f1 << SB) | (unsigned)i) & 0xffffu;  // out of range)
+                        if (two) *reinterpret_cast<unsigned *>(K16 + i * LD16 + j) = k0 | (k1 << 16);
+                        else K16[i * LD16 + j] = (unsigned short)k0;
                     }
                 }
             }
@@ -245,6 +266,24 @@ step_block_kernel(const Params p, const int SB)
                     for (int b = 0; b < nb; ++b) m |= (dist2d(sx[w * 32 + b], sy[w * 32 + b], xu, yu) < Cr ? 1u : 0u) << b;
                 }
                 inr_s[u * NWP + w] = m;
+            }
+        }
+
+        const bool narrow = __syncthreads_or(wide_needed) == 0 && HAS16;   // uniform; also publishes K16 and inr_s
+        if (p.piggy && !narrow) {     // (rare) entries older than the packed range: 32-bit keys
+            const int32_t *seqg = p.tab_seq + tbase;
+#pragma unroll 2
+            for (int j = warp; j < N; j += NWARPS) {
+#pragma unroll
+                for (int q = 0; q < NW; ++q) {
+                    const int i = q * 32 + lane;
+                    if (i < N) {
+                        int s = seqg[j * N + i];
+                        if (i == j) s += 1;
+                        const unsigned key = ((unsigned)s << SB) | (unsigned)i;
+                        if (KS) K[i * LD + j] = key; else __stcg(K + i * LD + j, key);
+                    }
+                }
             }
         }
 
@@ -394,8 +433,28 @@ step_block_kernel(const Params p, const int SB)
             }
             __syncthreads();
 
-            // merges, pass by pass: G receptions per warp and round, LPR lanes per row
-            if (merge_mode) {
+            // merges, pass by pass: G receptions per warp and round, LPR lanes per row (packed keys: twice as many
+            // receptions per round, two columns per VIMNMX.U16x2)
+            if (merge_mode && narrow) {
+                const int grp = lane / LPR16, sub = lane - grp * LPR16;
+                for (int rl = 0; rl < nres; ++rl) {
+                    const int np = cnt_s[rl];
+                    if (np == 0) continue;
+                    const unsigned short *pl = list + rl * T;
+                    for (int k0 = warp * G16; k0 < np; k0 += NWARPS * G16) {   // receptions of one pass are independent
+                        const int k = k0 + grp;
+                        if (k < np) {
+                            const unsigned en = pl[k];
+                            uint4 *ra = reinterpret_cast<uint4 *>(K16 + (en >> 8) * LD16) + sub;
+                            const uint4 *rb = reinterpret_cast<const uint4 *>(K16 + (en & 255u) * LD16) + sub;
+                            const uint4 alo = ra[0], ahi = ra[LPR16], blo = rb[0], bhi = rb[LPR16];
+                            ra[0] = make_uint4(__vmaxu2(alo.x, blo.x), __vmaxu2(alo.y, blo.y), __vmaxu2(alo.z, blo.z), __vmaxu2(alo.w, blo.w));
+                            ra[LPR16] = make_uint4(__vmaxu2(ahi.x, bhi.x), __vmaxu2(ahi.y, bhi.y), __vmaxu2(ahi.z, bhi.z), __vmaxu2(ahi.w, bhi.w));
+                        }
+                    }
+                    __syncthreads();
+                }
+            } else if (merge_mode) {
                 const int grp = lane / LPR, sub = lane - grp * LPR;
                 for (int rl = 0; rl < nres; ++rl) {
                     const int np = cnt_s[rl];
@@ -460,10 +519,16 @@ step_block_kernel(const Params p, const int SB)
                 for (int q = 0; q < NW; ++q) {
                     const int i = q * 32 + lane;
                     if (i < N) {
-                        const unsigned key = KS ? K[i * LD + j] : __ldcg(K + i * LD + j);
-                        const int sn = (int)(key >> SB);
+                        int sn; unsigned origin;
+                        if (narrow) {
+                            const unsigned hk = K16[i * LD16 + j], f = hk >> SB;
+                            sn = f ? (int)f + kbase : 0; origin = hk & srcmask;
+                        } else {
+                            const unsigned key = KS ? K[i * LD + j] : __ldcg(K + i * LD + j);
+                            sn = (int)(key >> SB); origin = key & srcmask;
+                        }
                         double xn = xo[q];
-                        if (sn != s0[q]) { xn = colx[key & srcmask]; lu[q] = 0; }              // vehicle.py:41-47
+                        if (sn != s0[q]) { xn = colx[origin]; lu[q] = 0; }                     // vehicle.py:41-47
                         __stcs(seqg + j * N + i, sn); __stcs(lug + j * N + i, lu[q]); __stcs(xg + j * N + i, xn);
                         if (vpd) {
                             bool in = j != i && lu[q] < age_thr;                                // network.py:547
@@ -556,42 +621,56 @@ step_block_kernel(const Params p, const int SB)
 
 int block_warps(int N) { return std::max(1, (N + 31) / 32); }
 
-template <int NW, bool KS>
+template <int NW, int KM>
 cudaError_t prepare_nw(size_t smem)
 {
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(step_block_kernel<NW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(step_block_kernel<NW, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-template <int NW, bool KS>
+template <int NW, int KM>
 cudaError_t launch_nw(const Params &p, size_t smem, int SB, cudaStream_t stream)
 {
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_block_kernel<NW, KS>, geo_threads(NW), smem);
+    if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_block_kernel<NW, KM>, geo_threads(NW), smem);
     if (err != cudaSuccess) return err;
     const long long resident = (long long)sms * std::max(per_sm, 1);
     const unsigned grid = (unsigned)std::min<long long>(p.E, resident);
-    step_block_kernel<NW, KS><<<grid, geo_threads(NW), smem, stream>>>(p, SB);
+    step_block_kernel<NW, KM><<<grid, geo_threads(NW), smem, stream>>>(p, SB);
     return cudaGetLastError();
+}
+
+// where the table keys live (see BlockSmem): 32-bit keys in shared memory up to 128 vehicles (two CTAs per SM);
+// beyond that the packed 16-bit keys only, with the 32-bit fallback in the scratch slice; nothing if even those
+// do not fit next to the histogram
+int key_mode(const Params &p)
+{
+    const int nw = block_warps(p.N);
+    const bool vpd = p.vpd_enabled != 0;
+    if (nw <= 4 && BlockSmem(p.B, nw, vpd, 2).bytes <= SMEM_BUDGET) return 2;
+    if (BlockSmem(p.B, nw, vpd, 1).bytes <= SMEM_BUDGET) return 1;
+    return 0;
 }
 
 template <int NW>
 cudaError_t prepare_both(const Params &p)
 {
-    const bool fit = step_block_keys_fit_smem(p);
-    const size_t smem = step_block_smem_bytes(p, fit);
-    return fit ? prepare_nw<NW, true>(smem) : prepare_nw<NW, false>(smem);
+    const int km = key_mode(p);
+    const size_t smem = BlockSmem(p.B, NW, p.vpd_enabled != 0, km).bytes;
+    if constexpr (NW <= 4) { if (km == 2) return prepare_nw<NW, 2>(smem); }
+    return km == 1 ? prepare_nw<NW, 1>(smem) : prepare_nw<NW, 0>(smem);
 }
 
 template <int NW>
 cudaError_t launch_both(const Params &p, cudaStream_t stream)
 {
-    const bool fit = step_block_keys_fit_smem(p);
-    const size_t smem = step_block_smem_bytes(p, fit);
+    const int km = key_mode(p);
+    const size_t smem = BlockSmem(p.B, NW, p.vpd_enabled != 0, km).bytes;
     const int SB = key_src_bits(p.N);
-    return fit ? launch_nw<NW, true>(p, smem, SB, stream) : launch_nw<NW, false>(p, smem, SB, stream);
+    if constexpr (NW <= 4) { if (km == 2) return launch_nw<NW, 2>(p, smem, SB, stream); }
+    return km == 1 ? launch_nw<NW, 1>(p, smem, SB, stream) : launch_nw<NW, 0>(p, smem, SB, stream);
 }
 
 }  // namespace
@@ -603,16 +682,11 @@ int key_src_bits(int N)
     return b;
 }
 
-bool step_block_keys_fit_smem(const Params &p)
-{
-    const BlockSmem lay(p.B, block_warps(p.N), p.vpd_enabled != 0, true);
-    return lay.bytes <= SMEM_BUDGET;
-}
+bool step_block_keys_fit_smem(const Params &p) { return key_mode(p) == 2; }
 
-size_t step_block_smem_bytes(const Params &p, bool keys_in_smem)
+size_t step_block_smem_bytes(const Params &p, bool /*keys_in_smem: derived from p*/)
 {
-    const BlockSmem lay(p.B, block_warps(p.N), p.vpd_enabled != 0, keys_in_smem);
-    return lay.bytes;
+    return BlockSmem(p.B, block_warps(p.N), p.vpd_enabled != 0, key_mode(p)).bytes;
 }
 
 size_t step_block_scratch_words_per_env(int N) { return (size_t)N * geo_ld(block_warps(N)); }

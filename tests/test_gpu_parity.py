@@ -344,6 +344,33 @@ def test_long_run_with_stale_entries():
     assert stale.any(), "the scenario must contain entries older than the packed key range"
 
 
+@pytest.mark.parametrize("n,r,length,T,packed_range", [(40, 6, 12000, 1100, 1023), (140, 8, 40000, 300, 255)])
+def test_block_kernel_stale_entries_take_the_32_bit_keys(n, r, length, T, packed_range):
+    """The one-CTA-per-env kernel packs keys into 16 bits while every entry is within 2^(16 - log2 N) - 1 slots of
+    the newest one; on a sparse highway older entries appear and those environments fall back to 32-bit keys
+    (shared memory up to 128 vehicles, the L2 scratch slice beyond).  Integer state bit-exact throughout."""
+    from oracle.c_oracle import COracle
+    kw = dict(num_users=n, num_channels=r, highway_length=length, reward_design=2, communication_range=250,
+              mobility=True, bin_range=500, State=_shipped_state())
+    E, seed = 3, 33
+    orc = COracle(num_envs=E, **kw)
+    orc.reset_philox(seed)
+    env = _env(E, variant="block", seed=seed, **kw)
+    for t in range(T):
+        a = orc.philox_actions(seed, t)
+        o_ref, r_ref = orc.step("my_step", a, t)
+        env._step("my_step", a, t, True)
+        if t % 50 == 49 or t > T - 25:
+            s_ref = orc.obtain_state(o_ref, a, r_ref)
+            _close32(_np(env._state), s_ref, "state", t, exact=True)
+            assert (_np(env.tab_seq) == orc.tab_seq).all(), "seq table, slot %d" % t
+            assert (_np(env.tab_lu) == orc.tab_lu).all(), "last_updated table, slot %d" % t
+            assert (_np(env.tab_x) == orc.tab_x).all(), "xpos table, slot %d" % t
+    stale = (orc.tab_seq > 0) & (orc.tab_seq <= T - packed_range)
+    assert stale.any(), "the scenario must contain entries older than the packed key range"
+    env.close()
+
+
 @pytest.mark.parametrize("share", [True, False])
 def test_replay_ring_matches_reference_memory(share):
     """diral_b200.replay.Memory (ring tensors + diral_ring_gather) against the restated reference Memory
