@@ -234,11 +234,12 @@ step_block_kernel(const Params p, const int SB)
             const int32_t *seqg = p.tab_seq + tbase;
             for (int j = 2 * warp; j < N; j += 2 * NWARPS) {
                 const bool two = j + 1 < N;
+                const int32_t *sc = seqg + (long long)j * N + lane;
 #pragma unroll
                 for (int q = 0; q < NW; ++q) {
                     const int i = q * 32 + lane;
                     if (i < N) {
-                        int s0 = seqg[j * N + i], s1 = two ? seqg[(j + 1) * N + i] : 0;
+                        int s0 = sc[q * 32], s1 = two ? sc[N + q * 32] : 0;
                         if (i == j) s0 += 1;
                         if (i == j + 1) s1 += 1;
                         wide_needed = wide_needed || !(s0 == 0 || (unsigned)(s0 - kbase - 1) < (unsigned)FMAX)
@@ -502,11 +503,15 @@ step_block_kernel(const Params p, const int SB)
             for (int j = warp; j < N; j += NWARPS) {
                 int s0[NW], lu[NW]; double xo[NW];
                 const double xj = sx[j], yj = sy[j];
+                // this lane's entries of column j: one pointer per array, the 32-row steps are immediates
+                const long long cb = (long long)j * N + lane;
+                int32_t *sc = seqg + cb, *lc = lug + cb; double *xc = xg + cb;
+                const unsigned short *kc16 = K16 + lane * LD16 + j;
 #pragma unroll
                 for (int q = 0; q < NW; ++q) {
                     const int i = q * 32 + lane;
                     s0[q] = 0; lu[q] = 0; xo[q] = 0.0;
-                    if (i < N) { s0[q] = __ldcs(seqg + j * N + i); lu[q] = __ldcs(lug + j * N + i); xo[q] = __ldcs(xg + j * N + i); }
+                    if (i < N) { s0[q] = __ldcs(sc + q * 32); lu[q] = __ldcs(lc + q * 32); xo[q] = __ldcs(xc + q * 32); }
                 }
 #pragma unroll
                 for (int q = 0; q < NW; ++q) {
@@ -521,7 +526,7 @@ step_block_kernel(const Params p, const int SB)
                     if (i < N) {
                         int sn; unsigned origin;
                         if (narrow) {
-                            const unsigned hk = K16[i * LD16 + j], f = hk >> SB;
+                            const unsigned hk = kc16[q * 32 * LD16], f = hk >> SB;
                             sn = f ? (int)f + kbase : 0; origin = hk & srcmask;
                         } else {
                             const unsigned key = KS ? K[i * LD + j] : __ldcg(K + i * LD + j);
@@ -529,7 +534,7 @@ step_block_kernel(const Params p, const int SB)
                         }
                         double xn = xo[q];
                         if (sn != s0[q]) { xn = colx[origin]; lu[q] = 0; }                     // vehicle.py:41-47
-                        __stcs(seqg + j * N + i, sn); __stcs(lug + j * N + i, lu[q]); __stcs(xg + j * N + i, xn);
+                        __stcs(sc + q * 32, sn); __stcs(lc + q * 32, lu[q]); __stcs(xc + q * 32, xn);
                         if (vpd) {
                             bool in = j != i && lu[q] < age_thr;                                // network.py:547
                             const double xi = sxn[i];
