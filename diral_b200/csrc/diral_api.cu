@@ -104,6 +104,7 @@ void fill_base(Handle *h)
     const diral_cfg &c = h->cfg;
     diral::Params &p = h->base;
     p = diral::Params{};
+    p.n_slots = 1;
     p.E = c.E; p.env0 = c.env0; p.N = c.N; p.R = c.R; p.B = c.B; p.S = state_space(c);
     p.L = c.L; p.C = c.C; p.C2 = 2 * c.C; p.W = c.W; p.sentinel = c.sentinel;
     p.inv_binw = (double)c.B / (2.0 * c.W);
@@ -378,6 +379,29 @@ int diral_step(void *handle, int mode, const int32_t *actions, int64_t timestep,
 
 int diral_rollout(void *handle, int mode, int32_t T, int64_t t0, uint64_t seed, void *stream)
 {
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (mode < DIRAL_MY_STEP || mode > DIRAL_MY_STEP_CH) return fail(DIRAL_ERR_ARG, "mode must be 0, 1 or 2 (got %d)", mode);
+    if (T < 1) return fail(DIRAL_ERR_ARG, "T must be >= 1 (got %d)", T);
+    // The lane-group kernel (N <= 32) runs all T slots of an environment in ONE launch: small configurations are
+    // launch- and latency-bound per slot, and no slot needs anything another environment wrote.
+    if (use_group(h) && fused_state_ok(h->cfg) && T > 1) {
+        const int src_bits = diral::key_src_bits(diral::group_width(h->cfg.N));
+        if (h->cfg.add_piggy && h->ticks + T >= (1ll << (32 - src_bits)))
+            return fail(DIRAL_ERR_SEQ_RANGE, "slot %lld since reset exceeds the %d-bit sequence field of the packed table keys",
+                        h->ticks + T, 32 - src_bits);
+        DeviceGuard g(h->device);
+        diral::Params p = h->base;
+        p.mode = mode; p.timestep = t0; p.episode = 0.0; p.epsilon = 1.0; p.seed = seed;
+        p.tick = (int)(h->ticks + 1); p.n_slots = T;
+        p.build_state = 1; p.actions = nullptr; p.gen_actions = 1; p.actions_out = nullptr;
+        if (mode == DIRAL_MY_STEP_CH && h->bufs.lat) h->lat_live = true;
+        p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;
+        DIRAL_CUDA(diral::launch_step_group(p, static_cast<cudaStream_t>(stream)));
+        h->launches += 1;
+        if (h->cfg.add_piggy) h->ticks += T;
+        return DIRAL_OK;
+    }
     for (int32_t k = 0; k < T; ++k)
         if (int rc = diral_step(handle, mode, nullptr, t0 + k, 1, 0.0, 1.0, seed, nullptr, stream)) return rc;
     return DIRAL_OK;

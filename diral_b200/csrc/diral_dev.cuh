@@ -37,6 +37,7 @@ struct Params {
     // per-call
     int mode, track_lat, build_state, gen_actions;
     int prefetch_ahead;       // envs between this CTA's env and the one that will reuse its SM slot
+    int n_slots;              // consecutive slots one launch of the lane-group kernel runs (fused rollout), >= 1
     long long timestep;
     int tick;                 // table ticks since the reset including this slot (= every vehicle's own seq)
     double episode, epsilon;
@@ -111,15 +112,19 @@ __device__ __forceinline__ double py_mod_pos(double a, double m)
 }
 
 // Network.update_positions (network.py:189-206)
-__device__ __forceinline__ double mobility_step(const Params &p, double x, double v, int u)
+__device__ __forceinline__ double mobility_step_at(const Params &p, double x, double v, int u, long long timestep)
 {
     if (!p.mobility) return x;
     if (p.trace) {
-        long long t = p.timestep % p.trace_len;
+        long long t = timestep % p.trace_len;
         if (t < 0) t += p.trace_len;
         return p.trace[t * p.N + u];
     }
     return py_mod_pos(__dadd_rn(__dadd_rn(x, v), p.L), p.L);
+}
+__device__ __forceinline__ double mobility_step(const Params &p, double x, double v, int u)
+{
+    return mobility_step_at(p, x, v, u, p.timestep);
 }
 
 // numpy.histogram(.., bins=B, range=(-W, W)) bin of a sample with |s| < W: NumPy's equal-width fast

@@ -151,7 +151,7 @@ __device__ __noinline__ int vpd_bin_edges(double s, double W, double inv_binw, i
 #define DIRAL_GROUP_WARPS 1      // tuning knob: warps (= environments at G == 32) per CTA for G >= 16
 #endif
 
-template <int G, bool FULL, int WARPS, int MODE, bool LAT>
+template <int G, bool FULL, int WARPS, int MODE, bool LAT, bool ROLL>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS == DIRAL_GROUP_WARPS ? (DIRAL_MIN_BLOCKS + WARPS - 1) / WARPS : 1))
 step_group_kernel(const Params p)
 {
@@ -188,9 +188,17 @@ step_group_kernel(const Params p)
     const long long vbase = e * N;           // first vehicle of this env in the [E][N] arrays
     const long long tbase = e * (long long)N * N;
 
-    // ---- A: start every independent global access before the first dependent use ------------------
     constexpr int SL = G < 8 ? G : 8;        // columns per slab
-    constexpr int NSL = G / SL;              // slabs per table
+    // Fused rollout: one launch runs n_slots consecutive slots of this environment.  Every global word a slot
+    // reads was written by the same lane one slot earlier (table columns, own position) or never changes, so the
+    // slots of an environment need no more than the group-wide __syncwarp at the end of the loop body.
+    // (a separate instantiation: the single-slot kernel keeps its register allocation)
+    const int n_slots = ROLL ? p.n_slots : 1;
+#pragma unroll 1
+    for (int slot = 0; slot < n_slots; ++slot) {
+    const long long timestep = p.timestep + slot;
+    const int tick = p.tick + slot;
+    // ---- A: start every independent global access before the first dependent use ------------------
     int32_t *seqp = p.tab_seq + tbase + u, *lup = p.tab_lu + tbase + u;   // column j of this lane: [j * N]
     double *xp = p.tab_x + tbase + u;
     int a = -1; double x = 0.0, y = 0.0, v = 0.0; int bad = 0;
@@ -232,7 +240,7 @@ step_group_kernel(const Params p)
         }
     }
     if (act) {
-        if (p.gen_actions) a = philox_action(p.seed, u, p.env0 + e, p.timestep, R);
+        if (p.gen_actions) a = philox_action(p.seed, u, p.env0 + e, timestep, R);
         if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
         if (p.gen_actions && p.actions_out) p.actions_out[vbase + u] = a;
     }
@@ -333,7 +341,7 @@ step_group_kernel(const Params p)
                         const int t = __ffs(m) - 1;
                         if (is_rx && !((inr_mask >> t) & 1u)) latp[t * N] = -1;
                     }
-                    if (MODE == MODE_CH && tstar >= 0) latp[tstar * N] = (int32_t)p.timestep;    // test_env.py:436
+                    if (MODE == MODE_CH && tstar >= 0) latp[tstar * N] = (int32_t)timestep;      // test_env.py:436
                 }
                 if (MODE == MODE_CH && tstar >= 0) smem_red_inc(&recv_s[tstar]);      // test_env.py:396-397
             }
@@ -400,7 +408,7 @@ step_group_kernel(const Params p)
     }
 
     // ---- D: mobility -------------------------------------------------------------------------------
-    const double x_new = act ? mobility_step(p, x, v, u) : 0.0;
+    const double x_new = act ? mobility_step_at(p, x, v, u, timestep) : 0.0;
     if (act && p.mobility) p.pos_x[vbase + u] = x_new;
 
     // ---- C2/E: per slab -- tick, replay the merge script, gather xpos, age, write back, VPD ---------
@@ -436,7 +444,7 @@ step_group_kernel(const Params p)
         // order of the packed halves equals the order of the 32-bit keys, and one shuffle + one
         // VIMNMX.U16x2 merge two entries.  Slabs holding older information take the 32-bit path.
         constexpr int FMAX = (1 << (16 - SB)) - 1;
-        const int base = p.tick - FMAX;
+        const int base = tick - FMAX;
         bool narrow = true;
 #pragma unroll
         for (int q = 0; q < SL; ++q) {
@@ -615,6 +623,8 @@ step_group_kernel(const Params p)
     };
     copy_out(p.obs + vbase * R, obsS, N * R);
     if (want_state && !direct) copy_out(p.state + vbase * S, st, N * S);
+    __syncwarp(gmask);                       // the next slot reuses the shared-memory staging
+    }   // slot
 }
 
 template <int G>
@@ -634,12 +644,15 @@ cudaError_t prepare_k(const Params &p)
     Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for
     const size_t smem = smem_bytes<G>(q, WarpsFor<G>::v);
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT>,
+    cudaError_t err = cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    return cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 // CTAs of this instantiation the whole device holds at once (cached per instantiation and smem size)
-template <int G, bool FULL, int W, int MODE, bool LAT>
+template <int G, bool FULL, int W, int MODE, bool LAT, bool ROLL>
 long long resident_ctas(size_t smem)
 {
     static size_t cached_smem = ~(size_t)0; static long long cached = 0;
@@ -647,7 +660,7 @@ long long resident_ctas(size_t smem)
         int dev = 0, sms = 148, per_sm = 16;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_group_kernel<G, FULL, W, MODE, LAT>, W * 32, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_group_kernel<G, FULL, W, MODE, LAT, ROLL>, W * 32, smem) != cudaSuccess)
             per_sm = 16;
         cached = (long long)sms * per_sm; cached_smem = smem;
     }
@@ -662,9 +675,12 @@ cudaError_t launch_k(const Params &p, cudaStream_t stream)
     const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
     size_t smem = smem_bytes<G>(p, W);
     Params q = p;
-    q.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT>(smem) * envs_per_cta);
+    const bool roll = p.n_slots > 1;
+    q.prefetch_ahead = (int)((roll ? resident_ctas<G, FULL, W, MODE, LAT, true>(smem)
+                                   : resident_ctas<G, FULL, W, MODE, LAT, false>(smem)) * envs_per_cta);
     if (const char *pad = getenv("DIRAL_SMEM_PER_CTA")) smem = std::max(smem, (size_t)atoll(pad));   // tuning knob
-    step_group_kernel<G, FULL, W, MODE, LAT><<<(unsigned)grid, W * 32, smem, stream>>>(q);
+    if (roll) step_group_kernel<G, FULL, W, MODE, LAT, true><<<(unsigned)grid, W * 32, smem, stream>>>(q);
+    else step_group_kernel<G, FULL, W, MODE, LAT, false><<<(unsigned)grid, W * 32, smem, stream>>>(q);
     return cudaGetLastError();
 }
 

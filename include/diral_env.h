@@ -121,7 +121,8 @@ int diral_step(void *handle, int mode, const int32_t *actions, int64_t timestep,
 int diral_obtain_state(void *handle, const float *obs, const int32_t *actions, const float *rews,
                        double episode, double epsilon, float *out, void *stream);
 
-/* T consecutive slots of diral_step(mode, NULL, t0 + k, build_state=1, ...) with on-device actions. */
+/* T consecutive slots of diral_step(mode, NULL, t0 + k, build_state=1, ...) with on-device actions; the buffers
+ * hold the outputs of the last slot.  For N <= 32 (lane-group kernel, fused state) all T slots run in ONE launch. */
 int diral_rollout(void *handle, int mode, int32_t T, int64_t t0, uint64_t seed, void *stream);
 
 /* Network.update_velocity (network.py:208-222); draws [E][N] int8 in {1,2,3} or NULL -> Philox. */

@@ -48,9 +48,21 @@ def main():
         ms = sum(a.elapsed_time(b) for a, b in ev) / steps
         n, r, b = env.N, env.R, env.B
         alg = (32 * n * n + n * (36 + 8 * r + 4 * b) + (8 * n * n if mode == "my_step_ch" else 0)) * E
-        print(json.dumps({"config": name, "envs": E, "mode": mode, "us_per_slot": ms * 1e3,
-                          "agent_steps_per_s": E * n / (ms / 1e3), "algorithmic_GBps": alg / (ms / 1e3) / 1e9,
-                          "roofline_frac": alg / (ms / 1e3) / 1e9 / peak}))
+        row = {"config": name, "envs": E, "mode": mode, "us_per_slot": ms * 1e3,
+               "agent_steps_per_s": E * n / (ms / 1e3), "algorithmic_GBps": alg / (ms / 1e3) / 1e9,
+               "roofline_frac": alg / (ms / 1e3) / 1e9 / peak}
+        if n <= 32:
+            # fused rollout: T slots of every environment in ONE launch (diral_rollout), on-device actions; the
+            # state of these small configurations stays in L1/L2, so this is a latency number, not an HBM one
+            T = 200
+            env.rollout(T, mode)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(); env.rollout(T, mode); r1.record()
+            torch.cuda.synchronize()
+            us = r0.elapsed_time(r1) * 1e3 / T
+            row["rollout_us_per_slot"] = us
+            row["rollout_agent_steps_per_s"] = E * n / (us / 1e6)
+        print(json.dumps(row))
         env.close(); del env
         torch.cuda.empty_cache()
 
