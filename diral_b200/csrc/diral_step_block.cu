@@ -22,8 +22,9 @@
 //       conflict-free, exactly the merges that happen; one barrier per non-empty pass (a pass never modifies
 //       a transmitter's row and a receiver appears once per pass)
 //   D   rewards (lane-local: a vehicle's collision set is txm[a]) and mobility
-//   E   one warp per subject column: xpos is gathered from the origin row through a per-warp column buffer
-//       (an entry's position is a pure function of (subject, seq)), ages, write-back, and the positional
+//   E   one warp per subject column: xpos of a merged entry is the old position held by the origin row (an
+//       entry's position is a pure function of (subject, seq)), gathered from the column itself before any
+//       lane writes it back; ages, write-back, and the positional
 //       distribution (network.py:473-513) binned with shared-memory reductions -- no CTA barrier inside
 //   F   state rows (TestEnv.obtain_state, test_env.py:527-583): one warp per row, coalesced stores
 #include "diral_dev.cuh"
@@ -39,7 +40,7 @@ namespace {
 __host__ __device__ constexpr int geo_lpr(int nw) { return nw <= 1 ? 4 : nw <= 2 ? 8 : nw <= 4 ? 16 : 32; }  // lanes per reception in a row merge (8 key words each)
 __host__ __device__ constexpr int geo_ld(int nw) { return 8 * geo_lpr(nw) + 4; }                              // key row stride (words)
 __host__ __device__ constexpr int geo_ld16(int nw) { return 8 * geo_lpr(nw) + 8; }                            // packed (16-bit) key row stride, in keys
-__host__ __device__ constexpr int geo_threads(int nw) { return nw <= 1 ? 128 : nw <= 2 ? 256 : 512; }
+__host__ __device__ constexpr int geo_threads(int nw) { return nw <= 1 ? 128 : nw <= 2 ? 256 : nw <= 4 ? 512 : 1024; }
 __host__ __device__ constexpr int geo_nwp(int nw) { return nw | 1; }                                         // odd stride of the bit-mask rows
 __host__ __device__ constexpr int geo_rc(int nw) { return nw <= 4 ? ((256 / nw) & ~31) : 64; }              // resources per decision chunk (lists no larger than the column buffers)
 
@@ -72,9 +73,11 @@ struct BlockSmem {
         off_inr = o;   o += align16c(4 * (size_t)T * NWP);
         off_own = o;   o += align16c(4 * (size_t)T * NWP);    // txm[a[t]] per vehicle t
         off_red = o;   o += align16c(8 * 4 * 16 + 16);
-        // phase-disjoint: reception lists (B, C) and per-warp column buffers (E)
+        // phase-disjoint: reception lists of one resource chunk (B, C) and -- up to 128 vehicles -- the per-warp
+        // column buffers of phase E (beyond that the merged positions are gathered from global memory instead,
+        // which leaves room for 1024-thread CTAs)
         list_bytes = align16c(2 * (size_t)RC * T);
-        const size_t colx = 8 * (size_t)NWARPS * T;
+        const size_t colx = nw <= 4 ? 8 * (size_t)NWARPS * T : 0;
         off_union = o; o += align16c(list_bytes > colx ? list_bytes : colx);
         // 32-bit keys when they fit (the packed 16-bit layout then uses the first half), else room for the packed
         // layout only and the 32-bit fallback lives in the L2 scratch slice; sized by the padded vehicle count
@@ -171,7 +174,8 @@ step_block_kernel(const Params p, const int SB)
     unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + fix.off_red + 8 * 4 * 16); // received, pairs, bad
     unsigned *hist = reinterpret_cast<unsigned *>(smem_raw + fix.off_hist);            // [B][T]
     unsigned short *list = reinterpret_cast<unsigned short *>(smem_raw + fix.off_union);   // [RC][T]  rx << 8 | tx
-    double *colx = reinterpret_cast<double *>(smem_raw + fix.off_union) + warp * T;    // phase E
+    constexpr bool COLX = NW <= 4;                // merged positions through a per-warp shared-memory column buffer
+    double *colx = reinterpret_cast<double *>(smem_raw + fix.off_union) + warp * T;    // phase E (COLX only)
     unsigned *K;
     if constexpr (KS) K = reinterpret_cast<unsigned *>(smem_raw + fix.off_keys);
     else K = p.scratch + (size_t)blockIdx.x * N * LD;
@@ -513,16 +517,20 @@ step_block_kernel(const Params p, const int SB)
                     s0[q] = 0; lu[q] = 0; xo[q] = 0.0;
                     if (i < N) { s0[q] = __ldcs(sc + q * 32); lu[q] = __ldcs(lc + q * 32); xo[q] = __ldcs(xc + q * 32); }
                 }
+                // tick, key decode, and the position of every merged entry: it is the OLD position held by the
+                // origin row (a pure function of (subject, seq)), read from the per-warp column buffer or (N > 128)
+                // straight from this column in global memory -- the warp loaded it a moment ago and nobody has
+                // written it yet (the __syncwarp below)
+                const double *xcol = xg + (long long)j * N;
+                if constexpr (COLX) {
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) colx[q * 32 + lane] = (q * 32 + lane == j) ? xj : xo[q];
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int q = 0; q < NW; ++q) {
                     const int i = q * 32 + lane;
                     if (i == j) { s0[q] += 1; lu[q] = 0; xo[q] = xj; } else lu[q] += 1;       // vehicle.py:58-70
-                    colx[i] = xo[q];
-                }
-                __syncwarp();
-#pragma unroll
-                for (int q = 0; q < NW; ++q) {
-                    const int i = q * 32 + lane;
                     if (i < N) {
                         int sn; unsigned origin;
                         if (narrow) {
@@ -532,8 +540,19 @@ step_block_kernel(const Params p, const int SB)
                             const unsigned key = KS ? K[i * LD + j] : __ldcg(K + i * LD + j);
                             sn = (int)(key >> SB); origin = key & srcmask;
                         }
-                        double xn = xo[q];
-                        if (sn != s0[q]) { xn = colx[origin]; lu[q] = 0; }                     // vehicle.py:41-47
+                        if (sn != s0[q]) {                                                     // vehicle.py:41-47
+                            xo[q] = COLX ? colx[origin] : (((int)origin == j) ? xj : xcol[origin]);
+                            lu[q] = 0; s0[q] = sn;
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < NW; ++q) {
+                    const int i = q * 32 + lane;
+                    if (i < N) {
+                        const int sn = s0[q];
+                        const double xn = xo[q];
                         __stcs(sc + q * 32, sn); __stcs(lc + q * 32, lu[q]); __stcs(xc + q * 32, xn);
                         if (vpd) {
                             bool in = j != i && lu[q] < age_thr;                                // network.py:547
@@ -555,7 +574,6 @@ step_block_kernel(const Params p, const int SB)
                         }
                     }
                 }
-                __syncwarp();
             }
         }
         __syncthreads();
