@@ -108,6 +108,27 @@ def test_no_cpu_fallback():
     h = C.c_void_p()
     rc = lib.diral_create(C.byref(cfg), C.byref(h))
     assert rc == -2 and not h.value and b"cuda" in lib.diral_last_error().lower()
+    # the RealNeS-side helpers and the replay ring are device-only as well
+    import numpy as np
+    from diral_b200 import realness
+    from diral_b200.replay import Memory
+    z = np.zeros((2, 3), dtype=np.float32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        realness.pack_tables(z, z, z.astype(np.int32), z.astype(np.int32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        realness.SemiPersistentScheduling(4, 20, -97.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Memory(8, agents=4, state_space=3)
+
+
+def test_wire_entry_layout_matches_the_c_struct():
+    """realness.WIRE_DTYPE is diral_wire_entry (include/diral_env.h): 16 bytes, MA_NeighborTableEntry field order."""
+    from diral_b200 import realness
+    assert realness.WIRE_DTYPE.itemsize == 16
+    assert realness.WIRE_DTYPE.names == ("pos_x", "pos_y", "seq_num", "last_update")
+    assert [realness.WIRE_DTYPE.fields[n][1] for n in realness.WIRE_DTYPE.names] == [0, 4, 8, 12]
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "diral_env.h")).read()
+    assert "float   pos_x, pos_y;" in header and "int32_t seq_num, last_update;" in header
 
 
 def test_product_code_never_imports_the_oracle():
