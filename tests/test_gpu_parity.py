@@ -256,6 +256,27 @@ def test_host_buffer_step_matches_device_step():
     assert torch.equal(dev.episode_metrics(), host.episode_metrics())
 
 
+@pytest.mark.parametrize("n,r,mode,E", [(6, 5, "my_step", 37), (32, 20, "my_step_ch", 20), (16, 8, "my_step_design", 9),
+                                         (4, 3, "my_step_ch", 70), (29, 33, "my_step", 5)])
+def test_fused_rollout_equals_slot_by_slot(n, r, mode, E):
+    """diral_rollout runs T slots in ONE launch of the lane-group kernel; every buffer and table must equal what T
+    single-slot launches with on-device actions leave behind, bit for bit (also across a second rollout)."""
+    kw = dict(num_users=n, num_channels=r, highway_length=40.0 * n, reward_design=3 if mode == "my_step_ch" else 2,
+              communication_range=250, mobility=True, bin_range=500, State=_shipped_state(add_channel_obs=(n == 29)))
+    fused, single = _env(E, seed=9, **kw), _env(E, seed=9, **kw)
+    for T in (7, 12):
+        t0 = fused.t
+        fused.rollout(T, mode)
+        for k in range(T):
+            single._step(mode, None, t0 + k, True)
+        single.t = fused.t
+        for name in ("_state", "_rews", "_obs", "_tab_seq", "_tab_lu", "_tab_x", "lat", "pos_x"):
+            a, b = getattr(fused, name), getattr(single, name)
+            assert torch.equal(a, b), (name, T)
+        assert torch.equal(fused.episode_metrics(), single.episode_metrics())
+    fused.close(); single.close()
+
+
 def test_rollout_and_velocity_draws_follow_the_philox_specification():
     from oracle.c_oracle import COracle
     kw = dict(num_users=10, num_channels=4, highway_length=400, reward_design=2, communication_range=250,
