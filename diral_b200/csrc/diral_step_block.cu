@@ -372,11 +372,15 @@ step_block_kernel(const Params p, const int SB)
             }
             __syncthreads();
 
-            // decisions: thread (u, w) walks the in-range vehicles t of word w
+            // decisions: thread (u, w, part) walks the in-range vehicles t of one part of word w (a CTA has more
+            // threads than (vehicle, word) pairs below 128 vehicles: SUBS parts per word keep all of them busy)
+            constexpr int SUBS = TT > T * NW ? TT / (T * NW) : 1;
             int n_recv = 0, n_pairs = 0;
-            for (int it = tid; it < T * NW; it += TT) {
-                const int w = it / T, u = it - w * T;
+            for (int it = tid; it < T * NW * SUBS; it += TT) {
+                const int part = it / (T * NW), wu = it - part * (T * NW);
+                const int w = wu / T, u = wu - w * T;
                 if (u >= N) continue;
+                const unsigned part_mask = SUBS == 1 ? 0xffffffffu : (((1u << (32 / SUBS)) - 1u) << (part * (32 / SUBS)));
                 const int au = sa[u];
                 const double xu = sx[u], yu = sy[u];
                 unsigned inr[NW];
@@ -385,7 +389,7 @@ step_block_kernel(const Params p, const int SB)
                 unsigned mine_w = 0u;
 #pragma unroll
                 for (int w2 = 0; w2 < NW; ++w2) if (w2 == w) mine_w = inr[w2];
-                for (unsigned c = mine_w; c; c &= c - 1) {
+                for (unsigned c = mine_w & part_mask; c; c &= c - 1) {
                     const int t = w * 32 + __ffs(c) - 1;
                     const int at = sa[t];
                     if (at == au || at < r0 || at >= rend) continue;          // u transmits there itself (half duplex)
@@ -420,7 +424,7 @@ step_block_kernel(const Params p, const int SB)
                 }
                 if (p.track_lat) {                                                       // network.py:394
                     const unsigned live = (w * 32 + 32 <= N) ? 0xffffffffu : ((1u << (N - w * 32)) - 1u);
-                    for (unsigned c = ~mine_w & live; c; c &= c - 1) {
+                    for (unsigned c = ~mine_w & live & part_mask; c; c &= c - 1) {
                         const int t = w * 32 + __ffs(c) - 1;
                         const int at = sa[t];
                         if (at != au && at >= r0 && at < rend) p.lat[tbase + (long long)t * N + u] = -1;

@@ -20,9 +20,14 @@ CONFIGS = [
     ("C3 32x20", 4096, dict(num_users=32, num_channels=20, highway_length=800), "my_step"),
     ("C3 32x20 PRR", 4096, dict(num_users=32, num_channels=20, highway_length=800, reward_design=3), "my_step_ch"),
     ("C4 128x64 (1/8 of 16384)", 2048, dict(num_users=128, num_channels=64, highway_length=3200), "my_step"),
+    # configs[4]: vehicle-count sweep at 8192 envs, L = 25 N, R = max(3, N / 2)
+    ("C5 4x3", 8192, dict(num_users=4, num_channels=3, highway_length=100), "my_step"),
+    ("C5 8x4", 8192, dict(num_users=8, num_channels=4, highway_length=200), "my_step"),
     ("C5 16x8", 8192, dict(num_users=16, num_channels=8, highway_length=400), "my_step"),
+    ("C5 32x16", 8192, dict(num_users=32, num_channels=16, highway_length=800), "my_step"),
     ("C5 64x32", 8192, dict(num_users=64, num_channels=32, highway_length=1600), "my_step"),
-    ("C5 256x128", 1024, dict(num_users=256, num_channels=128, highway_length=6400), "my_step"),
+    ("C5 128x64", 8192, dict(num_users=128, num_channels=64, highway_length=3200), "my_step"),
+    ("C5 256x128", 8192, dict(num_users=256, num_channels=128, highway_length=6400), "my_step"),
 ]
 
 
