@@ -40,7 +40,10 @@ namespace {
 __host__ __device__ constexpr int geo_lpr(int nw) { return nw <= 1 ? 4 : nw <= 2 ? 8 : nw <= 4 ? 16 : 32; }  // lanes per reception in a row merge (8 key words each)
 __host__ __device__ constexpr int geo_ld(int nw) { return 8 * geo_lpr(nw) + 4; }                              // key row stride (words)
 __host__ __device__ constexpr int geo_ld16(int nw) { return 8 * geo_lpr(nw) + 8; }                            // packed (16-bit) key row stride, in keys
-__host__ __device__ constexpr int geo_threads(int nw) { return nw <= 1 ? 128 : nw <= 2 ? 256 : nw <= 4 ? 512 : 1024; }
+#ifndef DIRAL_NW2_THREADS
+#define DIRAL_NW2_THREADS 256
+#endif
+__host__ __device__ constexpr int geo_threads(int nw) { return nw <= 1 ? 128 : nw <= 2 ? DIRAL_NW2_THREADS : nw <= 4 ? 512 : 1024; }
 __host__ __device__ constexpr int geo_nwp(int nw) { return nw | 1; }                                         // odd stride of the bit-mask rows
 __host__ __device__ constexpr int geo_rc(int nw) { return nw <= 4 ? ((256 / nw) & ~31) : 64; }              // resources per decision chunk (lists no larger than the column buffers)
 
