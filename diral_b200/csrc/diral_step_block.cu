@@ -1,31 +1,36 @@
 // diral_step_block.cu -- fused time-slot kernel for 32 < N <= 256 vehicles (one CTA per environment,
 // persistent CTAs that walk the environments of the launch).
 //
-// Same slot semantics as diral_step_group.cu, re-mapped for rows that no longer fit one warp.  The packed
-// table keys  seq << SB | origin-row  live in shared memory as K[observer i][subject j] (row stride LD,
-// rows 16 B aligned), or in an L2-resident scratch slice per CTA when they do not fit.
+// Same slot semantics as diral_step_group.cu, re-mapped for rows that no longer fit one warp.  The table keys
+// live in shared memory as K[observer i][subject j] (rows 16 B aligned), per environment in one of two forms:
+// packed 16-bit keys  fresh << SB | origin-row  (fresh = seq - (tick - FMAX), two columns per VIMNMX.U16x2) while
+// every sequence number is 0 or within FMAX slots of the newest one, else 32-bit keys  seq << SB | origin-row
+// (in shared memory up to 128 vehicles, in an L2-resident scratch slice per CTA beyond).  See KM below.
 //
-//   A   inputs -> shared memory; keys from the seq columns (one warp per subject column, coalesced);
-//       in-range bit mask of every vehicle (Network.check_communicaiton_range, network.py:595-607), thread
-//       (u, w) forms word w of vehicle u against warp-uniform candidate positions
+//   A   inputs -> shared memory; packed keys from the seq columns (one warp per PAIR of subject columns,
+//       coalesced, one 32-bit store carries both keys) and a block vote on whether they are exact, 32-bit keys
+//       otherwise; in-range bit mask of every vehicle (Network.check_communicaiton_range, network.py:595-607),
+//       thread (u, w) forms word w of vehicle u against warp-uniform candidate positions
 //   B   DECISIONS, no table access.  Resources are taken RC at a time.  Transmitter masks per resource (the
 //       per-resource collision histogram, envs/test_env.py:149-157) by shared-memory atomicOr, copied to a
 //       per-vehicle "who shares my resource" mask.  Channel observations start as coalesced rows of the
-//       no-reception value.  Then thread (u, w) walks the in-range vehicles t of word w: every t transmits
-//       on exactly one resource, so t is u's nearest in-range transmitter there (Network.find_closest_tx,
-//       network.py:378-398) unless another in-range vehicle shares t's resource -- the common case costs a
-//       few mask words, no search.  Winners store the distance and append (u, t) to the list of pass a[t]
+//       no-reception value.  Then thread (u, w, part) walks the in-range vehicles t of (a part of) word w: every
+//       t transmits on exactly one resource, so t is u's nearest in-range transmitter there
+//       (Network.find_closest_tx, network.py:378-398) unless another in-range vehicle shares t's resource -- the
+//       common case costs a few mask words, no search.  Winners store the distance and append (u, t) to the
+//       list of pass a[t]
 //   C   MERGES, resource passes in ascending order (they are a true dependency: Vehicle.periodic_update
-//       aliases the transmitted table, vehicle.py:61).  One warp per reception applies
-//       Vehicle.received_update (vehicle.py:35-47) to the whole row with vector accesses:
+//       aliases the transmitted table, vehicle.py:61).  One sub-warp per reception applies
+//       Vehicle.received_update (vehicle.py:35-47) to the whole row with 16 B accesses:
 //           K[rx][:] = max(K[rx][:], K[tx][:])
 //       conflict-free, exactly the merges that happen; one barrier per non-empty pass (a pass never modifies
 //       a transmitter's row and a receiver appears once per pass)
 //   D   rewards (lane-local: a vehicle's collision set is txm[a]) and mobility
 //   E   one warp per subject column: xpos of a merged entry is the old position held by the origin row (an
-//       entry's position is a pure function of (subject, seq)), gathered from the column itself before any
-//       lane writes it back; ages, write-back, and the positional
-//       distribution (network.py:473-513) binned with shared-memory reductions -- no CTA barrier inside
+//       entry's position is a pure function of (subject, seq)), gathered through a per-warp column buffer
+//       (N <= 128) or from the column itself in global memory before any lane writes it back; ages,
+//       write-back, and the positional distribution (network.py:473-513) binned with shared-memory reductions
+//       -- no CTA barrier inside
 //   F   state rows (TestEnv.obtain_state, test_env.py:527-583): one warp per row, coalesced stores
 #include "diral_dev.cuh"
 #include "diral_launch.h"
@@ -45,7 +50,7 @@ __host__ __device__ constexpr int geo_ld16(int nw) { return 8 * geo_lpr(nw) + 8;
 #endif
 __host__ __device__ constexpr int geo_threads(int nw) { return nw <= 1 ? 128 : nw <= 2 ? DIRAL_NW2_THREADS : nw <= 4 ? 512 : 1024; }
 __host__ __device__ constexpr int geo_nwp(int nw) { return nw | 1; }                                         // odd stride of the bit-mask rows
-__host__ __device__ constexpr int geo_rc(int nw) { return nw <= 4 ? ((256 / nw) & ~31) : 64; }              // resources per decision chunk (lists no larger than the column buffers)
+__host__ __device__ constexpr int geo_rc(int nw) { return nw <= 4 ? ((256 / nw) & ~31) : 64; }              // resources per decision chunk (reception lists <= 16 KB, 32 KB beyond 128 vehicles)
 
 // Shared-memory carve-up.  Everything the hot loops touch sits at an offset that depends on the
 // instantiation only (a compile-time constant inside the kernel: addresses fold into the instructions
