@@ -510,7 +510,8 @@ def test_wire_vpd_golden(pos_dist):
             _close32(got[1:], g["c%d_o1" % i][1:], "wire VPD type 1, case %d" % i, 0)
 
 
-@pytest.mark.parametrize("M,N,bins,rng", [(4096, 32, 20, 500.0), (777, 257, 10, 250.0), (50, 1024, 256, 3000.0)])
+@pytest.mark.parametrize("M,N,bins,rng", [(4096, 32, 20, 500.0), (777, 257, 10, 250.0), (50, 1024, 256, 3000.0), (64, 2, 1, 50.0),
+                                         (33, 1, 5, 10.0)])
 def test_wire_vpd_random_vs_oracle(M, N, bins, rng):
     from diral_b200 import realness
     from oracle import wire
