@@ -254,6 +254,9 @@ def main():
                                     State=shipped_state()), "my_step", 25, 41)
     run_case("n70x16_ch_d3", dict(c3, num_users=70, num_channels=16, highway_length=2500,
                                   reward_design=3, State=shipped_state()), "my_step_ch", 12, 42)
+    # beyond 128 vehicles: packed keys only in shared memory, 1024-thread CTAs, positions gathered from global memory
+    run_case("n130x40_my_step", dict(c3, num_users=130, num_channels=40, highway_length=3250,
+                                     State=shipped_state()), "my_step", 8, 43)
 
     # ---- every reward design, collision-heavy (8 UE x 3 res), toy and non-toy -----------
     for d in (1, 2, 3, 4, 5):
