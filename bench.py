@@ -201,7 +201,8 @@ def run_gpu(args):
     clocks.start()
     # a short spin kernel lets the host run ahead of the device, so that no timed interval contains the
     # host's own launch latency (with 8 ranks per box the host loop is the slower one at first)
-    torch.cuda._sleep(int(2.0e7))
+    if hasattr(torch.cuda, "_sleep"):
+        torch.cuda._sleep(int(2.0e7))
     t_host0 = time.perf_counter()
     for k in range(steps):
         flush()

@@ -33,7 +33,8 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    torch.cuda._sleep(int(2.0e7))                  # let the host run ahead of the device (see bench.py)
+    if hasattr(torch.cuda, "_sleep"):
+        torch.cuda._sleep(int(2.0e7))              # let the host run ahead of the device (see bench.py)
     for k in range(steps):
         flush_w.zero_(); flush_r.sum()
         ev[k][0].record(); env._step("my_step", None, 30 + k, True); ev[k][1].record()
