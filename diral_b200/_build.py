@@ -50,20 +50,25 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
             raise RuntimeError("nvcc failed building %s" % out)
         return out
     os.makedirs(OBJ, exist_ok=True)
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + HEADERS):
-            cmd = [nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            with open(o + ".log", "w") as f:
-                f.write(r.stdout + r.stderr)
-            if verbose or r.returncode:
-                sys.stderr.write(r.stdout + r.stderr)
-            if r.returncode:
-                raise RuntimeError("nvcc failed on %s" % src)
+            jobs.append((src, o, subprocess.Popen([nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o], stdout=subprocess.PIPE,
+                                                  stderr=subprocess.STDOUT, text=True)))
+    failed = []
+    for src, o, proc in jobs:            # the translation units compile side by side (the slot kernels take minutes)
+        out, _ = proc.communicate()
+        with open(o + ".log", "w") as f:
+            f.write(out)
+        if verbose or proc.returncode:
+            sys.stderr.write(out)
+        if proc.returncode:
+            failed.append(src)
+    if failed:
+        raise RuntimeError("nvcc failed on %s" % ", ".join(failed))
     if force or _stale(LIB, objs):
         subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     return LIB
