@@ -244,6 +244,9 @@ step_block_kernel(const Params p, const int SB)
         bool wide_needed = !HAS16;
         if (HAS16 && p.piggy) {       // two subject columns per warp pass: one 32-bit store carries both packed keys
             const int32_t *seqg = p.tab_seq + tbase;
+            // no sequence number exceeds the tick, so the packed form is exact iff every non-zero one is above
+            // kbase: one unsigned minimum of seq - 1 per entry (0 wraps to the maximum)
+            unsigned oldest = 0xffffffffu;
             for (int j = 2 * warp; j < N; j += 2 * NWARPS) {
                 const bool two = j + 1 < N;
                 const int32_t *sc = seqg + (long long)j * N + lane;
@@ -254,8 +257,7 @@ step_block_kernel(const Params p, const int SB)
                         int s0 = sc[q * 32], s1 = two ? sc[N + q * 32] : 0;
                         if (i == j) s0 += 1;
                         if (i == j + 1) s1 += 1;
-                        wide_needed = wide_needed || !(s0 == 0 || (unsigned)(s0 - kbase - 1) < (unsigned)FMAX)
-                                                  || !(s1 == 0 || (unsigned)(s1 - kbase - 1) < (unsigned)FMAX);
+                        oldest = min(oldest, min((unsigned)(s0 - 1), (unsigned)(s1 - 1)));
                         const unsigned f0 = s0 ? (unsigned)(s0 - kbase) : 0u, f1 = s1 ? (unsigned)(s1 - kbase) : 0u;   // (garbage when
                         const unsigned k0 = ((f0 << SB) | (unsigned)i) & 0xffffu, k1 = ((f1 << SB) | (unsigned)i) & 0xffffu;  // out of range)
                         if (two) *reinterpret_cast<unsigned *>(K16 + i * LD16 + j) = k0 | (k1 << 16);
@@ -263,6 +265,7 @@ step_block_kernel(const Params p, const int SB)
                     }
                 }
             }
+            wide_needed = kbase > 0 && oldest < (unsigned)kbase;
         }
         // who is within communication range of whom (self included; it never counts as a candidate):
         // thread (u, w) forms word w of vehicle u, the candidate positions are warp-uniform broadcasts

@@ -445,12 +445,15 @@ step_group_kernel(const Params p)
         // VIMNMX.U16x2 merge two entries.  Slabs holding older information take the 32-bit path.
         constexpr int FMAX = (1 << (16 - SB)) - 1;
         const int base = tick - FMAX;
-        bool narrow = true;
+        // No sequence number exceeds the tick (a vehicle's own), so "0 or within FMAX of the newest" is
+        // "every non-zero one is above base": one unsigned minimum of seq - 1 (0 wraps to the maximum) per column
+        unsigned oldest = 0xffffffffu;
 #pragma unroll
         for (int q = 0; q < SL; ++q) {
             if (jbase + q == u) sb[q] += 1;                                       // vehicle.py:58 (tick)
-            narrow = narrow && (sb[q] == 0 || (unsigned)(sb[q] - base - 1) < (unsigned)FMAX);
+            oldest = min(oldest, (unsigned)(sb[q] - 1));
         }
+        const bool narrow = base <= 0 || oldest >= (unsigned)base;
         if ((SL & 1) == 0 && (__ballot_sync(gmask, !narrow) & gmask) == 0u) {
             unsigned k2[SL / 2 > 0 ? SL / 2 : 1];
 #pragma unroll
