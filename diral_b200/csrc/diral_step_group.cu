@@ -438,7 +438,7 @@ step_group_kernel(const Params p)
                 s_next[q] = (FULL || (j < N && act)) ? seqp[j * N] : 0;
             }
         }
-        unsigned key[SL];
+        int snv[SL], org[SL];                    // after the replay: sequence number and origin row of every entry
         // Two columns per register when every sequence number of the slab is either 0 (never heard) or
         // within FMAX slots of the newest possible one: then  fresh = seq - base  fits 16 - SB bits, the
         // order of the packed halves equals the order of the 32-bit keys, and one shuffle + one
@@ -468,12 +468,13 @@ step_group_kernel(const Params p)
                 for (int i = 0; i < SL / 2; ++i) k2[i] = __vmaxu2(k2[i], __shfl_sync(gmask, k2[i], srcl, G));
             }
 #pragma unroll
-            for (int q = 0; q < SL; ++q) {
-                const unsigned hk = (k2[q / 2] >> (16 * (q & 1))) & 0xffffu;
+            for (int q = 0; q < SL; ++q) {       // straight to (new sequence number, origin row): no 32-bit key is formed
+                const unsigned hk = (q & 1) ? (k2[q / 2] >> 16) : (k2[q / 2] & 0xffffu);
                 const unsigned f = hk >> SB;
-                key[q] = ((f ? f + (unsigned)base : 0u) << SB) | (hk & (unsigned)(G - 1));
+                snv[q] = f ? (int)f + base : 0; org[q] = (int)(hk & (unsigned)(G - 1));
             }
         } else {
+            unsigned key[SL];
 #pragma unroll
             for (int q = 0; q < SL; ++q) key[q] = ((unsigned)sb[q] << SB) | (unsigned)u;
             // replay the passes in order on this slab's columns
@@ -482,14 +483,16 @@ step_group_kernel(const Params p)
 #pragma unroll
                 for (int q = 0; q < SL; ++q) key[q] = max(key[q], __shfl_sync(gmask, key[q], srcl, G));
             }
+#pragma unroll
+            for (int q = 0; q < SL; ++q) { snv[q] = (int)(key[q] >> SB); org[q] = (int)(key[q] & (unsigned)(G - 1)); }
         }
         // gather xpos from the origin row, age, write back (independent per column => ILP)
 #pragma unroll
         for (int q = 0; q < SL; ++q) {
             if (jbase + q == u) { lb[q] = 0; xb[q] = x; } else lb[q] += 1;        // vehicle.py:59-70 (tick)
-            const int sn = (int)(key[q] >> SB);
+            const int sn = snv[q];
             const bool changed = sn != sb[q];                  // strictly newer version merged in
-            const int src = changed ? (int)(key[q] & (unsigned)(G - 1)) : u;
+            const int src = changed ? org[q] : u;
             xb[q] = __shfl_sync(gmask, xb[q], src, G);
             if (changed) lb[q] = 0;                            // vehicle.py:47
             sb[q] = sn;
