@@ -12,9 +12,14 @@ shipped State block, B=20, W=500, C=250, L=800, reward design 2 -- so N GPUs ste
 
 Timing: per-step CUDA events on the launching stream, L2 flushed (untimed) before every timed step so
 the tables really come from HBM, summed over the K steps, max over ranks.  `e2e` drives the C-ABI
-host-buffer entry point (pinned host actions in, state + rewards out) and is wall-clock.
-`--impl reference` times the CPU port of the reference algorithm (oracle/, plain C, all host threads)
-on a bounded sample of the same workload; the Python reference itself cannot travel to the GPU box.
+host-buffer entry point diral_step_host (pinned host actions in, [E,N,S] float32 state rows + rewards out in the
+caller's pinned buffers, every copy and the host-side row assembly of the compact format inside the timed
+region) and is wall-clock; `extra.e2e_full_format` is the same call moving the full rows over PCIe.
+`extra.configs` carries the other BASELINE configs (C2, C4, the C5 sweep, C3 in PRR mode, the un-fused State
+variants), each with its own roofline fraction.  `cpu_baseline` = the C port of the reference on all host
+threads (a bounded sample) plus `reference_python`: the UNMODIFIED reference TestEnv (oracle/_ref, placed there
+by oracle/install_ref.py) on one core and on P processes.  `--impl reference` times the C port (the faster,
+hence conservative, CPU arm) and reports the Python reference beside it.
 """
 from __future__ import annotations
 
@@ -22,6 +27,7 @@ import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -88,6 +94,31 @@ def cpu_port_run(steps, warmup, target_seconds=20.0):
     return value, dt, cores, sample
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def reference_python_run(seconds=3.0):
+    """The unmodified reference TestEnv.my_step + obtain_state (envs/test_env.py:124,527) on this box's host cores,
+    in a child process (it forks P workers; this process may hold a CUDA context).  None when oracle/_ref is empty."""
+    from oracle import ref_python
+    if not ref_python.available():
+        return {"unavailable": "oracle/_ref/envs is empty (run python oracle/install_ref.py where /root/reference exists)"}
+    try:
+        out = subprocess.run([sys.executable, "-m", "oracle.ref_python", json.dumps(ENV_KW), "my_step", str(seconds), "0"],
+                             cwd=ROOT, capture_output=True, text=True, timeout=120)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": "reference run failed: %r" % (exc,)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -97,12 +128,14 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "cpu_model": cpu_model(), "reference_python": reference_python_run(3.0)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "CPU port (oracle/diral_oracle.c) of the reference's my_step + obtain_state; the reference is "
-                    "pure Python and cannot travel to the GPU box (it ran ~60x slower per core than this port in "
-                    "the build container, SURVEY.md section 6)"}
+            "note": "value = the plain-C port (oracle/diral_oracle.c) of the reference's my_step + obtain_state on all "
+                    "host threads: the reference itself is single-threaded Python, ~60x slower per core, so the port "
+                    "is the conservative CPU arm; cpu_baseline.reference_python is the unmodified reference "
+                    "(oracle/_ref) timed in the same run"}
     print_line(json.dumps(line))
 
 
@@ -155,6 +188,71 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def _peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def extra_configs(world):
+    """The other BASELINE.json configs (SURVEY.md 8(d) sizes: L = 25 N, R = max(3, N / 2) for the sweep), per GPU."""
+    base = dict(reward_design=2, communication_range=250, mobility=True, bin_range=500)
+    c4 = ("C4 128x64, 2048 envs per GPU (configs[3]: 16384 envs over 8 GPUs)", 2048,
+          dict(num_users=128, num_channels=64, highway_length=3200), "my_step", STATE)
+    if world > 1:
+        return [(n, e, dict(base, **kw), m, st) for n, e, kw, m, st in [c4]]
+    vpd1 = dict(STATE, add_positional_dist_type=1)
+    direct = dict(STATE, add_positional_dist_piggy=False, add_positional_dist=True)
+    cfgs = [
+        ("C2 6x5, 1024 envs (configs[1])", 1024, dict(num_users=6, num_channels=5, highway_length=1170), "my_step", STATE),
+        ("C3 32x20 PRR (my_step_ch, design 3), 4096 envs", 4096,
+         dict(num_users=32, num_channels=20, highway_length=800, reward_design=3), "my_step_ch", STATE),
+        c4,
+        ("C3 32x20 VPD type 1 (un-fused obtain_state), 4096 envs", 4096,
+         dict(num_users=32, num_channels=20, highway_length=800), "my_step", vpd1),
+        ("C3 32x20 sorted direct distribution (un-fused obtain_state), 4096 envs", 4096,
+         dict(num_users=32, num_channels=20, highway_length=800), "my_step", direct),
+    ]
+    for n in (4, 8, 16, 32, 64, 128, 256):
+        cfgs.append(("C5 %dx%d, 8192 envs (configs[4] sweep)" % (n, max(3, n // 2)), 8192,
+                     dict(num_users=n, num_channels=max(3, n // 2), highway_length=25 * n), "my_step", STATE))
+    return [(n, e, dict(base, **kw), m, st) for n, e, kw, m, st in cfgs]
+
+
+def run_extra_configs(torch, dist, TestEnv, dev, rank, world, flush, peak, slots=12, warm=30):
+    """Device-timed slot time of each extra config (L2 flushed before every timed slot, on-device actions)."""
+    rows = []
+    for name, E, kw, mode, state in extra_configs(world):
+        env = TestEnv(num_envs=E, device=dev, seed=1, env_offset=rank * E, State=state, **kw)
+        for t in range(warm):
+            env._step(mode, None, t, True)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(slots)]
+        for k in range(slots):
+            flush()
+            ev[k][0].record(); env._step(mode, None, warm + k, True); ev[k][1].record()
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in ev) / slots
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        n, r, b = env.N, env.R, env.B
+        piggy = bool(state["add_positional_dist_piggy"])
+        alg = ((32 * n * n if piggy else 0) + n * (36 + 8 * r + 4 * env.S - 4 * r)
+               + (8 * n * n if mode == "my_step_ch" else 0)) * E
+        row = {"config": name, "envs_per_gpu": E, "mode": mode, "us_per_slot": ms * 1e3,
+               "agent_steps_per_s": world * E * n / (ms / 1e3), "roofline_frac": alg / (ms / 1e3) / 1e9 / peak,
+               "kernel": ("step_group_kernel" if n <= 32 else "step_block_kernel")
+                         + ("" if env.lib.diral_get_option(env._handle, b"compact_ok") else " + obtain_state_kernel")}
+        if alg < 32e6:
+            row["note"] = "launch / latency bound: %.1f MB of state per slot" % (alg / 1e6)
+        rows.append(row)
+        env.close(); del env
+        torch.cuda.empty_cache()
+    return rows
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -190,6 +288,9 @@ def run_gpu(args):
     actions = [env.sample(t) for t in range(n_act)]
     for t in range(100):                          # leave the 20-slot phantom phase
         env.step(actions[t % n_act])
+    if world > 1:                                 # communicator set-up is not part of any timed interval
+        warm_vec = env.episode_metrics().clone()
+        all_reduce_metrics(warm_vec)
     for _ in range(warmup):
         flush(); env.step(actions[0])
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -208,21 +309,24 @@ def run_gpu(args):
         flush()
         ev0[k].record(stream)
         env.step(actions[k % n_act])
-        if (k + 1) % EPISODE == 0:                # end of episode: metric vector + the one collective
+        if (k + 1) % EPISODE == 0 or k == steps - 1:   # end of episode (and of the run): metric vector + THE collective
             vec = env.episode_metrics()
-            if world > 1:
-                side.wait_stream(stream)
-                with torch.cuda.stream(side):
-                    out = vec.clone()
-                    pending.append((out, all_reduce_metrics(out, async_op=True)))
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(side)
+                out = vec.clone()
+                work = all_reduce_metrics(out, async_op=True) if world > 1 else None
+                if work is not None:
+                    work.wait()                   # orders the side stream after the collective (no host block)
+                s1.record(side)
+                pending.append((out, s0, s1))
         ev1[k].record(stream)
     host_us_per_step = (time.perf_counter() - t_host0) / steps * 1e6
-    for _, work in pending:
-        if work is not None:
-            work.wait()
     barrier()
     clk = clocks.stop()
     gpu_launches = env.launch_count() - launches0
+    allreduce_us = [a.elapsed_time(b) * 1e3 for _, a, b in pending]
     ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     per_rank = None
@@ -248,58 +352,83 @@ def run_gpu(args):
     barrier()
     warm_value = E_PER_GPU * N_UE * steps / (e0.elapsed_time(e1) / 1e3)
 
-    # --- e2e through the C ABI with host buffers (pinned), copies inside the timed region
+    # --- e2e through the C ABI with host buffers (pinned), copies + host-side row assembly inside the timed region
     S = env.S
     h_act = [a.cpu().pin_memory() for a in actions[:8]]
     h_state = torch.empty((E_PER_GPU, N_UE, S), dtype=torch.float32).pin_memory()
     h_rews = torch.empty((E_PER_GPU, N_UE), dtype=torch.float32).pin_memory()
     e2e_steps = max(10, min(steps, 200))
-    for k in range(3):
-        env.step_host(h_act[k % 8], h_state, h_rews)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        env.step_host(h_act[k % 8], h_state, h_rews)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * E_PER_GPU * N_UE * e2e_steps / float(t_e2e.item())
+
+    def e2e_leg(fmt):
+        env.set_host_format(fmt)
+        for k in range(3):
+            env.step_host(h_act[k % 8], h_state, h_rews)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            env.step_host(h_act[k % 8], h_state, h_rews)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * E_PER_GPU * N_UE * e2e_steps / float(t.item())
+
+    e2e_full = e2e_leg("full")
+    e2e_value = e2e_leg("compact")
+    host_threads = int(env.lib.diral_get_option(env._handle, b"host_threads"))
     h2d = E_PER_GPU * N_UE * 4
-    d2h = E_PER_GPU * N_UE * (S + 1) * 4
+    d2h_full = E_PER_GPU * N_UE * (S + 1) * 4
+    d2h = E_PER_GPU * N_UE * (N_BINS + 4)          # one byte per VPD bin + the float32 reward
+    env.close()
+
+    peak, peak_src = _peak()
+    configs = None
+    if not args.no_configs:
+        del flush_r
+        flush_r = torch.ones(64 << 20, dtype=torch.float32, device=dev)
+        configs = run_extra_configs(torch, dist, TestEnv, dev, rank, world, flush, peak)
 
     if rank != 0:
         return
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg = algorithmic_bytes_per_env_step(N_UE, N_RES, N_BINS) * E_PER_GPU
     k_ms = ms / steps                             # the fused slot kernel is the only kernel of a step
     achieved = alg / (k_ms / 1e3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("step_group_kernel_dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get("step_group_kernel_dram_bytes_per_launch")
+        traffic_src = "profiles/traffic.json (%s): one ncu --set full capture of this kernel, NOT measured in this run" \
+                      % tj.get("capture", "round 1")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "diral_step_host (C ABI, pinned host buffers, synchronous)"},
+                    "steps": e2e_steps, "host_threads": host_threads,
+                    "api": "diral_step_host (C ABI, pinned host buffers, synchronous), host_format=compact: VPD bin "
+                           "counts (1 B per bin) + rewards cross PCIe, the [E,N,S] float32 rows are assembled in the "
+                           "caller's buffer by the library's host threads inside the timed region"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "step_group_kernel<32>", "algorithmic_bytes_per_launch": alg,
-                         "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "step_group_kernel<32>",
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             "extra": {"value_l2_resident_no_flush": warm_value,
-                      "note": "value_l2_resident_no_flush = same loop without the L2 flush (state fits the 126 MB L2)"}}
+                      "note": "value_l2_resident_no_flush = same loop without the L2 flush (state fits the 126 MB L2)",
+                      "e2e_full_format": {"value": e2e_full, "unit": UNIT, "d2h_bytes_per_step": d2h_full,
+                                          "note": "same call, host_format=full: the float32 rows themselves cross PCIe"},
+                      "episode_allreduce": {"count_in_timed_loop": len(allreduce_us), "world": world,
+                                            "side_stream_us": allreduce_us,
+                                            "note": "110-double metric vector: clone + all-reduce(sum) on a side stream "
+                                                    "(NCCL when world > 1), every 25 slots and after the last one"}}}
     line["extra"]["host_enqueue_us_per_step"] = host_us_per_step
+    if configs is not None:
+        line["extra"]["configs"] = configs
     if per_rank is not None:
         line["extra"]["per_rank"] = per_rank
     if world == 1 and not args.no_cpu:
         v, dt, cores, sample = cpu_port_run(20, 3, target_seconds=15.0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "cpu_model": cpu_model(), "reference_python": reference_python_run(3.0)}
     print_line(json.dumps(line))
 
 
@@ -322,6 +451,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip extra.configs (the other BASELINE configs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,9 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libdiral_env.so")
-SOURCES = ["diral_api.cu", "diral_step_group.cu", "diral_step_block.cu", "diral_aux.cu", "diral_wire.cu"]
-HEADERS = [os.path.join(CSRC, "diral_dev.cuh"), os.path.join(CSRC, "diral_launch.h"),
+SOURCES = ["diral_api.cu", "diral_step_group.cu", "diral_step_block.cu", "diral_aux.cu", "diral_wire.cu",
+           "diral_host.cpp"]
+HEADERS = [os.path.join(CSRC, "diral_dev.cuh"), os.path.join(CSRC, "diral_launch.h"), os.path.join(CSRC, "diral_host.h"),
            os.path.join(os.path.dirname(HERE), "include", "diral_env.h")]
+HASH = LIB + ".srchash"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-Xptxas", "-v"]
 
@@ -26,6 +28,25 @@ def nvcc() -> str:
     if not os.path.exists(exe):
         raise RuntimeError("nvcc not found: libdiral_env.so cannot be built here")
     return exe
+
+
+def source_hash() -> str:
+    """sha256 over the flags and every source / header: what the built library is checked against at load time
+    (content, not mtimes -- the library travels to the GPU box next to a fresh copy of the sources)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def up_to_date() -> bool:
+    if not (os.path.exists(LIB) and os.path.exists(HASH)):
+        return False
+    with open(HASH) as f:
+        return f.read().strip() == source_hash()
 
 
 def _stale(target: str, deps) -> bool:
@@ -49,11 +70,13 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("nvcc failed building %s" % out)
         return out
+    if not force and up_to_date():
+        return LIB
     os.makedirs(OBJ, exist_ok=True)
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + HEADERS):
             jobs.append((src, o, subprocess.Popen([nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o], stdout=subprocess.PIPE,
@@ -69,8 +92,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
             failed.append(src)
     if failed:
         raise RuntimeError("nvcc failed on %s" % ", ".join(failed))
-    if force or _stale(LIB, objs):
-        subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    if force or _stale(LIB, objs) or not up_to_date():
+        subprocess.check_call([nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread"])
+        with open(HASH, "w") as f:
+            f.write(source_hash())
     return LIB
 
 

@@ -10,7 +10,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MODES = {"my_step": 0, "my_step_design": 1, "my_step_ch": 2}
 ERR_NAMES = {-1: "DIRAL_ERR_ARG", -2: "DIRAL_ERR_CUDA", -3: "DIRAL_ERR_UNBOUND", -4: "DIRAL_ERR_SEQ_RANGE",
              -5: "DIRAL_ERR_UNSUPPORTED"}
@@ -77,6 +77,10 @@ SYMBOLS = {
     "diral_sps_step": (C.c_int, [_I64, _I32, _P, C.POINTER(DiralSpsCfg), _P, _U64, _I64, _P, _P, _P, _P, _P]),
     "diral_step_host": (C.c_int, [_P, C.c_int, _P, _I64, _D, _D, _P, _P, _P, _P]),
     "diral_launch_count": (C.c_int64, [_P]),
+    "diral_get_option": (C.c_int64, [_P, C.c_char_p]),
+    "diral_reset_topology": (C.c_int, [_P, _P, _P, _P, _U64, _P]),
+    "diral_expand_state_host": (C.c_int, [C.POINTER(DiralCfg), _I64, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I32, _P]),
+    "diral_ring_put": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
 }
 
 _lib = None
@@ -99,9 +103,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("DIRAL_ENV_LIB") or _build.LIB      # DIRAL_ENV_LIB: tuning variants only
-    if not os.path.exists(path):
-        path = _build.build()            # raises when nvcc is absent: no fallback exists
+    path = os.environ.get("DIRAL_ENV_LIB")                   # DIRAL_ENV_LIB: tuning variants only
+    if not path:
+        # build() is a no-op when the library matches the sources (content hash, so a checkout or a copy to the
+        # GPU box does not trigger it); it raises when a rebuild is needed and nvcc is absent: no fallback exists
+        path = _build.build()
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol

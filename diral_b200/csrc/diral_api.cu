@@ -3,13 +3,19 @@
 // either launches the sm_100a kernels or fails with a message.
 #include "../../include/diral_env.h"
 #include "diral_dev.cuh"
+#include "diral_host.h"
 #include "diral_launch.h"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
+#include <sched.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -32,12 +38,14 @@ int fail(int code, const char *fmt, ...)
     } while (0)
 
 enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2 };
+constexpr int MAX_HOST_CHUNKS = 32;
 
 struct Handle {
     diral_cfg cfg{};
     diral_buffers bufs{};
     diral::Params base{};
     bool bound = false;
+    bool group_ok = false, block_ok = false;   // which slot kernels this configuration's shared-memory carve-up fits
     int device = 0;
     int variant = VARIANT_AUTO;
     int force_track_lat = 0;
@@ -48,6 +56,16 @@ struct Handle {
     int32_t *d_actions = nullptr;   // staging for generated / host-side actions
     cudaStream_t pipe[2] = {nullptr, nullptr};   // diral_step_host: env chunks alternate between these
     cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
+    // compact host format of diral_step_host (see diral_host.h)
+    int host_format = 0;            // 0 = full rows over PCIe, 1 = compact record + host-side row assembly
+    int host_threads = 0;           // 0 = pick from the CPUs this process may run on
+    int host_chunks = 4;
+    diral::HostPool *pool = nullptr;
+    uint8_t *d_counts = nullptr;    // [E][N][B] device
+    uint8_t *h_counts = nullptr;    // pinned staging of the same
+    float *h_obs_stage = nullptr;   // pinned [E][N][R] when the State block wants obs and the caller passes no h_obs
+    double *h_kin = nullptr;        // pinned [3][E][N]: post-mobility x, y, velocity (add_position / add_velocity)
+    cudaEvent_t chunk_ev[MAX_HOST_CHUNKS] = {};
 };
 
 struct DeviceGuard {
@@ -91,12 +109,30 @@ int check_cfg(const diral_cfg *c)
 bool use_group(const Handle *h)
 {
     if (h->variant == VARIANT_BLOCK) return false;
-    return h->cfg.N <= diral::GROUP_MAX_N;
+    if (h->variant == VARIANT_AUTO && !h->block_ok) return true;
+    return h->group_ok;
 }
 
 bool fused_state_ok(const diral_cfg &c)
 {
     return !c.add_positional_dist && !(c.add_piggy && c.pos_dist_type == 1);
+}
+
+// the compact host format carries the positional distribution as one byte per bin (<= 255 samples per observer)
+bool compact_ok(const diral_cfg &c)
+{
+    return fused_state_ok(c) && c.N <= 256;
+}
+
+diral::HostLayout host_layout(const diral_cfg &c)
+{
+    diral::HostLayout l{};
+    l.N = c.N; l.R = c.R; l.B = c.B; l.S = state_space(c);
+    l.add_action = c.add_action != 0; l.action_binary = c.action_binary != 0; l.add_channel_obs = c.add_channel_obs != 0;
+    l.piggy = c.add_piggy != 0; l.add_reward = c.add_reward != 0; l.add_index = c.add_index != 0;
+    l.add_position = c.add_position != 0; l.add_velocity = c.add_velocity != 0; l.fingerprint = c.fingerprint != 0;
+    l.L = c.L;
+    return l;
 }
 
 void fill_base(Handle *h)
@@ -179,6 +215,107 @@ int ensure_actions_staging(Handle *h)
     return DIRAL_OK;
 }
 
+// CPUs this process may run on (cgroup / affinity aware), for the default size of the row-assembly pool
+int usable_cpus()
+{
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0) { const int n = CPU_COUNT(&set); if (n > 0) return n; }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
+
+// ends a row-assembly job on every exit path: a worker must never be left spinning on a chunk that will not come
+struct PoolJobGuard {
+    diral::HostPool *pool; int chunks; bool closed = false;
+    void close() { if (!closed) { pool->publish(chunks - 1); pool->finish(); closed = true; } }
+    ~PoolJobGuard() { close(); }
+};
+
+// diral_step_host, compact host format: only the information of a slot crosses PCIe -- VPD bin counts (one byte per
+// bin), rewards, and obs / positions / velocities when the State block carries them -- and the [E][N][S] rows are
+// assembled in the caller's buffer by the handle's host threads while later env chunks are still computing.
+int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
+                      float *h_state, float *h_rews, float *h_obs, cudaStream_t s)
+{
+    const diral_cfg &c = h->cfg;
+    const long long E = c.E, N = c.N, R = c.R, B = c.B, A = E * N;
+    const bool group = use_group(h);
+    const int src_bits = group ? diral::key_src_bits(diral::group_width(c.N)) : diral::key_src_bits(c.N);
+    if (c.add_piggy && h->ticks + 1 >= (1ll << (32 - src_bits)))
+        return fail(DIRAL_ERR_SEQ_RANGE, "slot %lld since reset exceeds the %d-bit sequence field of the packed table keys",
+                    h->ticks + 1, 32 - src_bits);
+    const bool want_obs = c.add_channel_obs != 0, want_kin = c.add_position || c.add_velocity;
+    if (c.add_piggy && !h->d_counts) {
+        DIRAL_CUDA(cudaMalloc(&h->d_counts, (size_t)(A * B)));
+        DIRAL_CUDA(cudaMallocHost(&h->h_counts, (size_t)(A * B)));
+    }
+    if (want_obs && !h_obs && !h->h_obs_stage) DIRAL_CUDA(cudaMallocHost(&h->h_obs_stage, sizeof(float) * (size_t)(A * R)));
+    if (want_kin && !h->h_kin) DIRAL_CUDA(cudaMallocHost(&h->h_kin, sizeof(double) * (size_t)(3 * A)));
+    for (auto &st : h->pipe) if (!st) DIRAL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &ev : h->pipe_ev) if (!ev) DIRAL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    const int chunks = E >= 1024 ? h->host_chunks : 1;
+    for (int k = 0; k < chunks; ++k)
+        if (!h->chunk_ev[k]) DIRAL_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
+    if (!h->pool) {
+        int n = h->host_threads > 0 ? h->host_threads : std::min(std::max(usable_cpus() - 1, 1), 32);
+        h->pool = new (std::nothrow) diral::HostPool(n);
+        if (!h->pool) return fail(DIRAL_ERR_ARG, "out of host memory");
+    }
+
+    diral::Params p = h->base;
+    p.mode = mode; p.timestep = timestep; p.episode = episode; p.epsilon = epsilon; p.seed = 0;
+    p.tick = (int)(h->ticks + 1);
+    p.build_state = 1; p.actions = h->d_actions; p.gen_actions = 0; p.actions_out = nullptr;
+    p.vpd_counts = h->d_counts;
+    if (mode == DIRAL_MY_STEP_CH && h->bufs.lat) h->lat_live = true;
+    p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;
+
+    float *obs_dst = h_obs ? h_obs : h->h_obs_stage;
+    diral::HostJob job{};
+    job.actions = h_actions; job.counts = h->h_counts; job.rews = h_rews; job.obs = obs_dst;
+    job.pos_x = h->h_kin; job.pos_y = h->h_kin ? h->h_kin + A : nullptr; job.vel = h->h_kin ? h->h_kin + 2 * A : nullptr;
+    job.episode = episode; job.epsilon = epsilon; job.out = h_state;
+    long long bounds[MAX_HOST_CHUNKS + 1];
+    for (int k = 0; k <= chunks; ++k) bounds[k] = (E * k / chunks) * N;
+    h->pool->begin(host_layout(c), job, bounds, chunks);
+    PoolJobGuard guard{h->pool, chunks};
+
+    DIRAL_CUDA(cudaEventRecord(h->pipe_ev[2], s));                 // everything queued on the caller's stream so far
+    for (int k = 0; k < chunks; ++k) {
+        const long long a0 = bounds[k], n = bounds[k + 1] - a0, e0 = a0 / N;
+        cudaStream_t ps = h->pipe[k & 1];
+        if (k < 2) DIRAL_CUDA(cudaStreamWaitEvent(ps, h->pipe_ev[2], 0));
+        DIRAL_CUDA(cudaMemcpyAsync(h->d_actions + a0, h_actions + a0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ps));
+        const diral::Params q = env_range(p, e0, n / N);
+        DIRAL_CUDA(group ? diral::launch_step_group(q, ps) : diral::launch_step_block(q, ps));
+        h->launches += 1;
+        if (c.add_piggy)
+            DIRAL_CUDA(cudaMemcpyAsync(h->h_counts + a0 * B, h->d_counts + a0 * B, (size_t)(n * B), cudaMemcpyDeviceToHost, ps));
+        DIRAL_CUDA(cudaMemcpyAsync(h_rews + a0, h->bufs.rews + a0, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ps));
+        if (h_obs || want_obs)
+            DIRAL_CUDA(cudaMemcpyAsync(obs_dst + a0 * R, h->bufs.obs + a0 * R, (size_t)(n * R) * sizeof(float), cudaMemcpyDeviceToHost, ps));
+        if (c.add_position) {
+            DIRAL_CUDA(cudaMemcpyAsync(h->h_kin + a0, h->bufs.pos_x + a0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ps));
+            DIRAL_CUDA(cudaMemcpyAsync(h->h_kin + A + a0, h->bufs.pos_y + a0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ps));
+        }
+        if (c.add_velocity)
+            DIRAL_CUDA(cudaMemcpyAsync(h->h_kin + 2 * A + a0, h->bufs.vel + a0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ps));
+        DIRAL_CUDA(cudaEventRecord(h->chunk_ev[k], ps));
+    }
+    if (c.add_piggy) h->ticks += 1;
+    for (int k = 0; k < 2; ++k) {                                  // the caller's stream sees the step as done
+        DIRAL_CUDA(cudaEventRecord(h->pipe_ev[k], h->pipe[k]));
+        DIRAL_CUDA(cudaStreamWaitEvent(s, h->pipe_ev[k], 0));
+    }
+    for (int k = 0; k < chunks; ++k) {                             // rows of chunk k are assembled while k+1.. still run
+        DIRAL_CUDA(cudaEventSynchronize(h->chunk_ev[k]));
+        h->pool->publish(k);
+    }
+    guard.close();
+    return DIRAL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -228,19 +365,22 @@ int diral_create(const diral_cfg *cfg, void **handle)
     if (err == cudaSuccess) err = cudaMemcpy(h->d_edges, edges.data(), sizeof(double) * edges.size(), cudaMemcpyHostToDevice);
     if (err != cudaSuccess) { delete h; return fail(DIRAL_ERR_CUDA, "edge table upload: %s", cudaGetErrorString(err)); }
     fill_base(h);
-    // make the (possibly > 48 KB) dynamic shared memory carve-ups legal once, up front
-    if (cfg->N <= diral::GROUP_MAX_N) err = diral::prepare_step_group(h->base);
-    if (err == cudaSuccess) {
-        diral::Params q = h->base; q.build_state = 1;
-        const size_t need = diral::step_block_smem_bytes(q, diral::step_block_keys_fit_smem(q));
-        if (need > (size_t)prop.sharedMemPerBlockOptin) {
-            if (cfg->N > diral::GROUP_MAX_N) {
-                cudaFree(h->d_edges); delete h;
-                return fail(DIRAL_ERR_UNSUPPORTED, "N=%d R=%d B=%d needs %zu B of shared memory per CTA (limit %zu)",
-                            cfg->N, cfg->R, cfg->B, need, (size_t)prop.sharedMemPerBlockOptin);
-            }
-        } else err = diral::prepare_step_block(h->base);
+    // make the (possibly > 48 KB) dynamic shared memory carve-ups legal once, up front.  The lane-group kernel
+    // keeps one observation row and one merge-script row per resource in shared memory: when that carve-up does
+    // not fit (R beyond ~1300 at 32 vehicles) the one-CTA-per-env kernel, which chunks resources, takes over.
+    diral::Params q = h->base; q.build_state = 1;
+    bool group_fits = cfg->N <= diral::GROUP_MAX_N && diral::step_group_smem_bytes(q) <= (size_t)prop.sharedMemPerBlockOptin;
+    const size_t need = diral::step_block_smem_bytes(q, diral::step_block_keys_fit_smem(q));
+    const bool block_fits = need <= (size_t)prop.sharedMemPerBlockOptin;
+    if (!group_fits && !block_fits) {
+        cudaFree(h->d_edges); delete h;
+        return fail(DIRAL_ERR_UNSUPPORTED, "N=%d R=%d B=%d needs %zu B of shared memory per CTA (limit %zu)",
+                    cfg->N, cfg->R, cfg->B, need, (size_t)prop.sharedMemPerBlockOptin);
     }
+    if (group_fits) err = diral::prepare_step_group(h->base);
+    else h->variant = VARIANT_BLOCK;
+    if (err == cudaSuccess && block_fits) err = diral::prepare_step_block(h->base);
+    h->group_ok = group_fits; h->block_ok = block_fits;
     if (err != cudaSuccess) { cudaFree(h->d_edges); delete h; return fail(DIRAL_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(err)); }
     *handle = h;
     return DIRAL_OK;
@@ -255,6 +395,12 @@ int diral_destroy(void *handle)
     cudaFree(h->d_actions);
     for (auto &st : h->pipe) if (st) cudaStreamDestroy(st);
     for (auto &ev : h->pipe_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->chunk_ev) if (ev) cudaEventDestroy(ev);
+    delete h->pool;
+    cudaFree(h->d_counts);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->h_obs_stage) cudaFreeHost(h->h_obs_stage);
+    if (h->h_kin) cudaFreeHost(h->h_kin);
     delete h;
     return DIRAL_OK;
 }
@@ -267,11 +413,54 @@ int diral_set_option(void *handle, const char *name, int64_t value)
         if (value < 0 || value > 2) return fail(DIRAL_ERR_ARG, "variant must be 0 (auto), 1 (group) or 2 (block)");
         if (value == VARIANT_GROUP && h->cfg.N > diral::GROUP_MAX_N)
             return fail(DIRAL_ERR_ARG, "the group kernel handles num_users <= %d", diral::GROUP_MAX_N);
+        if (value == VARIANT_GROUP && !h->group_ok)
+            return fail(DIRAL_ERR_UNSUPPORTED, "the group kernel's shared-memory carve-up does not fit at R=%d", h->cfg.R);
+        if (value == VARIANT_BLOCK && !h->block_ok)
+            return fail(DIRAL_ERR_UNSUPPORTED, "the one-CTA-per-env kernel's shared-memory carve-up does not fit this configuration");
+        if (value == VARIANT_AUTO && !h->group_ok) value = VARIANT_BLOCK;
         h->variant = (int)value;
         return DIRAL_OK;
     }
     if (!strcmp(name, "track_lat")) { h->force_track_lat = value != 0; return DIRAL_OK; }
+    if (!strcmp(name, "host_format")) {
+        if (value != 0 && value != 1) return fail(DIRAL_ERR_ARG, "host_format must be 0 (full rows) or 1 (compact)");
+        h->host_format = (int)value;
+        return DIRAL_OK;
+    }
+    if (!strcmp(name, "host_threads")) {
+        if (value < 0 || value > 256) return fail(DIRAL_ERR_ARG, "host_threads must be in [0, 256]");
+        if (h->pool && h->pool->threads() != (int)value) { delete h->pool; h->pool = nullptr; }
+        h->host_threads = (int)value;
+        return DIRAL_OK;
+    }
+    if (!strcmp(name, "host_chunks")) {
+        if (value < 1 || value > MAX_HOST_CHUNKS) return fail(DIRAL_ERR_ARG, "host_chunks must be in [1, %d]", MAX_HOST_CHUNKS);
+        h->host_chunks = (int)value;
+        return DIRAL_OK;
+    }
+    // checkpoint restore (TestEnv.load_state_dict): the slot counters the kernels derive keys and stamps from
+    if (!strcmp(name, "ticks")) {
+        if (value < 0) return fail(DIRAL_ERR_ARG, "ticks must be >= 0");
+        h->ticks = value;
+        return DIRAL_OK;
+    }
+    if (!strcmp(name, "lat_live")) { h->lat_live = value != 0; return DIRAL_OK; }
     return fail(DIRAL_ERR_ARG, "unknown option '%s'", name);
+}
+
+int64_t diral_get_option(void *handle, const char *name)
+{
+    Handle *h = as_handle(handle);
+    if (!h || !name) return -1;
+    if (!strcmp(name, "variant")) return use_group(h) ? VARIANT_GROUP : VARIANT_BLOCK;
+    if (!strcmp(name, "track_lat")) return h->force_track_lat;
+    if (!strcmp(name, "host_format")) return h->host_format;
+    if (!strcmp(name, "host_threads")) return h->pool ? h->pool->threads() : h->host_threads;
+    if (!strcmp(name, "host_chunks")) return h->host_chunks;
+    if (!strcmp(name, "ticks")) return h->ticks;
+    if (!strcmp(name, "lat_live")) return h->lat_live ? 1 : 0;
+    if (!strcmp(name, "compact_ok")) return compact_ok(h->cfg) ? 1 : 0;
+    return -1;
 }
 
 int diral_bind(void *handle, const diral_buffers *b)
@@ -311,6 +500,26 @@ int diral_reset(void *handle, const double *x0, const double *y0, const double *
     DIRAL_CUDA(diral::launch_reset(p, x0, y0, v0, s));
     h->launches += 1;
     h->ticks = 0; h->lat_live = false;
+    return DIRAL_OK;
+}
+
+int diral_reset_topology(void *handle, const double *x0, const double *y0, const double *v0, uint64_t seed, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (x0 && (!y0 || !v0)) return fail(DIRAL_ERR_ARG, "x0, y0 and v0 must be given together");
+    DeviceGuard g(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const diral_cfg &c = h->cfg;
+    const size_t ENN = (size_t)c.E * c.N * c.N;
+    if (h->bufs.tab_seq) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_seq, 0, ENN * 4, s));     // vehicle.py:24-33
+    if (h->bufs.tab_lu) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_lu, 0, ENN * 4, s));
+    if (h->bufs.tab_x) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_x, 0, ENN * 8, s));
+    diral::Params p = h->base;
+    p.seed = seed;
+    DIRAL_CUDA(diral::launch_reset(p, x0, y0, v0, s));
+    h->launches += 1;
+    h->ticks = 0;
     return DIRAL_OK;
 }
 
@@ -523,6 +732,8 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
     if (int rc = ensure_actions_staging(h)) return rc;
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (h->host_format == 1 && compact_ok(h->cfg))
+        return step_host_compact(h, mode, h_actions, timestep, episode, epsilon, h_state, h_rews, h_obs, s);
     const long long E = h->cfg.E, N = h->cfg.N, R = h->cfg.R, S = h->base.S;
     // Envs are independent, so the batch is cut into chunks that alternate between two internal
     // streams: chunk c's results travel over PCIe while chunk c+1 computes and chunk c+2's actions arrive.
@@ -572,6 +783,47 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
         DIRAL_CUDA(cudaStreamWaitEvent(s, h->pipe_ev[k], 0));
     }
     DIRAL_CUDA(cudaStreamSynchronize(s));
+    return DIRAL_OK;
+}
+
+int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t *actions, const uint8_t *counts,
+                            const float *rews, const float *obs, const double *pos_x, const double *pos_y,
+                            const double *vel, double episode, double epsilon, int32_t threads, float *out)
+{
+    if (int rc = check_cfg(cfg)) return rc;
+    if (!compact_ok(*cfg)) return fail(DIRAL_ERR_UNSUPPORTED, "this State block has no compact host format");
+    if (!actions || !out || agents < 0) return fail(DIRAL_ERR_ARG, "actions/out must not be NULL");
+    if (cfg->add_piggy && !counts) return fail(DIRAL_ERR_ARG, "add_positional_dist_piggy needs counts");
+    if (cfg->add_reward && !rews) return fail(DIRAL_ERR_ARG, "add_reward needs rews");
+    if (cfg->add_channel_obs && !obs) return fail(DIRAL_ERR_ARG, "add_channel_obs needs obs");
+    if (cfg->add_position && (!pos_x || !pos_y)) return fail(DIRAL_ERR_ARG, "add_position needs pos_x and pos_y");
+    if (cfg->add_velocity && !vel) return fail(DIRAL_ERR_ARG, "add_velocity needs vel");
+    diral::HostJob job{};
+    job.actions = actions; job.counts = counts; job.rews = rews; job.obs = obs; job.pos_x = pos_x; job.pos_y = pos_y;
+    job.vel = vel; job.episode = episode; job.epsilon = epsilon; job.out = out;
+    const diral::HostLayout lay = host_layout(*cfg);
+    if (threads <= 1) { diral::expand_rows(lay, job, 0, agents); return DIRAL_OK; }
+    // one pool per thread count, kept for the life of the process (this entry point has no handle to own it)
+    static std::mutex mu;
+    static std::vector<std::unique_ptr<diral::HostPool>> pools;
+    std::lock_guard<std::mutex> lock(mu);
+    diral::HostPool *pool = nullptr;
+    for (auto &q : pools) if (q->threads() == threads) pool = q.get();
+    if (!pool) { pools.emplace_back(new diral::HostPool(threads)); pool = pools.back().get(); }
+    const long long bounds[3] = {0, (agents / 2) & ~3ll, agents};      // two chunks: exercises the chunk hand-over too
+    pool->begin(lay, job, bounds, 2);
+    pool->publish(0); pool->publish(1);
+    pool->finish();
+    return DIRAL_OK;
+}
+
+int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes, const void *src, void *stream)
+{
+    if (!ring || !src) return fail(DIRAL_ERR_ARG, "ring/src must not be NULL");
+    if (capacity < 1 || slot < 0 || slot >= capacity || row_bytes < 1)
+        return fail(DIRAL_ERR_ARG, "slot must be in [0, capacity) and row_bytes >= 1");
+    DIRAL_CUDA(cudaMemcpyAsync(static_cast<char *>(ring) + slot * row_bytes, src, (size_t)row_bytes, cudaMemcpyDeviceToDevice,
+                               static_cast<cudaStream_t>(stream)));
     return DIRAL_OK;
 }
 

@@ -49,6 +49,7 @@ struct Params {
     int32_t *tab_seq, *tab_lu; double *tab_x;
     int32_t *lat;
     float *obs, *rews, *state;
+    uint8_t *vpd_counts;      // [E][N][B] raw VPD bin counts (compact host format, diral_step_host) or NULL
     double *acc_reward; long long *acc_count;
     uint32_t *scratch;
     const double *trace; long long trace_len;

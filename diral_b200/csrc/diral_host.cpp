@@ -1,0 +1,241 @@
+// diral_host.cpp -- assembling TestEnv.obtain_state rows (reference envs/test_env.py:527-583) on the host from the
+// compact per-agent record diral_step_host moves over PCIe.  See diral_host.h.
+//
+// The expander is bound by host-memory write bandwidth (S float32 per agent, 21.5 MB per slot at the headline
+// configuration), so rows are built in a small L1-resident staging block and leave as non-temporal 16-byte stores:
+// no read-for-ownership of the destination lines, and nothing of the output stays in the caches.
+#include "diral_host.h"
+
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <emmintrin.h>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace diral {
+
+namespace {
+
+// counts / len of the positional distribution (network.py:501): float32 rounding of the float64 quotient, exactly
+// what the kernels store.  One table for every observer (len <= 255 samples at <= 256 vehicles).
+const float *vpd_quotients()
+{
+    static std::vector<float> lut;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        lut.assign(256 * 256, 0.0f);
+        for (int m = 1; m < 256; ++m)
+            for (int c = 0; c < 256; ++c) lut[m * 256 + c] = (float)((double)c / (double)m);
+    });
+    return lut.data();
+}
+
+void stream_out(float *dst, const float *src, long long n)
+{
+    // dst is 16-byte aligned whenever the caller's buffer is and the row range starts at a multiple of 4 agents
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (n & 3) == 0) {
+        for (long long i = 0; i < n; i += 4)
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_load_si128(reinterpret_cast<const __m128i *>(src + i)));
+    } else {
+        std::memcpy(dst, src, (size_t)n * sizeof(float));
+    }
+}
+
+}  // namespace
+
+namespace {
+
+// Rows whose blocks are all whole 16-byte groups (one-hot over R % 4 == 0 resources, obs likewise, B % 4 == 0 bins,
+// no scalar tail -- the shipped State block, S = R + B) are formed in registers and leave as non-temporal stores
+// straight from them: per agent R/4 compares for the one-hot and B/4 divisions (IEEE float32 division of two small
+// integers is the float32 rounding of the quotient, which is what the kernels store).
+bool vector_rows_ok(const HostLayout &lay, const HostJob &job)
+{
+    if (lay.add_reward || lay.add_index || lay.add_position || lay.add_velocity || lay.fingerprint) return false;
+    if (lay.add_action && (!lay.action_binary || (lay.R & 3))) return false;
+    if (lay.add_channel_obs && (lay.R & 3)) return false;
+    if (lay.piggy && (lay.B & 3)) return false;
+    return (lay.S & 3) == 0 && (reinterpret_cast<uintptr_t>(job.out) & 15) == 0;
+}
+
+void expand_rows_vector(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
+{
+    const int R = lay.R, B = lay.B, S = lay.S;
+    const __m128i lane_id = _mm_set_epi32(3, 2, 1, 0), four = _mm_set1_epi32(4), zero = _mm_setzero_si128();
+    const __m128i one_bits = _mm_castps_si128(_mm_set1_ps(1.0f));
+    for (long long a = a0; a < a1; ++a) {
+        float *w = job.out + a * S;
+        if (lay.add_action) {
+            int act = job.actions[a];
+            act = act < 0 ? 0 : (act >= R ? R - 1 : act);
+            const __m128i av = _mm_set1_epi32(act);
+            __m128i idx = lane_id;
+            for (int r = 0; r < R; r += 4, w += 4) {
+                _mm_stream_si128(reinterpret_cast<__m128i *>(w), _mm_and_si128(_mm_cmpeq_epi32(idx, av), one_bits));
+                idx = _mm_add_epi32(idx, four);
+            }
+        }
+        if (lay.add_channel_obs) {
+            const float *o = job.obs + a * R;
+            for (int r = 0; r < R; r += 4, w += 4) _mm_stream_ps(w, _mm_loadu_ps(o + r));
+        }
+        if (lay.piggy) {
+            const uint8_t *c = job.counts + a * B;
+            __m128i acc = zero;
+            __m128i c32[64];                     // B <= 256 bins
+            for (int b = 0; b < B; b += 4) {
+                int word;
+                std::memcpy(&word, c + b, 4);
+                const __m128i v = _mm_unpacklo_epi16(_mm_unpacklo_epi8(_mm_cvtsi32_si128(word), zero), zero);
+                c32[b >> 2] = v;
+                acc = _mm_add_epi32(acc, v);
+            }
+            acc = _mm_add_epi32(acc, _mm_shuffle_epi32(acc, 0x4e));
+            acc = _mm_add_epi32(acc, _mm_shuffle_epi32(acc, 0xb1));       // every lane = len(s)
+            // len == 0: every count is 0 too; dividing by 1 leaves the all-zero vector (network.py:502-505)
+            const __m128 den = _mm_cvtepi32_ps(_mm_max_epi16(acc, _mm_set1_epi32(1)));
+            for (int b = 0; b < B; b += 4, w += 4) _mm_stream_ps(w, _mm_div_ps(_mm_cvtepi32_ps(c32[b >> 2]), den));
+        }
+    }
+    _mm_sfence();
+}
+
+}  // namespace
+
+void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
+{
+    if (vector_rows_ok(lay, job)) { expand_rows_vector(lay, job, a0, a1); return; }
+    const int N = lay.N, R = lay.R, B = lay.B, S = lay.S;
+    const float *lut = vpd_quotients();
+    // staging block: a multiple of 4 rows (so every flush is a whole number of 16-byte pieces), about 16 KB
+    long long rows_per_block = (16384 / (4 * (long long)S)) & ~3ll;
+    if (rows_per_block < 4) rows_per_block = 4;
+    alignas(64) static thread_local float stage_small[4096 + 16];
+    std::vector<float> stage_big;
+    float *stage = stage_small;
+    if (rows_per_block * S > 4096) { stage_big.resize((size_t)(rows_per_block * S) + 16); stage = stage_big.data(); }
+    stage = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(stage) + 63) & ~(uintptr_t)63);
+
+    for (long long b0 = a0; b0 < a1; b0 += rows_per_block) {
+        const long long b1 = b0 + rows_per_block < a1 ? b0 + rows_per_block : a1;
+        float *w = stage;
+        for (long long a = b0; a < b1; ++a) {
+            int act = job.actions[a];
+            act = act < 0 ? 0 : (act >= R ? R - 1 : act);                     // the kernels clamp (and count) bad actions
+            if (lay.add_action) {                                             // test_env.py:539-545
+                if (lay.action_binary) { std::memset(w, 0, sizeof(float) * (size_t)R); w[act] = 1.0f; w += R; }
+                else *w++ = (float)act;
+            }
+            if (lay.add_channel_obs) { std::memcpy(w, job.obs + a * R, sizeof(float) * (size_t)R); w += R; }   // :547-548
+            if (lay.piggy) {                                                  // :554-562, network.py:495-505
+                const uint8_t *c = job.counts + a * B;
+                int m = 0;
+                for (int b = 0; b < B; ++b) m += c[b];
+                const float *q = lut + (m > 255 ? 255 : m) * 256;
+                for (int b = 0; b < B; ++b) w[b] = q[c[b]];
+                w += B;
+            }
+            if (lay.add_reward) *w++ = job.rews[a];                           // :568-570
+            if (lay.add_index) *w++ = (float)(a % N + 1);                     // :571-572
+            if (lay.add_position) {                                           // :573-574, network.py:403-407
+                *w++ = (float)(job.pos_x[a] / lay.L);
+                *w++ = (float)(job.pos_y[a] / 2.0);
+            }
+            if (lay.add_velocity) *w++ = (float)job.vel[a];                   // :575-576
+            if (lay.fingerprint) { *w++ = (float)job.episode; *w++ = (float)job.epsilon; }   // :577-579
+        }
+        stream_out(job.out + b0 * S, stage, (b1 - b0) * S);
+    }
+    _mm_sfence();
+}
+
+struct HostPool::Impl {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    unsigned long long job_seq = 0;      // guarded by mu
+    bool stop = false;
+    // the running job (written by begin() before job_seq moves)
+    HostLayout lay{};
+    HostJob job{};
+    std::vector<long long> bounds;
+    int nchunks = 0;
+    std::atomic<int> ready{0};           // chunks whose inputs are in host memory
+    std::atomic<int> done{0};            // workers that have finished the job
+
+    void run(int idx, int nthreads)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                cv.wait(lock, [&] { return stop || job_seq != seen; });
+                if (stop) return;
+                seen = job_seq;
+            }
+            for (int c = 0; c < nchunks; ++c) {
+                int spins = 0;
+                while (ready.load(std::memory_order_acquire) <= c) {
+                    _mm_pause();
+                    if (++spins > 20000) { std::this_thread::yield(); spins = 0; }
+                }
+                // this worker's share of chunk c, cut at multiples of 4 agents (16-byte aligned row ranges)
+                const long long lo = bounds[c], n = bounds[c + 1] - lo;
+                long long s0 = (n * idx / nthreads) & ~3ll, s1 = (n * (idx + 1) / nthreads) & ~3ll;
+                if (idx == nthreads - 1) s1 = n;
+                if (s1 > s0) expand_rows(lay, job, lo + s0, lo + s1);
+            }
+            done.fetch_add(1, std::memory_order_release);
+        }
+    }
+};
+
+HostPool::HostPool(int threads) : impl(new Impl)
+{
+    const int n = threads < 1 ? 1 : threads;
+    vpd_quotients();
+    for (int i = 0; i < n; ++i) impl->workers.emplace_back([this, i, n] { impl->run(i, n); });
+}
+
+HostPool::~HostPool()
+{
+    {
+        std::lock_guard<std::mutex> lock(impl->mu);
+        impl->stop = true;
+    }
+    impl->cv.notify_all();
+    for (auto &t : impl->workers) t.join();
+    delete impl;
+}
+
+int HostPool::threads() const { return (int)impl->workers.size(); }
+
+void HostPool::begin(const HostLayout &lay, const HostJob &job, const long long *bounds, int nchunks)
+{
+    impl->lay = lay; impl->job = job;
+    impl->bounds.assign(bounds, bounds + nchunks + 1);
+    impl->nchunks = nchunks;
+    impl->ready.store(0, std::memory_order_relaxed);
+    impl->done.store(0, std::memory_order_relaxed);
+    {
+        std::lock_guard<std::mutex> lock(impl->mu);
+        impl->job_seq += 1;
+    }
+    impl->cv.notify_all();
+}
+
+void HostPool::publish(int chunk) { impl->ready.store(chunk + 1, std::memory_order_release); }
+
+void HostPool::finish()
+{
+    const int n = (int)impl->workers.size();
+    int spins = 0;
+    while (impl->done.load(std::memory_order_acquire) < n) {
+        _mm_pause();
+        if (++spins > 20000) { std::this_thread::yield(); spins = 0; }
+    }
+}
+
+}  // namespace diral

@@ -1,0 +1,50 @@
+// diral_host.h -- host side of the compact host format of diral_step_host (internal to libdiral_env.so).
+//
+// TestEnv.obtain_state (reference envs/test_env.py:527-583) emits, per agent, blocks that are either known to the
+// host already (the one-hot of the action it just sent, the agent index, episode / epsilon) or a few bytes of
+// information (B small integers behind the B float32 of the positional distribution).  In the compact format only
+// the information crosses PCIe -- bin counts as one byte each, rewards, and the float64 positions / velocities /
+// channel observations when the State block asks for them -- and the [E][N][S] float32 rows the caller expects are
+// assembled here by a pool of host threads, bit for bit what the device writes into bufs.state.
+#pragma once
+#include <cstdint>
+
+namespace diral {
+
+struct HostLayout {                 // the State block (test_env.py:27-41) as the expander needs it
+    int N, R, B, S;
+    int add_action, action_binary, add_channel_obs, piggy, add_reward, add_index, add_position, add_velocity, fingerprint;
+    double L;
+};
+
+struct HostJob {                    // one call: per-agent inputs (index a = env * N + vehicle) and the output rows
+    const int32_t *actions;         // [A]          what the caller sent (clamped to [0, R) like the kernels do)
+    const uint8_t *counts;          // [A][B]       VPD bin counts (piggy)
+    const float *rews;              // [A]
+    const float *obs;               // [A][R]       (add_channel_obs)
+    const double *pos_x, *pos_y;    // [A]          post-mobility x, y (add_position)
+    const double *vel;              // [A]          (add_velocity)
+    double episode, epsilon;
+    float *out;                     // [A][S]
+};
+
+// rows [a0, a1) of one job, on the calling thread
+void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long long a1);
+
+// Persistent worker threads.  begin() wakes them for one job split into `nchunks` consecutive agent ranges
+// [bounds[c], bounds[c+1]); publish(c) says chunk c's inputs have landed in host memory; finish() waits until every
+// row has been written.  The workers sleep between jobs and spin (pause) inside one.
+class HostPool {
+public:
+    explicit HostPool(int threads);
+    ~HostPool();
+    int threads() const;
+    void begin(const HostLayout &lay, const HostJob &job, const long long *bounds, int nchunks);
+    void publish(int chunk);
+    void finish();
+private:
+    struct Impl;
+    Impl *impl;
+};
+
+}  // namespace diral

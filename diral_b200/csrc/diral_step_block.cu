@@ -624,6 +624,7 @@ step_block_kernel(const Params p, const int SB)
                             val = __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0);
                         }
                         srow[o_vpd + b] = val;
+                        if (p.vpd_counts) p.vpd_counts[(vbase + u) * B + b] = (unsigned char)(have ? hist[b * T + u] : 0u);
                     }
                 if (lane < S - o_tail) {
                     float val = 0.0f; int k = lane;

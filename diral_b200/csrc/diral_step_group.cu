@@ -46,7 +46,7 @@
 #include "diral_launch.h"
 
 #include <algorithm>
-#include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 namespace diral {
@@ -450,10 +450,11 @@ step_group_kernel(const Params p)
         unsigned oldest = 0xffffffffu;
 #pragma unroll
         for (int q = 0; q < SL; ++q) {
-            if (jbase + q == u) sb[q] += 1;                                       // vehicle.py:58 (tick)
+            if (jbase + q == u && act) sb[q] += 1;                                // vehicle.py:58 (tick)
             oldest = min(oldest, (unsigned)(sb[q] - 1));
         }
-        const bool narrow = base <= 0 || oldest >= (unsigned)base;
+        // (lanes beyond N hold no entries: they must not veto the packed form for the whole group)
+        const bool narrow = !act || base <= 0 || oldest >= (unsigned)base;
         if ((SL & 1) == 0 && (__ballot_sync(gmask, !narrow) & gmask) == 0u) {
             unsigned k2[SL / 2 > 0 ? SL / 2 : 1];
 #pragma unroll
@@ -596,6 +597,16 @@ step_group_kernel(const Params p)
                 unsigned hv[8]; float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) hv[i] = (have && b0 + i < B) ? hist[(b0 + i) * G + u] : 0u;
+                if (p.vpd_counts) {                  // compact host format: the counts themselves, one byte per bin
+                    unsigned char *cp = p.vpd_counts + (vbase + u) * B + b0;
+                    if ((B & 3) == 0) {
+                        *reinterpret_cast<unsigned *>(cp) = hv[0] | (hv[1] << 8) | (hv[2] << 16) | (hv[3] << 24);
+                        if (b0 + 4 < B) *reinterpret_cast<unsigned *>(cp + 4) = hv[4] | (hv[5] << 8) | (hv[6] << 16) | (hv[7] << 24);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) if (b0 + i < B) cp[i] = (unsigned char)hv[i];
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float c = (float)hv[i];
@@ -657,20 +668,25 @@ cudaError_t prepare_k(const Params &p)
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-// CTAs of this instantiation the whole device holds at once (cached per instantiation and smem size)
+// CTAs of this instantiation the current device holds at once (cached per instantiation, device and smem size)
 template <int G, bool FULL, int W, int MODE, bool LAT, bool ROLL>
 long long resident_ctas(size_t smem)
 {
-    static size_t cached_smem = ~(size_t)0; static long long cached = 0;
-    if (smem != cached_smem) {
-        int dev = 0, sms = 148, per_sm = 16;
-        cudaGetDevice(&dev);
+    constexpr int MAX_DEV = 64;
+    static std::mutex mu;
+    static size_t cached_smem[MAX_DEV]; static long long cached[MAX_DEV];      // zero-initialised: 0 = not cached
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < MAX_DEV ? dev : 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached[slot] == 0 || smem != cached_smem[slot] || slot != dev) {
+        int sms = 148, per_sm = 16;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_group_kernel<G, FULL, W, MODE, LAT, ROLL>, W * 32, smem) != cudaSuccess)
             per_sm = 16;
-        cached = (long long)sms * per_sm; cached_smem = smem;
+        cached[slot] = (long long)sms * std::max(per_sm, 1); cached_smem[slot] = smem;
     }
-    return cached;
+    return cached[slot];
 }
 
 template <int G, bool FULL, int MODE, bool LAT>
@@ -684,7 +700,6 @@ cudaError_t launch_k(const Params &p, cudaStream_t stream)
     const bool roll = p.n_slots > 1;
     q.prefetch_ahead = (int)((roll ? resident_ctas<G, FULL, W, MODE, LAT, true>(smem)
                                    : resident_ctas<G, FULL, W, MODE, LAT, false>(smem)) * envs_per_cta);
-    if (const char *pad = getenv("DIRAL_SMEM_PER_CTA")) smem = std::max(smem, (size_t)atoll(pad));   // tuning knob
     if (roll) step_group_kernel<G, FULL, W, MODE, LAT, true><<<(unsigned)grid, W * 32, smem, stream>>>(q);
     else step_group_kernel<G, FULL, W, MODE, LAT, false><<<(unsigned)grid, W * 32, smem, stream>>>(q);
     return cudaGetLastError();

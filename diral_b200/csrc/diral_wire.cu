@@ -46,6 +46,10 @@ __global__ void __launch_bounds__(128) wire_vpd_kernel(const WireEntry *__restri
     if (m >= M) return;
     const WireEntry *tab = tables + m * N;
     const int tx = observer[m];
+    if (tx < 0 || tx >= N) {             // an observer id outside the table: NaN row instead of an out-of-bounds read
+        for (int b = lane; b < B; b += 32) out[m * B + b] = __int_as_float(0x7fc00000);
+        return;
+    }
     const float4 own = *reinterpret_cast<const float4 *>(tab + tx);          // uniform address: one broadcast load
     const double xo = (double)own.x, yo = (double)own.y;
     float *row = out + m * B;

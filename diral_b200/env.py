@@ -97,7 +97,8 @@ class TestEnv:
 
     __test__ = False     # not a pytest class, whatever the name says
 
-    def __init__(self, num_envs=1, device="cuda", seed=0, env_offset=0, init=None, variant="auto", **kwargs):
+    def __init__(self, num_envs=1, device="cuda", seed=0, env_offset=0, init=None, variant="auto",
+                 host_format="full", host_threads=None, **kwargs):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -127,6 +128,7 @@ class TestEnv:
             check(self.lib.diral_create(C.byref(self.cfg), C.byref(self._handle)))
         if variant != "auto":
             check(self.lib.diral_set_option(self._handle, b"variant", {"group": 1, "block": 2}[variant]))
+        self.set_host_format(host_format, host_threads)
         self._alloc()
         self._trace = None
         self._bind()
@@ -181,6 +183,22 @@ class TestEnv:
             self.close()
         except Exception:
             pass
+
+    def set_host_format(self, host_format="compact", host_threads=None):
+        """How ``step_host`` moves a slot's results to the host: ``"full"`` copies the [E, N, S] float32 rows over
+        PCIe; ``"compact"`` copies only what the host cannot know (VPD bin counts as bytes, rewards, ...) and lets
+        ``host_threads`` library threads assemble the same rows in the caller's buffer (include/diral_env.h).
+        ``host_threads=None``: the CPUs this process may use, shared between the ranks of a torchrun job."""
+        if host_format not in ("full", "compact"):
+            raise ValueError("host_format must be 'full' or 'compact'")
+        check(self.lib.diral_set_option(self._handle, b"host_format", int(host_format == "compact")))
+        if host_threads is None:
+            import os
+            cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            local = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1")), 1)
+            host_threads = max(min(cpus // local - 1, 32), 1)
+        check(self.lib.diral_set_option(self._handle, b"host_threads", int(host_threads)))
+        self.host_format = host_format if self.lib.diral_get_option(self._handle, b"compact_ok") else "full"
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -276,14 +294,14 @@ class TestEnv:
 
     def reset_mobility_env(self):
         """test_env.py:479-484 -> Network.reset_positions (network.py:181-187): the fixed 4-vehicle toy
-        topology with fresh tables; ``last_arrival_time`` survives, as in the reference."""
+        topology with fresh tables.  Only the vehicles are rebuilt, as in the reference: ``last_arrival_time``,
+        the slot / episode counters, the episode accumulators and the last obs / rewards keep their values."""
         if self.N != 4:
             raise ValueError("reset_mobility_env installs the fixed 4-vehicle topology (network.py:81-90)")
-        lat = self.lat.clone()
-        self.reset(init=(_FIXED_TOY["x"], _FIXED_TOY["y"], _FIXED_TOY["v"]))
-        self.lat.copy_(lat)
-        if bool((lat != -1).any()):
-            check(self.lib.diral_set_option(self._handle, b"track_lat", 1))
+        x0, y0, v0 = (self._as_f64(_FIXED_TOY[k], k) for k in ("x", "y", "v"))
+        with torch.cuda.device(self.device):
+            check(self.lib.diral_reset_topology(self._handle, x0.data_ptr(), y0.data_ptr(), v0.data_ptr(),
+                                                C.c_uint64(self.seed), self._stream()))
 
     def get_total_users(self):
         return self.NUM_USERS
@@ -297,17 +315,21 @@ class TestEnv:
     def get_action_space(self):
         return self.action_space
 
-    def update_velocity(self, draws=None, force=False):
+    def update_velocity(self, draws=None, force=False, episode=None):
         """test_env.py:498-504 -> network.py:208-222; ``draws`` [E, N] in {1,2,3} replays recorded
-        ``random.randrange(1, 4)`` outcomes, else Philox(seed, episode)."""
+        ``random.randrange(1, 4)`` outcomes, else Philox keyed by (seed, global env, vehicle, episode).  The
+        reference calls this once per episode (main_test.py:226-236), so every call advances ``self.episode``
+        -- two calls never repeat a draw; ``episode=`` pins the key explicitly."""
         if not (self.mobility_vary or force):
             return
+        ep = self.episode if episode is None else int(episode)
         d = None
         if draws is not None:
             d = torch.as_tensor(np.ascontiguousarray(draws, dtype=np.int8), device=self.device).reshape(self.E, self.N)
         with torch.cuda.device(self.device):
             check(self.lib.diral_update_velocity(self._handle, d.data_ptr() if d is not None else None,
-                                                 C.c_uint64(self.seed), C.c_int64(self.episode), self._stream()))
+                                                 C.c_uint64(self.seed), C.c_int64(ep), self._stream()))
+        self.episode = ep + 1
 
     def load_saved_positions(self, trace=None):
         """test_env.py:109-114 -> Network.load_x_positions (network.py:171-178): replay a [T, N]
@@ -396,31 +418,75 @@ class TestEnv:
         return int(self.lib.diral_launch_count(self._handle))
 
     # ------------------------------------------------------------------ reference-layout views
+    def _need_tables(self):
+        if self._tab_seq is None:
+            raise AttributeError("neighbour tables exist only with State.add_positional_dist_piggy (vehicle.py:20-33 "
+                                 "are never read otherwise)")
+
     @property
     def tab_seq(self):
         """``[E, i, j]`` = vehicles[i].pos_of_neighbors[j]["seq_number"] (vehicle.py:32)."""
+        self._need_tables()
         return self._tab_seq.transpose(1, 2)
 
     @property
     def tab_lu(self):
+        self._need_tables()
         return self._tab_lu.transpose(1, 2)
 
     @property
     def tab_x(self):
+        self._need_tables()
         return self._tab_x.transpose(1, 2)
 
     @property
     def tab_y(self):
         """ypos is derived: pos_y never changes between resets, so an entry that has ever been written
         (seq > 0) holds pos_y of its subject (vehicle.py:31,43,60)."""
+        self._need_tables()
         return torch.where(self.tab_seq > 0, self.pos_y[:, None, :].expand(-1, self.N, -1),
                            torch.zeros((), dtype=torch.float64, device=self.device))
 
+    # ------------------------------------------------------------------ checkpoint (SURVEY.md section 5)
+    _STATE_TENSORS = ("pos_x", "pos_y", "vel", "lat", "_tab_seq", "_tab_lu", "_tab_x", "_acc_reward", "_acc_count",
+                      "_obs", "_rews", "_state")
+
     def state_dict(self):
-        d = dict(pos_x=self.pos_x, pos_y=self.pos_y, vel=self.vel, lat=self.lat, t=self.t, episode=self.episode)
-        if self.cfg.add_piggy:
-            d.update(tab_seq=self._tab_seq, tab_lu=self._tab_lu, tab_x=self._tab_x)
+        """Everything a restored env needs to continue bit for bit: kinematics, tables, last_arrival_time, the
+        episode accumulators, the last outputs, and the host-side counters the kernels derive keys from."""
+        d = {k.lstrip("_"): getattr(self, k).clone() for k in self._STATE_TENSORS if getattr(self, k) is not None}
+        d.update(t=self.t, episode=self.episode, seed=self.seed,
+                 ticks=int(self.lib.diral_get_option(self._handle, b"ticks")),
+                 lat_live=int(self.lib.diral_get_option(self._handle, b"lat_live")),
+                 track_lat=int(self.lib.diral_get_option(self._handle, b"track_lat")))
+        if hasattr(self, "_shape_sums"):
+            d.update(sum_ia_prev=self._sum_ia_prev.clone(), ia_counter=self._ia_counter.clone(),
+                     prev_actions=self._prev_actions.clone())
         return d
+
+    def load_state_dict(self, d):
+        """Inverse of ``state_dict`` on an env of the same configuration."""
+        for k in self._STATE_TENSORS:
+            dst = getattr(self, k)
+            if dst is None:
+                continue
+            src = d[k.lstrip("_")]
+            if tuple(src.shape) != tuple(dst.shape):
+                raise ValueError("state_dict['%s'] has shape %s, this env needs %s" % (k.lstrip("_"), tuple(src.shape), tuple(dst.shape)))
+            dst.copy_(src)
+        self.t, self.episode, self.seed = int(d["t"]), int(d["episode"]), int(d.get("seed", self.seed))
+        for name in ("ticks", "lat_live", "track_lat"):
+            check(self.lib.diral_set_option(self._handle, name.encode(), int(d[name])))
+        if "sum_ia_prev" in d:
+            if not hasattr(self, "_shape_sums"):     # the shaping state is created lazily (shape_rewards)
+                dev = self.device
+                self._shape_sums = torch.zeros((self.E, 3), dtype=torch.float64, device=dev)
+                self._sum_ia_prev = torch.zeros((self.E,), dtype=torch.int64, device=dev)
+                self._ia_counter = torch.zeros((self.E, self.N), dtype=torch.int32, device=dev)
+                self._prev_actions = torch.full((self.E, self.N), -1, dtype=torch.int32, device=dev)
+            self._sum_ia_prev.copy_(d["sum_ia_prev"]); self._ia_counter.copy_(d["ia_counter"])
+            self._prev_actions.copy_(d["prev_actions"])
+        return self
 
 
 BatchedTestEnv = TestEnv

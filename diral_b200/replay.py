@@ -48,10 +48,22 @@ class Memory:
         [E, N, S] / [E, N] (or already flattened to [A, ...]) are copied into the ring."""
         state, action, reward, next_state = experience
         slot = self.count % self.capacity
-        self.states[slot].copy_(state.reshape(self.A, self.S))
-        self.actions[slot].copy_(action.reshape(self.A))
-        self.rewards[slot].copy_(reward.reshape(self.A))
-        self.next_states[0 if self.share_next_state else slot].copy_(next_state.reshape(self.A, self.S))
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+        def put(ring, slot, src, dtype, shape):
+            if not (isinstance(src, torch.Tensor) and src.device == self.device and src.dtype == dtype and src.is_contiguous()):
+                src = torch.as_tensor(src).to(device=self.device, dtype=dtype).contiguous()
+            if src.numel() != int(np.prod(shape)):
+                raise ValueError("experience entry has %d elements, the ring row holds %s" % (src.numel(), shape))
+            row_bytes = src.numel() * src.element_size()
+            with torch.cuda.device(self.device):
+                check(self.lib.diral_ring_put(ring.data_ptr(), C.c_int64(ring.shape[0]), C.c_int64(slot),
+                                              C.c_int64(row_bytes), src.data_ptr(), stream))
+
+        put(self.states, slot, state, torch.float32, (self.A, self.S))
+        put(self.actions, slot, action, torch.int32, (self.A,))
+        put(self.rewards, slot, reward, torch.float32, (self.A,))
+        put(self.next_states, 0 if self.share_next_state else slot, next_state, torch.float32, (self.A, self.S))
         self.count += 1
 
     def _gather(self, ring, width, elem_bytes, start, batch, step, out):

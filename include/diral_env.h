@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DIRAL_ABI_VERSION 1
+#define DIRAL_ABI_VERSION 2
 
 enum {
     DIRAL_OK = 0,
@@ -103,6 +103,12 @@ int diral_bind(void *handle, const diral_buffers *bufs);
  * generator (Philox4x32-10 keyed by seed and the GLOBAL env index). */
 int diral_reset(void *handle, const double *x0, const double *y0, const double *v0, uint64_t seed,
                 void *stream);
+
+/* Network.reset_positions (network.py:181-187), reached through TestEnv.reset_mobility_env (test_env.py:479-484):
+ * fresh vehicles -- zero tables and a new topology as in diral_reset -- while last_arrival_time, the episode
+ * accumulators and everything the caller counts (slot, episode) keep their values. */
+int diral_reset_topology(void *handle, const double *x0, const double *y0, const double *v0, uint64_t seed,
+                         void *stream);
 
 /* TestEnv.sample (test_env.py:116-122): uniform actions on [0,R), out [E][N] int32 (device). */
 int diral_sample(void *handle, uint64_t seed, int64_t t, int32_t *out, void *stream);
@@ -210,9 +216,31 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
                     double episode, double epsilon, float *h_state, float *h_rews, float *h_obs,
                     void *stream);
 
-/* Test/bench knobs: "variant" = 0 auto | 1 lane-group kernel (N <= 32) | 2 one-CTA-per-env kernel;
- * "track_lat" = 1 keeps last_arrival_time bookkeeping on even before the first my_step_ch call. */
+/* Compact host format of diral_step_host ("host_format" = 1, opt-in): the state rows of TestEnv.obtain_state
+ * (test_env.py:527-583) are mostly known to the host already (the one-hot of the action it sent, index, episode,
+ * epsilon) or a few bytes of information per agent (B bin counts behind the B float32 of the positional
+ * distribution).  With host_format 1 only that information crosses PCIe (counts as bytes, rewards, and obs /
+ * positions / velocities when the State block carries them) and the library's host threads ("host_threads", default
+ * = the CPUs the process may run on, minus one) assemble the [E][N][S] float32 rows in h_state, bit for bit what
+ * host_format 0 delivers.  State blocks without a fused build (add_positional_dist, VPD type 1) keep format 0.
+ *
+ * diral_expand_state_host is that row assembly alone (no device involved): agents = E*N records in, rows out. */
+int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t *actions, const uint8_t *counts,
+                            const float *rews, const float *obs, const double *pos_x, const double *pos_y,
+                            const double *vel, double episode, double epsilon, int32_t threads, float *out);
+
+/* One slot of a device-resident replay ring (Memory.add, utils/memory.py:169-175): ring[slot] = src, row_bytes
+ * bytes device to device on `stream`. */
+int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes, const void *src, void *stream);
+
+/* Options.  Test/bench knobs: "variant" = 0 auto | 1 lane-group kernel (N <= 32) | 2 one-CTA-per-env kernel;
+ * "track_lat" = 1 keeps last_arrival_time bookkeeping on even before the first my_step_ch call.
+ * diral_step_host: "host_format" (0 full rows | 1 compact), "host_threads", "host_chunks" (env chunks pipelined per
+ * call).  Checkpoint restore: "ticks" (table ticks since the reset = every vehicle's own sequence number) and
+ * "lat_live" (a my_step_ch has stamped last_arrival_time); diral_get_option reads any of them back (-1: unknown),
+ * plus "compact_ok" (1 when this State block has a compact host format). */
 int diral_set_option(void *handle, const char *name, int64_t value);
+int64_t diral_get_option(void *handle, const char *name);
 
 /* Number of kernels launched through this handle since creation (bench bookkeeping). */
 int64_t diral_launch_count(void *handle);
