@@ -60,6 +60,7 @@ struct Handle {
     int host_format = 0;            // 0 = full rows over PCIe, 1 = compact record + host-side row assembly
     int host_threads = 0;           // 0 = pick from the CPUs this process may run on
     int host_chunks = 4;
+    int host_nt = -1;               // output-row stores: 1 non-temporal, 0 ordinary, -1 by output size per thread
     diral::HostPool *pool = nullptr;
     uint8_t *d_counts = nullptr;    // [E][N][B] device
     uint8_t *h_counts = nullptr;    // pinned staging of the same
@@ -278,7 +279,11 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     job.episode = episode; job.epsilon = epsilon; job.out = h_state;
     long long bounds[MAX_HOST_CHUNKS + 1];
     for (int k = 0; k <= chunks; ++k) bounds[k] = (E * k / chunks) * N;
-    h->pool->begin(host_layout(c), job, bounds, chunks);
+    diral::HostLayout lay = host_layout(c);
+    // a worker's share of the rows stays in its private L2 from call to call when it is small enough
+    lay.nt_stores = h->host_nt >= 0 ? h->host_nt
+                                    : ((size_t)A * lay.S * sizeof(float) / (size_t)h->pool->threads() > (size_t)(1 << 20) + (1 << 19));
+    h->pool->begin(lay, job, bounds, chunks);
     PoolJobGuard guard{h->pool, chunks};
 
     DIRAL_CUDA(cudaEventRecord(h->pipe_ev[2], s));                 // everything queued on the caller's stream so far
@@ -433,6 +438,11 @@ int diral_set_option(void *handle, const char *name, int64_t value)
         h->host_threads = (int)value;
         return DIRAL_OK;
     }
+    if (!strcmp(name, "host_nt")) {
+        if (value < -1 || value > 1) return fail(DIRAL_ERR_ARG, "host_nt must be -1 (auto), 0 or 1");
+        h->host_nt = (int)value;
+        return DIRAL_OK;
+    }
     if (!strcmp(name, "host_chunks")) {
         if (value < 1 || value > MAX_HOST_CHUNKS) return fail(DIRAL_ERR_ARG, "host_chunks must be in [1, %d]", MAX_HOST_CHUNKS);
         h->host_chunks = (int)value;
@@ -457,6 +467,7 @@ int64_t diral_get_option(void *handle, const char *name)
     if (!strcmp(name, "host_format")) return h->host_format;
     if (!strcmp(name, "host_threads")) return h->pool ? h->pool->threads() : h->host_threads;
     if (!strcmp(name, "host_chunks")) return h->host_chunks;
+    if (!strcmp(name, "host_nt")) return h->host_nt;
     if (!strcmp(name, "ticks")) return h->ticks;
     if (!strcmp(name, "lat_live")) return h->lat_live ? 1 : 0;
     if (!strcmp(name, "compact_ok")) return compact_ok(h->cfg) ? 1 : 0;
@@ -801,7 +812,9 @@ int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t 
     diral::HostJob job{};
     job.actions = actions; job.counts = counts; job.rews = rews; job.obs = obs; job.pos_x = pos_x; job.pos_y = pos_y;
     job.vel = vel; job.episode = episode; job.epsilon = epsilon; job.out = out;
-    const diral::HostLayout lay = host_layout(*cfg);
+    diral::HostLayout lay = host_layout(*cfg);
+    lay.nt_stores = threads < 0;             // (bench knob: a negative thread count selects non-temporal stores)
+    if (threads < 0) threads = -threads;
     if (threads <= 1) { diral::expand_rows(lay, job, 0, agents); return DIRAL_OK; }
     // one pool per thread count, kept for the life of the process (this entry point has no handle to own it)
     static std::mutex mu;

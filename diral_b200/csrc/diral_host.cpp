@@ -1,9 +1,10 @@
 // diral_host.cpp -- assembling TestEnv.obtain_state rows (reference envs/test_env.py:527-583) on the host from the
 // compact per-agent record diral_step_host moves over PCIe.  See diral_host.h.
 //
-// The expander is bound by host-memory write bandwidth (S float32 per agent, 21.5 MB per slot at the headline
-// configuration), so rows are built in a small L1-resident staging block and leave as non-temporal 16-byte stores:
-// no read-for-ownership of the destination lines, and nothing of the output stays in the caches.
+// The expander writes S float32 per agent (21.5 MB per slot at the headline configuration).  Every worker owns the
+// same contiguous row range in every call, so when a worker's share fits its private L2 the rows are written with
+// ordinary stores and stay cache-resident for the consumer (no DRAM round trip at all when the caller reuses its
+// buffer); larger outputs leave as non-temporal 16-byte stores (no read-for-ownership of the destination lines).
 #include "diral_host.h"
 
 #include <atomic>
@@ -32,10 +33,10 @@ const float *vpd_quotients()
     return lut.data();
 }
 
-void stream_out(float *dst, const float *src, long long n)
+void stream_out(float *dst, const float *src, long long n, bool nt)
 {
     // dst is 16-byte aligned whenever the caller's buffer is and the row range starts at a multiple of 4 agents
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (n & 3) == 0) {
+    if (nt && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (n & 3) == 0) {
         for (long long i = 0; i < n; i += 4)
             _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_load_si128(reinterpret_cast<const __m128i *>(src + i)));
     } else {
@@ -60,6 +61,14 @@ bool vector_rows_ok(const HostLayout &lay, const HostJob &job)
     return (lay.S & 3) == 0 && (reinterpret_cast<uintptr_t>(job.out) & 15) == 0;
 }
 
+template <bool NT>
+inline void put4(float *w, __m128i v)
+{
+    if (NT) _mm_stream_si128(reinterpret_cast<__m128i *>(w), v);
+    else _mm_store_si128(reinterpret_cast<__m128i *>(w), v);
+}
+
+template <bool NT>
 void expand_rows_vector(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
 {
     const int R = lay.R, B = lay.B, S = lay.S;
@@ -73,13 +82,13 @@ void expand_rows_vector(const HostLayout &lay, const HostJob &job, long long a0,
             const __m128i av = _mm_set1_epi32(act);
             __m128i idx = lane_id;
             for (int r = 0; r < R; r += 4, w += 4) {
-                _mm_stream_si128(reinterpret_cast<__m128i *>(w), _mm_and_si128(_mm_cmpeq_epi32(idx, av), one_bits));
+                put4<NT>(w, _mm_and_si128(_mm_cmpeq_epi32(idx, av), one_bits));
                 idx = _mm_add_epi32(idx, four);
             }
         }
         if (lay.add_channel_obs) {
             const float *o = job.obs + a * R;
-            for (int r = 0; r < R; r += 4, w += 4) _mm_stream_ps(w, _mm_loadu_ps(o + r));
+            for (int r = 0; r < R; r += 4, w += 4) put4<NT>(w, _mm_castps_si128(_mm_loadu_ps(o + r)));
         }
         if (lay.piggy) {
             const uint8_t *c = job.counts + a * B;
@@ -96,17 +105,20 @@ void expand_rows_vector(const HostLayout &lay, const HostJob &job, long long a0,
             acc = _mm_add_epi32(acc, _mm_shuffle_epi32(acc, 0xb1));       // every lane = len(s)
             // len == 0: every count is 0 too; dividing by 1 leaves the all-zero vector (network.py:502-505)
             const __m128 den = _mm_cvtepi32_ps(_mm_max_epi16(acc, _mm_set1_epi32(1)));
-            for (int b = 0; b < B; b += 4, w += 4) _mm_stream_ps(w, _mm_div_ps(_mm_cvtepi32_ps(c32[b >> 2]), den));
+            for (int b = 0; b < B; b += 4, w += 4) put4<NT>(w, _mm_castps_si128(_mm_div_ps(_mm_cvtepi32_ps(c32[b >> 2]), den)));
         }
     }
-    _mm_sfence();
+    if (NT) _mm_sfence();
 }
 
 }  // namespace
 
 void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
 {
-    if (vector_rows_ok(lay, job)) { expand_rows_vector(lay, job, a0, a1); return; }
+    if (vector_rows_ok(lay, job)) {
+        if (lay.nt_stores) expand_rows_vector<true>(lay, job, a0, a1); else expand_rows_vector<false>(lay, job, a0, a1);
+        return;
+    }
     const int N = lay.N, R = lay.R, B = lay.B, S = lay.S;
     const float *lut = vpd_quotients();
     // staging block: a multiple of 4 rows (so every flush is a whole number of 16-byte pieces), about 16 KB
@@ -146,7 +158,7 @@ void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long l
             if (lay.add_velocity) *w++ = (float)job.vel[a];                   // :575-576
             if (lay.fingerprint) { *w++ = (float)job.episode; *w++ = (float)job.epsilon; }   // :577-579
         }
-        stream_out(job.out + b0 * S, stage, (b1 - b0) * S);
+        stream_out(job.out + b0 * S, stage, (b1 - b0) * S, lay.nt_stores != 0);
     }
     _mm_sfence();
 }

@@ -15,6 +15,7 @@ struct HostLayout {                 // the State block (test_env.py:27-41) as th
     int N, R, B, S;
     int add_action, action_binary, add_channel_obs, piggy, add_reward, add_index, add_position, add_velocity, fingerprint;
     double L;
+    int nt_stores;                  // non-temporal stores for the output rows (else ordinary, cache-resident ones)
 };
 
 struct HostJob {                    // one call: per-agent inputs (index a = env * N + vehicle) and the output rows

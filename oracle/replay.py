@@ -4,7 +4,8 @@
 
 Parity status: ``Memory`` is pinned against the reference's own class by
 tests/golden/make_golden_replay.py (fixture tests/golden/replay_memory.npz); the regrouping functions
-live in a module that imports TensorFlow and are restated line by line (unpinned).
+live in a module that imports TensorFlow, so ``regroup`` is pinned against their text sliced out of the unmodified
+file and executed by tests/golden/make_golden_regroup.py (fixture replay_regroup.npz).
 """
 from collections import deque
 

@@ -3,8 +3,10 @@
 
 The reference keeps this code inline in ``marl_test`` (main_test.py:14), a function that cannot run
 here because the module imports TensorFlow; only ``calculate_ia_penalty`` is importable.  Parity
-status: ``ia_penalty_sum`` is pinned against the reference's own function by
-tests/golden/make_golden_shaping.py; the shaping loop is a line-by-line restatement (unpinned).
+status: PINNED.  ``ia_penalty_sum`` against the reference's own function (tests/golden/make_golden_shaping.py);
+``shape_slot`` against the reference's own loop body, sliced out of the unmodified main_test.py and executed with stub
+``env`` / ``mainDRQN`` objects by tests/golden/make_golden_shaping_slots.py (fixture shaping_slots.json,
+tests/test_oracle_golden.py::test_shape_slot_matches_reference_text).
 """
 import numpy as np
 

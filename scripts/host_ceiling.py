@@ -67,9 +67,10 @@ def expander(threads, reps=30):
     return {"threads": threads, "us": dt * 1e6, "GBps_written": A * S * 4 / dt / 1e9}
 
 
-def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, reps=40):
+def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, nt=-1, reps=40):
     env.set_host_format(fmt, threads)
     env.lib.diral_set_option(env._handle, b"host_chunks", chunks)
+    env.lib.diral_set_option(env._handle, b"host_nt", nt)
     for k in range(4):
         env.step_host(h_act[k % 8], h_state, h_rews)
     torch.cuda.synchronize()
@@ -78,7 +79,7 @@ def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, reps=40):
         env.step_host(h_act[k % 8], h_state, h_rews)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
-    return {"format": fmt, "host_threads": threads, "chunks": chunks, "us_per_slot": dt * 1e6,
+    return {"format": fmt, "host_threads": threads, "chunks": chunks, "nt_stores": nt, "us_per_slot": dt * 1e6,
             "agent_steps_per_s": E_PER_GPU * N_UE / dt}
 
 
@@ -95,8 +96,9 @@ def main():
         for nb in (full, compact, 256 << 20):
             out["d2h"].append(d2h_ceiling(n, nb))
         n *= 2
-    for th in sorted({1, 2, 4, 8, max(cpus // 2, 1), max(cpus - 1, 1), cpus}):
-        out["expander"].append(expander(th))
+    for th in sorted({1, 2, 4, 8, 12, max(cpus - 2, 1), max(cpus - 1, 1)}):
+        out["expander"].append(dict(expander(th), stores="ordinary"))
+        out["expander"].append(dict(expander(-th), stores="non-temporal"))
     env = TestEnv(num_envs=E_PER_GPU, device="cuda:0", seed=1234, **ENV_KW)
     acts = [env.sample(t) for t in range(8)]
     for t in range(60):
@@ -105,9 +107,10 @@ def main():
     h_state = torch.empty((E_PER_GPU, N_UE, env.S), dtype=torch.float32).pin_memory()
     h_rews = torch.empty((E_PER_GPU, N_UE), dtype=torch.float32).pin_memory()
     out["step_host"].append(step_host(env, "full", 1, 4, h_act, h_state, h_rews))
-    for th in sorted({4, 8, max(cpus - 1, 1), max(cpus // 2, 1)}):
-        for ch in (2, 4, 8, 16):
-            out["step_host"].append(step_host(env, "compact", th, ch, h_act, h_state, h_rews))
+    for th in sorted({4, 8, 12, max(cpus - 3, 1), max(cpus - 2, 1), max(cpus - 1, 1)}):
+        for ch in (2, 4, 8):
+            for nt in (0, 1):
+                out["step_host"].append(step_host(env, "compact", th, ch, h_act, h_state, h_rews, nt))
     print(json.dumps(out, indent=1))
 
 

@@ -8,7 +8,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-AUX_FIXTURES = {"replay_memory", "wire_vpd", "sps"}      # fixtures of the "next" rows, not env rollouts
+AUX_FIXTURES = {"replay_memory", "replay_regroup", "wire_vpd", "sps"}      # fixtures of the "next" rows, not env rollouts
 
 
 def golden_names():

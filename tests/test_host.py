@@ -184,3 +184,102 @@ def test_signed_distance_identity():
         d = math.sqrt((x2 - x1) ** 2 + (0.0 - 0.0) ** 2)
         s_ref = d * (1 if x1 - x2 > 0.0 else -1)
         assert s_ref == x1 - x2 or (s_ref == 0 and x1 - x2 == 0)
+
+
+# the EnvironmentTest blocks of the six shipped YAML files (configs/4ue_3r_toy/*.yaml): they differ in num_bins only
+_SHIPPED_ENVIRONMENT_TEST = dict(
+    congestion_test=True, load_positions=False,
+    load_file_pos="save_results/realness/drqn/config_realness_pos_store/positions_2000.npy", num_channels=3, num_users=4,
+    mobility=True, mobility_vary=False, highway_length=100, enable_fingerprint=False, reward_design=2,
+    communication_range=250,
+    State=dict(type=2, add_action=True, add_reward=False, add_index=False, add_velocity=False, action_index="binary",
+               piggybacking=False, add_position=False, add_positional_dist=False, add_positional_dist_piggy=True,
+               add_positional_dist_type=2, add_channel_obs=False, num_bins=20))
+
+
+@pytest.mark.parametrize("bins", [10, 20, 20, 20, 20, 40])     # b10_dis_07, b20_dis_03/05/07/95, b40_dis_07
+def test_every_shipped_yaml_block_is_accepted(bins):
+    """cfg_from_kwargs takes the shipped EnvironmentTest blocks verbatim (TestEnv(**cfg["EnvironmentTest"]),
+    main_test.py:46) and yields the state space the reference computes (test_env.py:49-85: R + num_bins)."""
+    from diral_b200 import _lib, cfg_from_kwargs
+    kw = dict(_SHIPPED_ENVIRONMENT_TEST, State=dict(_SHIPPED_ENVIRONMENT_TEST["State"], num_bins=bins))
+    cfg = cfg_from_kwargs(8, 0, kw)
+    assert (cfg.N, cfg.R, cfg.B, cfg.toy, cfg.mobility, cfg.L, cfg.C, cfg.W) == (4, 3, bins, 1, 1, 100.0, 250.0, 500.0)
+    assert _lib.load().diral_state_space(C.byref(cfg)) == 3 + bins
+
+
+@pytest.mark.parametrize("state,extra,threads", [
+    (dict(), {}, 1), (dict(), {}, 4), (dict(), {}, -3),
+    (dict(add_channel_obs=True, add_reward=True, add_index=True, add_position=True, add_velocity=True),
+     dict(enable_fingerprint=True), 3),
+    (dict(action_index="real", num_bins=7, add_reward=True), dict(num_channels=5, num_users=13), 2),
+    (dict(add_action=False, num_bins=12), dict(num_channels=9), -2),
+    (dict(add_positional_dist_piggy=False, add_channel_obs=True), dict(num_channels=8), 2),
+])
+def test_host_row_assembly_matches_obtain_state_layout(state, extra, threads):
+    """diral_expand_state_host -- the host half of the compact host format -- against the row layout of
+    TestEnv.obtain_state (test_env.py:527-583) built with NumPy in float64 and rounded to float32 once."""
+    from diral_b200 import _lib, cfg_from_kwargs
+    lib = _lib.load()
+    kw = dict(dict(num_users=32, num_channels=20, highway_length=800, reward_design=2, communication_range=250,
+                   mobility=True, bin_range=500), **extra)
+    st = _state(**state)
+    kw["State"] = st
+    E = 97
+    cfg = cfg_from_kwargs(E, 0, kw)
+    N, R, B = cfg.N, cfg.R, cfg.B
+    A, S = E * N, lib.diral_state_space(C.byref(cfg))
+    rs = np.random.RandomState(5)
+    act = rs.randint(0, R, A).astype(np.int32); act[3] = R + 2; act[4] = -1          # clamped like the kernels do
+    counts = (rs.randint(0, 4, (A, B)) * (rs.rand(A, 1) < 0.9)).astype(np.uint8)
+    rews = rs.randn(A).astype(np.float32); obs = (rs.rand(A, R) * 300).astype(np.float32)
+    px = rs.rand(A) * 800; py = rs.randint(0, 3, A).astype(np.float64); vel = rs.rand(A) + 1.1
+    out = np.full((A, S), np.nan, np.float32)
+    rc = lib.diral_expand_state_host(C.byref(cfg), A, act.ctypes.data, counts.ctypes.data, rews.ctypes.data, obs.ctypes.data,
+                                     px.ctypes.data, py.ctypes.data, vel.ctypes.data, 3.0, 0.25, threads, out.ctypes.data)
+    assert rc == 0, lib.diral_last_error()
+    cols = []
+    a = np.clip(act, 0, R - 1)
+    if st["add_action"]:
+        cols.append(np.eye(R)[a] if st["action_index"] == "binary" else a[:, None].astype(np.float64))
+    if st["add_channel_obs"]:
+        cols.append(obs.astype(np.float64))
+    if st["add_positional_dist_piggy"]:
+        m = counts.sum(1, keepdims=True).astype(np.float64)
+        cols.append(np.where(m > 0, counts / np.maximum(m, 1), 0.0))
+    if st["add_reward"]:
+        cols.append(rews[:, None].astype(np.float64))
+    if st["add_index"]:
+        cols.append((np.arange(A) % N + 1)[:, None].astype(np.float64))
+    if st["add_position"]:
+        cols += [(px / cfg.L)[:, None], (py / 2)[:, None]]
+    if st["add_velocity"]:
+        cols.append(vel[:, None])
+    if kw.get("enable_fingerprint"):
+        cols += [np.full((A, 1), 3.0), np.full((A, 1), 0.25)]
+    ref = np.concatenate(cols, axis=1).astype(np.float32)
+    assert ref.shape == out.shape and (out == ref).all()
+
+
+def test_host_row_assembly_rejects_unfused_state_blocks():
+    from diral_b200 import _lib, cfg_from_kwargs
+    lib = _lib.load()
+    kw = dict(num_users=8, num_channels=3, highway_length=200, State=_state(add_positional_dist_type=1))
+    cfg = cfg_from_kwargs(2, 0, kw)
+    out = np.zeros((16, 23), np.float32); act = np.zeros(16, np.int32); cnt = np.zeros((16, 20), np.uint8)
+    rc = lib.diral_expand_state_host(C.byref(cfg), 16, act.ctypes.data, cnt.ctypes.data, None, None, None, None, None,
+                                     0.0, 1.0, 1, out.ctypes.data)
+    assert rc == -5 and b"compact" in lib.diral_last_error()
+
+
+def test_reference_install_recipe_and_timing_harness():
+    """oracle/install_ref.py places the unmodified env files under oracle/_ref/ (git-ignored); oracle/ref_python.py
+    imports them with the two shims and steps the real TestEnv.  Skipped where neither the reference nor an
+    installed copy exists."""
+    from oracle import install_ref, ref_python
+    if not install_ref.install() and not ref_python.available():
+        pytest.skip("no /root/reference and no oracle/_ref on this machine")
+    res = ref_python.time_reference(dict(_SHIPPED_ENVIRONMENT_TEST), seconds=0.2, warm=2, processes=2)
+    assert res["one_core"] > 0 and res["all_cores_P_processes"] > 0 and res["P"] == 2
+    ignored = open(os.path.join(ROOT, ".gitignore")).read()
+    assert "oracle/_ref/" in ignored

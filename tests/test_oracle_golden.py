@@ -128,3 +128,43 @@ def test_sps_oracle_matches_reference():
             assert (a == s["c%d_acts" % i][t]).all(), (i, t)
             assert (bank.prev == s["c%d_prev" % i][t]).all() and (bank.counter == s["c%d_cnt" % i][t]).all(), (i, t)
             assert not f.any()
+
+
+def test_shape_slot_matches_reference_text():
+    """oracle/shaping.py::shape_slot against the reference's own loop body -- main_test.py:150-206, sliced out of the
+    unmodified file and executed by tests/golden/make_golden_shaping_slots.py: shaped rewards, slot sums and every
+    loop-carried variable, float64 bit for bit, over all option combinations."""
+    import json
+    import os
+    from golden_util import GOLDEN_DIR
+    from oracle.shaping import ShapingState, shape_slot
+    fx = json.load(open(os.path.join(GOLDEN_DIR, "shaping_slots.json")))
+    assert len(fx["cases"]) >= 20
+    for c in fx["cases"]:
+        st = ShapingState(c["num_users"])
+        for k, s in enumerate(c["slots"]):
+            reward = np.array(s["reward_in"], dtype=np.float64)
+            sum_r, coll, ia_sum = shape_slot(st, s["ia"], s["action"], reward, c["num_channels"], **c["opts"])
+            assert reward.tolist() == s["reward_out"], (c["opts"], k)
+            assert (sum_r, coll, ia_sum) == (s["sum_r"], s["collision"], s["ia_sum"]), (c["opts"], k)
+            if c["opts"]["ia_averaging"]:
+                assert st.sum_ia_prev == s["sum_ia_prev"]
+            if c["opts"]["ia_penalty_enable"]:
+                assert [int(x) for x in st.counter] == s["counter"]
+                assert [int(x) for x in st.previous_actions] == s["previous_actions"]
+
+
+def test_regroup_matches_reference_text():
+    """oracle/replay.py::regroup against get_states_user / get_actions_user / get_rewards_user / get_next_states_user
+    (algorithms/drl_drqn.py:294-377), sliced out of the unmodified file and executed by make_golden_regroup.py."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from oracle.replay import regroup
+    g = np.load(os.path.join(GOLDEN_DIR, "replay_regroup.npz"))
+    st, ac, rw, nx = g["states"], g["actions"], g["rewards"], g["next_states"]
+    BATCH, STEP, U = ac.shape
+    batch = [[(st[b, k], ac[b, k], rw[b, k], nx[b, k]) for k in range(STEP)] for b in range(BATCH)]
+    for field, name in enumerate(("states", "actions", "rewards", "next_states")):
+        got = regroup(batch, field, U)
+        want = g["out_" + name]
+        assert got.shape == want.shape and got.dtype == want.dtype and (got == want).all(), name
