@@ -80,6 +80,7 @@ SYMBOLS = {
     "diral_get_option": (C.c_int64, [_P, C.c_char_p]),
     "diral_reset_topology": (C.c_int, [_P, _P, _P, _P, _U64, _P]),
     "diral_expand_state_host": (C.c_int, [C.POINTER(DiralCfg), _I64, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I32, _P]),
+    "diral_host_trace": (C.c_int32, [_P, _P, _I32]),
     "diral_ring_put": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
 }
 

@@ -7,6 +7,7 @@
 #include "diral_launch.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -67,6 +68,8 @@ struct Handle {
     float *h_obs_stage = nullptr;   // pinned [E][N][R] when the State block wants obs and the caller passes no h_obs
     double *h_kin = nullptr;        // pinned [3][E][N]: post-mobility x, y, velocity (add_position / add_velocity)
     cudaEvent_t chunk_ev[MAX_HOST_CHUNKS] = {};
+    double trace_us[MAX_HOST_CHUNKS + 4] = {};   // timeline of the last compact diral_step_host call (diral_host_trace)
+    int trace_n = 0;
 };
 
 struct DeviceGuard {
@@ -205,6 +208,7 @@ diral::Params env_range(const diral::Params &p, long long e0, long long n)
     if (q.tab_seq) { q.tab_seq += e0 * NN; q.tab_lu += e0 * NN; q.tab_x += e0 * NN; }
     if (q.lat) q.lat += e0 * NN;
     q.obs += e0 * N * p.R; q.rews += e0 * N; q.state += e0 * N * p.S;
+    if (q.vpd_counts) q.vpd_counts += e0 * N * p.B;
     q.acc_reward += e0; q.acc_count += e0 * diral::ACC_COUNTS;
     if (q.scratch) q.scratch += e0 * (long long)diral::step_block_scratch_words_per_env(p.N);
     return q;
@@ -239,6 +243,8 @@ struct PoolJobGuard {
 int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
                       float *h_state, float *h_rews, float *h_obs, cudaStream_t s)
 {
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_entry).count(); };
     const diral_cfg &c = h->cfg;
     const long long E = c.E, N = c.N, R = c.R, B = c.B, A = E * N;
     const bool group = use_group(h);
@@ -285,6 +291,7 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
                                     : ((size_t)A * lay.S * sizeof(float) / (size_t)h->pool->threads() > (size_t)(1 << 20) + (1 << 19));
     h->pool->begin(lay, job, bounds, chunks);
     PoolJobGuard guard{h->pool, chunks};
+    h->trace_us[0] = since();                                      // workers woken
 
     DIRAL_CUDA(cudaEventRecord(h->pipe_ev[2], s));                 // everything queued on the caller's stream so far
     for (int k = 0; k < chunks; ++k) {
@@ -313,11 +320,15 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         DIRAL_CUDA(cudaEventRecord(h->pipe_ev[k], h->pipe[k]));
         DIRAL_CUDA(cudaStreamWaitEvent(s, h->pipe_ev[k], 0));
     }
+    h->trace_us[1] = since();                                      // everything enqueued
     for (int k = 0; k < chunks; ++k) {                             // rows of chunk k are assembled while k+1.. still run
         DIRAL_CUDA(cudaEventSynchronize(h->chunk_ev[k]));
         h->pool->publish(k);
+        h->trace_us[2 + k] = since();                              // chunk k's record is in host memory
     }
     guard.close();
+    h->trace_us[2 + chunks] = since();                             // every row assembled
+    h->trace_n = 3 + chunks;
     return DIRAL_OK;
 }
 
@@ -828,6 +839,15 @@ int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t 
     pool->publish(0); pool->publish(1);
     pool->finish();
     return DIRAL_OK;
+}
+
+int32_t diral_host_trace(void *handle, double *out_us, int32_t n)
+{
+    Handle *h = as_handle(handle);
+    if (!h || !out_us) return 0;
+    const int m = std::min<int>(n, h->trace_n);
+    for (int i = 0; i < m; ++i) out_us[i] = h->trace_us[i];
+    return m;
 }
 
 int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes, const void *src, void *stream)

@@ -9,8 +9,9 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
-#include <emmintrin.h>
+#include <immintrin.h>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -48,6 +49,8 @@ void stream_out(float *dst, const float *src, long long n, bool nt)
 
 namespace {
 
+#define DIRAL_TARGET_FMA_FWD __attribute__((target("avx2,fma")))
+
 // Rows whose blocks are all whole 16-byte groups (one-hot over R % 4 == 0 resources, obs likewise, B % 4 == 0 bins,
 // no scalar tail -- the shipped State block, S = R + B) are formed in registers and leave as non-temporal stores
 // straight from them: per agent R/4 compares for the one-hot and B/4 divisions (IEEE float32 division of two small
@@ -61,6 +64,11 @@ bool vector_rows_ok(const HostLayout &lay, const HostJob &job)
     return (lay.S & 3) == 0 && (reinterpret_cast<uintptr_t>(job.out) & 15) == 0;
 }
 
+DIRAL_TARGET_FMA_FWD inline __m128 fma_quotient(__m128 c, __m128 den, __m128 rcp, __m128 q0)
+{
+    return _mm_fmadd_ps(_mm_fnmadd_ps(q0, den, c), rcp, q0);
+}
+
 template <bool NT>
 inline void put4(float *w, __m128i v)
 {
@@ -68,8 +76,17 @@ inline void put4(float *w, __m128i v)
     else _mm_store_si128(reinterpret_cast<__m128i *>(w), v);
 }
 
-template <bool NT>
-void expand_rows_vector(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
+// counts / len without a division per bin: one correctly rounded reciprocal per agent, then per group of four bins
+//   q0 = c * rcp;  q = fma(fma(-q0, len, c), rcp, q0)
+// which equals the correctly rounded c / len for all 0 <= c <= len < 1024 (the lemma the kernels use, checked
+// exhaustively in tests/test_host.py).  Needs fused multiply-add: compiled for AVX2+FMA, chosen at run time.
+#define DIRAL_TARGET_FMA __attribute__((target("avx2,fma")))
+
+template <bool NT, bool FMA>
+#if defined(__GNUC__)
+__attribute__((always_inline))
+#endif
+inline void expand_rows_vector_impl(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
 {
     const int R = lay.R, B = lay.B, S = lay.S;
     const __m128i lane_id = _mm_set_epi32(3, 2, 1, 0), four = _mm_set1_epi32(4), zero = _mm_setzero_si128();
@@ -105,10 +122,30 @@ void expand_rows_vector(const HostLayout &lay, const HostJob &job, long long a0,
             acc = _mm_add_epi32(acc, _mm_shuffle_epi32(acc, 0xb1));       // every lane = len(s)
             // len == 0: every count is 0 too; dividing by 1 leaves the all-zero vector (network.py:502-505)
             const __m128 den = _mm_cvtepi32_ps(_mm_max_epi16(acc, _mm_set1_epi32(1)));
-            for (int b = 0; b < B; b += 4, w += 4) put4<NT>(w, _mm_castps_si128(_mm_div_ps(_mm_cvtepi32_ps(c32[b >> 2]), den)));
+            if (FMA) {
+                const __m128 rcp = _mm_div_ps(_mm_set1_ps(1.0f), den);
+                for (int b = 0; b < B; b += 4, w += 4) {
+                    const __m128 c = _mm_cvtepi32_ps(c32[b >> 2]);
+                    const __m128 q0 = _mm_mul_ps(c, rcp);
+                    put4<NT>(w, _mm_castps_si128(fma_quotient(c, den, rcp, q0)));
+                }
+            } else {
+                for (int b = 0; b < B; b += 4, w += 4) put4<NT>(w, _mm_castps_si128(_mm_div_ps(_mm_cvtepi32_ps(c32[b >> 2]), den)));
+            }
         }
     }
     if (NT) _mm_sfence();
+}
+
+void rows_sse_nt(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<true, false>(l, j, a0, a1); }
+void rows_sse_st(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<false, false>(l, j, a0, a1); }
+DIRAL_TARGET_FMA void rows_fma_nt(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<true, true>(l, j, a0, a1); }
+DIRAL_TARGET_FMA void rows_fma_st(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<false, true>(l, j, a0, a1); }
+
+bool cpu_has_fma()
+{
+    static const bool yes = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma") && !getenv("DIRAL_HOST_NO_FMA");
+    return yes;
 }
 
 }  // namespace
@@ -116,7 +153,8 @@ void expand_rows_vector(const HostLayout &lay, const HostJob &job, long long a0,
 void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
 {
     if (vector_rows_ok(lay, job)) {
-        if (lay.nt_stores) expand_rows_vector<true>(lay, job, a0, a1); else expand_rows_vector<false>(lay, job, a0, a1);
+        if (cpu_has_fma()) { if (lay.nt_stores) rows_fma_nt(lay, job, a0, a1); else rows_fma_st(lay, job, a0, a1); }
+        else { if (lay.nt_stores) rows_sse_nt(lay, job, a0, a1); else rows_sse_st(lay, job, a0, a1); }
         return;
     }
     const int N = lay.N, R = lay.R, B = lay.B, S = lay.S;

@@ -229,6 +229,11 @@ int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t 
                             const float *rews, const float *obs, const double *pos_x, const double *pos_y,
                             const double *vel, double episode, double epsilon, int32_t threads, float *out);
 
+/* Timeline of the last compact-format diral_step_host call, microseconds since its entry: [0] host threads woken,
+ * [1] all chunks enqueued, [2 + k] chunk k's record landed in host memory, [2 + chunks] every row assembled.
+ * Returns the number of values written (<= n).  Measurement aid: says what bounds the end-to-end slot. */
+int32_t diral_host_trace(void *handle, double *out_us, int32_t n);
+
 /* One slot of a device-resident replay ring (Memory.add, utils/memory.py:169-175): ring[slot] = src, row_bytes
  * bytes device to device on `stream`. */
 int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes, const void *src, void *stream);

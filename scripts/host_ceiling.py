@@ -79,7 +79,9 @@ def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, nt=-1, reps=40)
         env.step_host(h_act[k % 8], h_state, h_rews)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
-    return {"format": fmt, "host_threads": threads, "chunks": chunks, "nt_stores": nt, "us_per_slot": dt * 1e6,
+    tr = (C.c_double * 40)()
+    n = env.lib.diral_host_trace(env._handle, tr, 40)
+    return {"trace_us_last_call": [round(tr[i], 1) for i in range(n)], "format": fmt, "host_threads": threads, "chunks": chunks, "nt_stores": nt, "us_per_slot": dt * 1e6,
             "agent_steps_per_s": E_PER_GPU * N_UE / dt}
 
 
