@@ -68,6 +68,7 @@ struct Handle {
     float *h_obs_stage = nullptr;   // pinned [E][N][R] when the State block wants obs and the caller passes no h_obs
     double *h_kin = nullptr;        // pinned [3][E][N]: post-mobility x, y, velocity (add_position / add_velocity)
     cudaEvent_t chunk_ev[MAX_HOST_CHUNKS] = {};
+    cudaStream_t chunk_stream[MAX_HOST_CHUNKS] = {};
     double trace_us[MAX_HOST_CHUNKS + 4] = {};   // timeline of the last compact diral_step_host call (diral_host_trace)
     int trace_n = 0;
 };
@@ -208,7 +209,7 @@ diral::Params env_range(const diral::Params &p, long long e0, long long n)
     if (q.tab_seq) { q.tab_seq += e0 * NN; q.tab_lu += e0 * NN; q.tab_x += e0 * NN; }
     if (q.lat) q.lat += e0 * NN;
     q.obs += e0 * N * p.R; q.rews += e0 * N; q.state += e0 * N * p.S;
-    if (q.vpd_counts) q.vpd_counts += e0 * N * p.B;
+    if (q.vpd_counts) q.vpd_counts += e0 * N * p.rec_stride;
     q.acc_reward += e0; q.acc_count += e0 * diral::ACC_COUNTS;
     if (q.scratch) q.scratch += e0 * (long long)diral::step_block_scratch_words_per_env(p.N);
     return q;
@@ -237,35 +238,39 @@ struct PoolJobGuard {
     ~PoolJobGuard() { close(); }
 };
 
-// diral_step_host, compact host format: only the information of a slot crosses PCIe -- VPD bin counts (one byte per
-// bin), rewards, and obs / positions / velocities when the State block carries them -- and the [E][N][S] rows are
-// assembled in the caller's buffer by the handle's host threads while later env chunks are still computing.
+// diral_step_host, compact host format: only the information of a slot crosses PCIe -- per agent one record of VPD
+// bin counts (one byte per bin) and the float32 reward, plus obs / positions / velocities when the State block
+// carries them -- and the [E][N][S] rows are assembled in the caller's buffer by the handle's host threads while later
+// env chunks are still in flight.  A chunk is latency-bound on the device (copy in, one slot kernel, copy out: ~45 us
+// whatever its size), so every chunk runs on its own stream and all of them overlap.
 int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
                       float *h_state, float *h_rews, float *h_obs, cudaStream_t s)
 {
     const auto t_entry = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_entry).count(); };
     const diral_cfg &c = h->cfg;
-    const long long E = c.E, N = c.N, R = c.R, B = c.B, A = E * N;
+    const long long E = c.E, N = c.N, R = c.R, A = E * N;
+    const long long nb = c.add_piggy ? c.B : 0, rec = ((nb + 3) & ~3ll) + 4;     // counts, padding, float32 reward
     const bool group = use_group(h);
     const int src_bits = group ? diral::key_src_bits(diral::group_width(c.N)) : diral::key_src_bits(c.N);
     if (c.add_piggy && h->ticks + 1 >= (1ll << (32 - src_bits)))
         return fail(DIRAL_ERR_SEQ_RANGE, "slot %lld since reset exceeds the %d-bit sequence field of the packed table keys",
                     h->ticks + 1, 32 - src_bits);
     const bool want_obs = c.add_channel_obs != 0, want_kin = c.add_position || c.add_velocity;
-    if (c.add_piggy && !h->d_counts) {
-        DIRAL_CUDA(cudaMalloc(&h->d_counts, (size_t)(A * B)));
-        DIRAL_CUDA(cudaMallocHost(&h->h_counts, (size_t)(A * B)));
+    if (!h->d_counts) {
+        DIRAL_CUDA(cudaMalloc(&h->d_counts, (size_t)(A * rec)));
+        DIRAL_CUDA(cudaMallocHost(&h->h_counts, (size_t)(A * rec)));
     }
     if (want_obs && !h_obs && !h->h_obs_stage) DIRAL_CUDA(cudaMallocHost(&h->h_obs_stage, sizeof(float) * (size_t)(A * R)));
     if (want_kin && !h->h_kin) DIRAL_CUDA(cudaMallocHost(&h->h_kin, sizeof(double) * (size_t)(3 * A)));
-    for (auto &st : h->pipe) if (!st) DIRAL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto &ev : h->pipe_ev) if (!ev) DIRAL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     const int chunks = E >= 1024 ? h->host_chunks : 1;
-    for (int k = 0; k < chunks; ++k)
+    if (!h->pipe_ev[2]) DIRAL_CUDA(cudaEventCreateWithFlags(&h->pipe_ev[2], cudaEventDisableTiming));
+    for (int k = 0; k < chunks; ++k) {
+        if (!h->chunk_stream[k]) DIRAL_CUDA(cudaStreamCreateWithFlags(&h->chunk_stream[k], cudaStreamNonBlocking));
         if (!h->chunk_ev[k]) DIRAL_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
+    }
     if (!h->pool) {
-        int n = h->host_threads > 0 ? h->host_threads : std::min(std::max(usable_cpus() - 1, 1), 32);
+        int n = h->host_threads > 0 ? h->host_threads : std::min(std::max(usable_cpus() - 2, 1), 32);
         h->pool = new (std::nothrow) diral::HostPool(n);
         if (!h->pool) return fail(DIRAL_ERR_ARG, "out of host memory");
     }
@@ -274,13 +279,15 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     p.mode = mode; p.timestep = timestep; p.episode = episode; p.epsilon = epsilon; p.seed = 0;
     p.tick = (int)(h->ticks + 1);
     p.build_state = 1; p.actions = h->d_actions; p.gen_actions = 0; p.actions_out = nullptr;
-    p.vpd_counts = h->d_counts;
+    p.vpd_counts = h->d_counts; p.rec_stride = (int)rec;
     if (mode == DIRAL_MY_STEP_CH && h->bufs.lat) h->lat_live = true;
     p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;
 
     float *obs_dst = h_obs ? h_obs : h->h_obs_stage;
     diral::HostJob job{};
-    job.actions = h_actions; job.counts = h->h_counts; job.rews = h_rews; job.obs = obs_dst;
+    job.actions = h_actions; job.counts = h->h_counts; job.count_stride = rec;
+    job.rews = reinterpret_cast<const float *>(h->h_counts + (rec - 4)); job.rew_stride = rec; job.rews_out = h_rews;
+    job.obs = obs_dst;
     job.pos_x = h->h_kin; job.pos_y = h->h_kin ? h->h_kin + A : nullptr; job.vel = h->h_kin ? h->h_kin + 2 * A : nullptr;
     job.episode = episode; job.epsilon = epsilon; job.out = h_state;
     long long bounds[MAX_HOST_CHUNKS + 1];
@@ -296,15 +303,13 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     DIRAL_CUDA(cudaEventRecord(h->pipe_ev[2], s));                 // everything queued on the caller's stream so far
     for (int k = 0; k < chunks; ++k) {
         const long long a0 = bounds[k], n = bounds[k + 1] - a0, e0 = a0 / N;
-        cudaStream_t ps = h->pipe[k & 1];
-        if (k < 2) DIRAL_CUDA(cudaStreamWaitEvent(ps, h->pipe_ev[2], 0));
+        cudaStream_t ps = h->chunk_stream[k];
+        DIRAL_CUDA(cudaStreamWaitEvent(ps, h->pipe_ev[2], 0));
         DIRAL_CUDA(cudaMemcpyAsync(h->d_actions + a0, h_actions + a0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ps));
         const diral::Params q = env_range(p, e0, n / N);
         DIRAL_CUDA(group ? diral::launch_step_group(q, ps) : diral::launch_step_block(q, ps));
         h->launches += 1;
-        if (c.add_piggy)
-            DIRAL_CUDA(cudaMemcpyAsync(h->h_counts + a0 * B, h->d_counts + a0 * B, (size_t)(n * B), cudaMemcpyDeviceToHost, ps));
-        DIRAL_CUDA(cudaMemcpyAsync(h_rews + a0, h->bufs.rews + a0, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ps));
+        DIRAL_CUDA(cudaMemcpyAsync(h->h_counts + a0 * rec, h->d_counts + a0 * rec, (size_t)(n * rec), cudaMemcpyDeviceToHost, ps));
         if (h_obs || want_obs)
             DIRAL_CUDA(cudaMemcpyAsync(obs_dst + a0 * R, h->bufs.obs + a0 * R, (size_t)(n * R) * sizeof(float), cudaMemcpyDeviceToHost, ps));
         if (c.add_position) {
@@ -314,17 +319,14 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         if (c.add_velocity)
             DIRAL_CUDA(cudaMemcpyAsync(h->h_kin + 2 * A + a0, h->bufs.vel + a0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ps));
         DIRAL_CUDA(cudaEventRecord(h->chunk_ev[k], ps));
+        DIRAL_CUDA(cudaStreamWaitEvent(s, h->chunk_ev[k], 0));    // the caller's stream sees the step as done
     }
     if (c.add_piggy) h->ticks += 1;
-    for (int k = 0; k < 2; ++k) {                                  // the caller's stream sees the step as done
-        DIRAL_CUDA(cudaEventRecord(h->pipe_ev[k], h->pipe[k]));
-        DIRAL_CUDA(cudaStreamWaitEvent(s, h->pipe_ev[k], 0));
-    }
     h->trace_us[1] = since();                                      // everything enqueued
-    for (int k = 0; k < chunks; ++k) {                             // rows of chunk k are assembled while k+1.. still run
+    for (int k = 0; k < chunks; ++k) {                             // rows of chunk k are assembled while k+1.. are in flight
         DIRAL_CUDA(cudaEventSynchronize(h->chunk_ev[k]));
         h->pool->publish(k);
-        h->trace_us[2 + k] = since();                              // chunk k's record is in host memory
+        h->trace_us[2 + k] = since();                              // chunk k's records are in host memory
     }
     guard.close();
     h->trace_us[2 + chunks] = since();                             // every row assembled
@@ -412,6 +414,7 @@ int diral_destroy(void *handle)
     for (auto &st : h->pipe) if (st) cudaStreamDestroy(st);
     for (auto &ev : h->pipe_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->chunk_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &st : h->chunk_stream) if (st) cudaStreamDestroy(st);
     delete h->pool;
     cudaFree(h->d_counts);
     if (h->h_counts) cudaFreeHost(h->h_counts);
@@ -821,7 +824,8 @@ int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t 
     if (cfg->add_position && (!pos_x || !pos_y)) return fail(DIRAL_ERR_ARG, "add_position needs pos_x and pos_y");
     if (cfg->add_velocity && !vel) return fail(DIRAL_ERR_ARG, "add_velocity needs vel");
     diral::HostJob job{};
-    job.actions = actions; job.counts = counts; job.rews = rews; job.obs = obs; job.pos_x = pos_x; job.pos_y = pos_y;
+    job.actions = actions; job.counts = counts; job.count_stride = cfg->B; job.rews = rews; job.rew_stride = sizeof(float);
+    job.rews_out = nullptr; job.obs = obs; job.pos_x = pos_x; job.pos_y = pos_y;
     job.vel = vel; job.episode = episode; job.epsilon = epsilon; job.out = out;
     diral::HostLayout lay = host_layout(*cfg);
     lay.nt_stores = threads < 0;             // (bench knob: a negative thread count selects non-temporal stores)

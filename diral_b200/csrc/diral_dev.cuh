@@ -49,7 +49,9 @@ struct Params {
     int32_t *tab_seq, *tab_lu; double *tab_x;
     int32_t *lat;
     float *obs, *rews, *state;
-    uint8_t *vpd_counts;      // [E][N][B] raw VPD bin counts (compact host format, diral_step_host) or NULL
+    uint8_t *vpd_counts;      // compact host record per agent (diral_step_host) or NULL: B bin counts (one byte each, when
+                              // piggy), padded to 4 bytes, then the float32 reward; rec_stride bytes apart
+    int rec_stride;
     double *acc_reward; long long *acc_count;
     uint32_t *scratch;
     const double *trace; long long trace_len;

@@ -34,6 +34,13 @@ const float *vpd_quotients()
     return lut.data();
 }
 
+inline float rew_at(const HostJob &job, long long a)
+{
+    float r;
+    std::memcpy(&r, reinterpret_cast<const char *>(job.rews) + a * job.rew_stride, sizeof r);
+    return r;
+}
+
 void stream_out(float *dst, const float *src, long long n, bool nt)
 {
     // dst is 16-byte aligned whenever the caller's buffer is and the row range starts at a multiple of 4 agents
@@ -93,6 +100,7 @@ inline void expand_rows_vector_impl(const HostLayout &lay, const HostJob &job, l
     const __m128i one_bits = _mm_castps_si128(_mm_set1_ps(1.0f));
     for (long long a = a0; a < a1; ++a) {
         float *w = job.out + a * S;
+        if (job.rews_out) job.rews_out[a] = rew_at(job, a);
         if (lay.add_action) {
             int act = job.actions[a];
             act = act < 0 ? 0 : (act >= R ? R - 1 : act);
@@ -108,7 +116,7 @@ inline void expand_rows_vector_impl(const HostLayout &lay, const HostJob &job, l
             for (int r = 0; r < R; r += 4, w += 4) put4<NT>(w, _mm_castps_si128(_mm_loadu_ps(o + r)));
         }
         if (lay.piggy) {
-            const uint8_t *c = job.counts + a * B;
+            const uint8_t *c = job.counts + a * job.count_stride;
             __m128i acc = zero;
             __m128i c32[64];                     // B <= 256 bins
             for (int b = 0; b < B; b += 4) {
@@ -172,6 +180,7 @@ void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long l
         const long long b1 = b0 + rows_per_block < a1 ? b0 + rows_per_block : a1;
         float *w = stage;
         for (long long a = b0; a < b1; ++a) {
+            if (job.rews_out) job.rews_out[a] = rew_at(job, a);
             int act = job.actions[a];
             act = act < 0 ? 0 : (act >= R ? R - 1 : act);                     // the kernels clamp (and count) bad actions
             if (lay.add_action) {                                             // test_env.py:539-545
@@ -180,14 +189,14 @@ void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long l
             }
             if (lay.add_channel_obs) { std::memcpy(w, job.obs + a * R, sizeof(float) * (size_t)R); w += R; }   // :547-548
             if (lay.piggy) {                                                  // :554-562, network.py:495-505
-                const uint8_t *c = job.counts + a * B;
+                const uint8_t *c = job.counts + a * job.count_stride;
                 int m = 0;
                 for (int b = 0; b < B; ++b) m += c[b];
                 const float *q = lut + (m > 255 ? 255 : m) * 256;
                 for (int b = 0; b < B; ++b) w[b] = q[c[b]];
                 w += B;
             }
-            if (lay.add_reward) *w++ = job.rews[a];                           // :568-570
+            if (lay.add_reward) *w++ = rew_at(job, a);                           // :568-570
             if (lay.add_index) *w++ = (float)(a % N + 1);                     // :571-572
             if (lay.add_position) {                                           // :573-574, network.py:403-407
                 *w++ = (float)(job.pos_x[a] / lay.L);

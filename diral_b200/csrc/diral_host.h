@@ -20,8 +20,10 @@ struct HostLayout {                 // the State block (test_env.py:27-41) as th
 
 struct HostJob {                    // one call: per-agent inputs (index a = env * N + vehicle) and the output rows
     const int32_t *actions;         // [A]          what the caller sent (clamped to [0, R) like the kernels do)
-    const uint8_t *counts;          // [A][B]       VPD bin counts (piggy)
-    const float *rews;              // [A]
+    const uint8_t *counts;          // [A] x count_stride bytes: B VPD bin counts per agent (piggy)
+    const float *rews;              // [A] x rew_stride bytes: rewards
+    long long count_stride, rew_stride;
+    float *rews_out;                // [A] or NULL: rewards copied out densely (the caller's h_rews)
     const float *obs;               // [A][R]       (add_channel_obs)
     const double *pos_x, *pos_y;    // [A]          post-mobility x, y (add_position)
     const double *vel;              // [A]          (add_velocity)

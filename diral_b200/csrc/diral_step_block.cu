@@ -505,6 +505,7 @@ step_block_kernel(const Params p, const int SB)
                 s_rewd[tid] = rew;
             }
             p.rews[vbase + tid] = (float)rew;
+            if (p.vpd_counts) *reinterpret_cast<float *>(p.vpd_counts + (vbase + tid + 1) * p.rec_stride - 4) = (float)rew;
             s_rew[tid] = (float)rew;
             const double x_new = mobility_step(p, sx[tid], p.vel[vbase + tid], tid);
             if (p.mobility) p.pos_x[vbase + tid] = x_new;
@@ -624,7 +625,7 @@ step_block_kernel(const Params p, const int SB)
                             val = __fmaf_rn(__fmaf_rn(-q0, den, c), rcp, q0);
                         }
                         srow[o_vpd + b] = val;
-                        if (p.vpd_counts) p.vpd_counts[(vbase + u) * B + b] = (unsigned char)(have ? hist[b * T + u] : 0u);
+                        if (p.vpd_counts) p.vpd_counts[(vbase + u) * p.rec_stride + b] = (unsigned char)(have ? hist[b * T + u] : 0u);
                     }
                 if (lane < S - o_tail) {
                     float val = 0.0f; int k = lane;

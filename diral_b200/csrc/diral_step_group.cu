@@ -569,6 +569,7 @@ step_group_kernel(const Params p)
         }
     }
     if (act) p.rews[vbase + u] = (float)rew;
+    if (act && p.vpd_counts) *reinterpret_cast<float *>(p.vpd_counts + (vbase + u + 1) * p.rec_stride - 4) = (float)rew;
 
     // ---- F: state rows (TestEnv.obtain_state) in shared memory -----------------------------------
     // Row u sits at st[u*S .. u*S+S) exactly as in global memory, so the copy-out is a plain
@@ -598,7 +599,7 @@ step_group_kernel(const Params p)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) hv[i] = (have && b0 + i < B) ? hist[(b0 + i) * G + u] : 0u;
                 if (p.vpd_counts) {                  // compact host format: the counts themselves, one byte per bin
-                    unsigned char *cp = p.vpd_counts + (vbase + u) * B + b0;
+                    unsigned char *cp = p.vpd_counts + (vbase + u) * p.rec_stride + b0;
                     if ((B & 3) == 0) {
                         *reinterpret_cast<unsigned *>(cp) = hv[0] | (hv[1] << 8) | (hv[2] << 16) | (hv[3] << 24);
                         if (b0 + 4 < B) *reinterpret_cast<unsigned *>(cp + 4) = hv[4] | (hv[5] << 8) | (hv[6] << 16) | (hv[7] << 24);

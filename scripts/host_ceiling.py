@@ -109,8 +109,8 @@ def main():
     h_state = torch.empty((E_PER_GPU, N_UE, env.S), dtype=torch.float32).pin_memory()
     h_rews = torch.empty((E_PER_GPU, N_UE), dtype=torch.float32).pin_memory()
     out["step_host"].append(step_host(env, "full", 1, 4, h_act, h_state, h_rews))
-    for th in sorted({4, 8, 12, max(cpus - 3, 1), max(cpus - 2, 1), max(cpus - 1, 1)}):
-        for ch in (2, 4, 8):
+    for th in sorted({8, 12, max(cpus - 3, 1), max(cpus - 2, 1)}):
+        for ch in (2, 4, 8, 16):
             for nt in (0, 1):
                 out["step_host"].append(step_host(env, "compact", th, ch, h_act, h_state, h_rews, nt))
     print(json.dumps(out, indent=1))
