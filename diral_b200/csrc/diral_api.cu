@@ -60,7 +60,7 @@ struct Handle {
     // compact host format of diral_step_host (see diral_host.h)
     int host_format = 0;            // 0 = full rows over PCIe, 1 = compact record + host-side row assembly
     int host_threads = 0;           // 0 = pick from the CPUs this process may run on
-    int host_chunks = 4;
+    int host_chunks = 8;
     int host_nt = -1;               // output-row stores: 1 non-temporal, 0 ordinary, -1 by output size per thread
     diral::HostPool *pool = nullptr;
     uint8_t *d_counts = nullptr;    // [E][N][B] device

@@ -196,7 +196,8 @@ class TestEnv:
             import os
             cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             local = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1")), 1)
-            host_threads = max(min(cpus // local - 2, 32), 1)    # leave room for the caller and the CUDA runtime's threads
+            share = cpus // local
+            host_threads = max(min(share - (2 if share >= 8 else 1), 32), 1)   # room for the caller and the CUDA runtime's threads
         check(self.lib.diral_set_option(self._handle, b"host_threads", int(host_threads)))
         self.host_format = host_format if self.lib.diral_get_option(self._handle, b"compact_ok") else "full"
 
