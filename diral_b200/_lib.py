@@ -36,7 +36,7 @@ class DiralBuffers(C.Structure):
                 ("tab_seq", C.c_void_p), ("tab_lu", C.c_void_p), ("tab_x", C.c_void_p),
                 ("lat", C.c_void_p), ("obs", C.c_void_p), ("rews", C.c_void_p), ("state", C.c_void_p),
                 ("acc_reward", C.c_void_p), ("acc_count", C.c_void_p), ("scratch", C.c_void_p),
-                ("trace", C.c_void_p), ("trace_len", C.c_int64)]
+                ("trace", C.c_void_p), ("trace_len", C.c_int64), ("ring", C.c_void_p)]
 
 
 class DiralShaping(C.Structure):
@@ -81,6 +81,7 @@ SYMBOLS = {
     "diral_reset_topology": (C.c_int, [_P, _P, _P, _P, _U64, _P]),
     "diral_expand_state_host": (C.c_int, [C.POINTER(DiralCfg), _I64, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I32, _P]),
     "diral_host_trace": (C.c_int32, [_P, _P, _I32]),
+    "diral_materialize_x": (C.c_int, [_P, _P, _P]),
     "diral_ring_put": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
 }
 

@@ -38,7 +38,7 @@ int fail(int code, const char *fmt, ...)
             return fail(DIRAL_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
     } while (0)
 
-enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2 };
+enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2, VARIANT_BLOCK_V1 = 3 };
 constexpr int MAX_HOST_CHUNKS = 32;
 
 struct Handle {
@@ -47,6 +47,7 @@ struct Handle {
     diral::Params base{};
     bool bound = false;
     bool group_ok = false, block_ok = false;   // which slot kernels this configuration's shared-memory carve-up fits
+    bool row_ok = false;            // the row-layout kernel (diral_step_row.cu) takes this configuration
     int device = 0;
     int variant = VARIANT_AUTO;
     int force_track_lat = 0;
@@ -113,9 +114,15 @@ int check_cfg(const diral_cfg *c)
 
 bool use_group(const Handle *h)
 {
-    if (h->variant == VARIANT_BLOCK) return false;
+    if (h->variant == VARIANT_BLOCK || h->variant == VARIANT_BLOCK_V1) return false;
     if (h->variant == VARIANT_AUTO && !h->block_ok) return true;
     return h->group_ok;
+}
+
+// the row-layout kernel is the one-CTA-per-env kernel of choice wherever it applies; VARIANT_BLOCK_V1 pins round 1's
+bool use_row(const Handle *h)
+{
+    return h->row_ok && !use_group(h) && h->variant != VARIANT_BLOCK_V1;
 }
 
 bool fused_state_ok(const diral_cfg &c)
@@ -162,10 +169,35 @@ void fill_base(Handle *h)
     p.edges = h->d_edges;
 }
 
+// table layout of the kernel that will run (fixed once buffers are bound)
+void set_layout(Handle *h)
+{
+    diral::Params &p = h->base;
+    const bool row = use_row(h);
+    p.layout = row ? 1 : 0;
+    p.T = row ? diral::step_row_stride(h->cfg.N) : h->cfg.N;
+    p.H = row ? diral::step_row_ring_depth(h->cfg.N) : 0;
+    p.spill_half = row ? (long long)h->cfg.E * h->cfg.N * p.T : 0;
+}
+
+size_t handle_scratch_bytes(const Handle *h)
+{
+    if (!h->cfg.add_piggy || use_group(h)) return 0;
+    if (use_row(h)) return diral::step_row_scratch_bytes(h->cfg.E, h->cfg.N);
+    return diral_scratch_bytes(&h->cfg);
+}
+
+cudaError_t launch_slot(const Handle *h, const diral::Params &p, cudaStream_t s)
+{
+    if (use_group(h)) return diral::launch_step_group(p, s);
+    return use_row(h) ? diral::launch_step_row(p, s) : diral::launch_step_block(p, s);
+}
+
 void bind_params(Handle *h)
 {
     diral::Params &p = h->base;
     const diral_buffers &b = h->bufs;
+    p.ring = b.ring;
     p.pos_x = b.pos_x; p.pos_y = b.pos_y; p.vel = b.vel;
     p.tab_seq = b.tab_seq; p.tab_lu = b.tab_lu; p.tab_x = b.tab_x; p.lat = b.lat;
     p.obs = b.obs; p.rews = b.rews; p.state = b.state;
@@ -190,6 +222,19 @@ void np_linspace(double start, double stop, int num, double *y)
 
 Handle *as_handle(void *h) { return static_cast<Handle *>(h); }
 
+// fresh neighbour tables (vehicle.py:24-33) in whichever layout the handle uses
+int zero_tables(Handle *h, cudaStream_t s)
+{
+    const diral_cfg &c = h->cfg;
+    const diral::Params &p = h->base;
+    const size_t ent = (size_t)c.E * c.N * (p.layout ? p.T : c.N);
+    if (h->bufs.tab_seq) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_seq, 0, ent * 4, s));
+    if (h->bufs.tab_lu) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_lu, 0, ent * 4, s));
+    if (h->bufs.tab_x) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_x, 0, ent * 8 * (p.layout ? 2 : 1), s));
+    if (p.layout && h->bufs.ring) DIRAL_CUDA(cudaMemsetAsync(h->bufs.ring, 0, (size_t)c.E * p.H * p.T * 8, s));
+    return DIRAL_OK;
+}
+
 int require_bound(Handle *h)
 {
     if (!h) return fail(DIRAL_ERR_ARG, "handle is NULL");
@@ -201,17 +246,18 @@ int require_bound(Handle *h)
 diral::Params env_range(const diral::Params &p, long long e0, long long n)
 {
     diral::Params q = p;
-    const long long N = p.N, NN = N * N;
+    const long long N = p.N, NN = N * (p.layout ? p.T : N);
     q.E = n; q.env0 = p.env0 + e0;
     if (q.actions) q.actions += e0 * N;
     if (q.actions_out) q.actions_out += e0 * N;
     q.pos_x += e0 * N; q.pos_y += e0 * N; q.vel += e0 * N;
     if (q.tab_seq) { q.tab_seq += e0 * NN; q.tab_lu += e0 * NN; q.tab_x += e0 * NN; }
-    if (q.lat) q.lat += e0 * NN;
+    if (q.ring) q.ring += e0 * (long long)p.H * p.T;
+    if (q.lat) q.lat += e0 * N * N;
     q.obs += e0 * N * p.R; q.rews += e0 * N; q.state += e0 * N * p.S;
     if (q.vpd_counts) q.vpd_counts += e0 * N * p.rec_stride;
     q.acc_reward += e0; q.acc_count += e0 * diral::ACC_COUNTS;
-    if (q.scratch) q.scratch += e0 * (long long)diral::step_block_scratch_words_per_env(p.N);
+    if (q.scratch) q.scratch += e0 * (p.layout ? (long long)p.T * p.T : (long long)diral::step_block_scratch_words_per_env(p.N));
     return q;
 }
 
@@ -307,7 +353,7 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         DIRAL_CUDA(cudaStreamWaitEvent(ps, h->pipe_ev[2], 0));
         DIRAL_CUDA(cudaMemcpyAsync(h->d_actions + a0, h_actions + a0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ps));
         const diral::Params q = env_range(p, e0, n / N);
-        DIRAL_CUDA(group ? diral::launch_step_group(q, ps) : diral::launch_step_block(q, ps));
+        DIRAL_CUDA(launch_slot(h, q, ps));
         h->launches += 1;
         DIRAL_CUDA(cudaMemcpyAsync(h->h_counts + a0 * rec, h->d_counts + a0 * rec, (size_t)(n * rec), cudaMemcpyDeviceToHost, ps));
         if (h_obs || want_obs)
@@ -399,6 +445,9 @@ int diral_create(const diral_cfg *cfg, void **handle)
     else h->variant = VARIANT_BLOCK;
     if (err == cudaSuccess && block_fits) err = diral::prepare_step_block(h->base);
     h->group_ok = group_fits; h->block_ok = block_fits;
+    h->row_ok = diral::step_row_supported(h->base) && diral::step_row_smem_bytes(q) <= (size_t)prop.sharedMemPerBlockOptin;
+    if (err == cudaSuccess && h->row_ok) err = diral::prepare_step_row(h->base);
+    set_layout(h);
     if (err != cudaSuccess) { cudaFree(h->d_edges); delete h; return fail(DIRAL_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(err)); }
     *handle = h;
     return DIRAL_OK;
@@ -429,15 +478,17 @@ int diral_set_option(void *handle, const char *name, int64_t value)
     Handle *h = as_handle(handle);
     if (!h || !name) return fail(DIRAL_ERR_ARG, "handle/name is NULL");
     if (!strcmp(name, "variant")) {
-        if (value < 0 || value > 2) return fail(DIRAL_ERR_ARG, "variant must be 0 (auto), 1 (group) or 2 (block)");
+        if (value < 0 || value > 3) return fail(DIRAL_ERR_ARG, "variant must be 0 (auto), 1 (group), 2 (block) or 3 (round-1 block kernel)");
+        if (h->bound) return fail(DIRAL_ERR_ARG, "the kernel variant fixes the table layout: choose it before diral_bind()");
         if (value == VARIANT_GROUP && h->cfg.N > diral::GROUP_MAX_N)
             return fail(DIRAL_ERR_ARG, "the group kernel handles num_users <= %d", diral::GROUP_MAX_N);
         if (value == VARIANT_GROUP && !h->group_ok)
             return fail(DIRAL_ERR_UNSUPPORTED, "the group kernel's shared-memory carve-up does not fit at R=%d", h->cfg.R);
-        if (value == VARIANT_BLOCK && !h->block_ok)
+        if ((value == VARIANT_BLOCK && !h->block_ok && !h->row_ok) || (value == VARIANT_BLOCK_V1 && !h->block_ok))
             return fail(DIRAL_ERR_UNSUPPORTED, "the one-CTA-per-env kernel's shared-memory carve-up does not fit this configuration");
         if (value == VARIANT_AUTO && !h->group_ok) value = VARIANT_BLOCK;
         h->variant = (int)value;
+        set_layout(h);
         return DIRAL_OK;
     }
     if (!strcmp(name, "track_lat")) { h->force_track_lat = value != 0; return DIRAL_OK; }
@@ -477,6 +528,11 @@ int64_t diral_get_option(void *handle, const char *name)
     Handle *h = as_handle(handle);
     if (!h || !name) return -1;
     if (!strcmp(name, "variant")) return use_group(h) ? VARIANT_GROUP : VARIANT_BLOCK;
+    if (!strcmp(name, "kernel")) return use_group(h) ? 1 : (use_row(h) ? 3 : 2);      // 1 lane-group, 2 round-1 block, 3 row layout
+    if (!strcmp(name, "layout")) return h->base.layout;
+    if (!strcmp(name, "row_stride")) return h->base.T;
+    if (!strcmp(name, "ring_depth")) return h->base.H;
+    if (!strcmp(name, "scratch_bytes")) return (int64_t)handle_scratch_bytes(h);
     if (!strcmp(name, "track_lat")) return h->force_track_lat;
     if (!strcmp(name, "host_format")) return h->host_format;
     if (!strcmp(name, "host_threads")) return h->pool ? h->pool->threads() : h->host_threads;
@@ -496,8 +552,9 @@ int diral_bind(void *handle, const diral_buffers *b)
         return fail(DIRAL_ERR_ARG, "pos_x/pos_y/vel/obs/rews/state/acc_* must all be bound");
     if (h->cfg.add_piggy && (!b->tab_seq || !b->tab_lu || !b->tab_x))
         return fail(DIRAL_ERR_ARG, "add_positional_dist_piggy needs tab_seq/tab_lu/tab_x");
-    if (diral_scratch_bytes(&h->cfg) > 0 && !b->scratch)
-        return fail(DIRAL_ERR_ARG, "this configuration needs %zu B of scratch", diral_scratch_bytes(&h->cfg));
+    if (handle_scratch_bytes(h) > 0 && !b->scratch)
+        return fail(DIRAL_ERR_ARG, "this configuration needs %zu B of scratch", handle_scratch_bytes(h));
+    if (h->base.layout && !b->ring) return fail(DIRAL_ERR_ARG, "the row layout needs the position ring (diral_buffers.ring)");
     if (b->trace && b->trace_len < 1) return fail(DIRAL_ERR_ARG, "trace_len must be >= 1 when a trace is bound");
     h->bufs = *b;
     bind_params(h);
@@ -514,9 +571,7 @@ int diral_reset(void *handle, const double *x0, const double *y0, const double *
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const diral_cfg &c = h->cfg;
     const size_t EN = (size_t)c.E * c.N, ENN = EN * c.N;
-    if (h->bufs.tab_seq) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_seq, 0, ENN * 4, s));     // vehicle.py:24-33
-    if (h->bufs.tab_lu) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_lu, 0, ENN * 4, s));
-    if (h->bufs.tab_x) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_x, 0, ENN * 8, s));
+    if (int rc = zero_tables(h, s)) return rc;
     if (h->bufs.lat) DIRAL_CUDA(cudaMemsetAsync(h->bufs.lat, 0xFF, ENN * 4, s));           // network.py:39-42
     DIRAL_CUDA(cudaMemsetAsync(h->bufs.acc_reward, 0, (size_t)c.E * 8, s));
     DIRAL_CUDA(cudaMemsetAsync(h->bufs.acc_count, 0, (size_t)c.E * 8 * diral::ACC_COUNTS, s));
@@ -535,11 +590,7 @@ int diral_reset_topology(void *handle, const double *x0, const double *y0, const
     if (x0 && (!y0 || !v0)) return fail(DIRAL_ERR_ARG, "x0, y0 and v0 must be given together");
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const diral_cfg &c = h->cfg;
-    const size_t ENN = (size_t)c.E * c.N * c.N;
-    if (h->bufs.tab_seq) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_seq, 0, ENN * 4, s));     // vehicle.py:24-33
-    if (h->bufs.tab_lu) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_lu, 0, ENN * 4, s));
-    if (h->bufs.tab_x) DIRAL_CUDA(cudaMemsetAsync(h->bufs.tab_x, 0, ENN * 8, s));
+    if (int rc = zero_tables(h, s)) return rc;
     diral::Params p = h->base;
     p.seed = seed;
     DIRAL_CUDA(diral::launch_reset(p, x0, y0, v0, s));
@@ -569,7 +620,7 @@ int diral_obtain_state(void *handle, const float *obs, const int32_t *actions, c
     if (!obs || !actions || !rews || !out) return fail(DIRAL_ERR_ARG, "obs/actions/rews/out must not be NULL");
     DeviceGuard g(h->device);
     diral::Params p = h->base;
-    p.episode = episode; p.epsilon = epsilon;
+    p.episode = episode; p.epsilon = epsilon; p.tick = (int)h->ticks;
     DIRAL_CUDA(diral::launch_obtain_state(p, obs, actions, rews, out, static_cast<cudaStream_t>(stream)));
     h->launches += 1;
     return DIRAL_OK;
@@ -600,7 +651,7 @@ int diral_step(void *handle, int mode, const int32_t *actions, int64_t timestep,
         if (int rc = ensure_actions_staging(h)) return rc;
         p.actions_out = h->d_actions;
     }
-    DIRAL_CUDA(group ? diral::launch_step_group(p, s) : diral::launch_step_block(p, s));
+    DIRAL_CUDA(launch_slot(h, p, s));
     h->launches += 1;
     if (h->cfg.add_piggy) h->ticks += 1;
     if (build_state && !fused) {
@@ -793,7 +844,7 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
         DIRAL_CUDA(cudaMemcpyAsync(h->d_actions + e0 * N, h_actions + e0 * N, (size_t)(n * N) * sizeof(int32_t),
                                    cudaMemcpyHostToDevice, ps));
         const diral::Params q = env_range(p, e0, n);
-        DIRAL_CUDA(group ? diral::launch_step_group(q, ps) : diral::launch_step_block(q, ps));
+        DIRAL_CUDA(launch_slot(h, q, ps));
         h->launches += 1;
         DIRAL_CUDA(cudaMemcpyAsync(h_state + e0 * N * S, h->bufs.state + e0 * N * S, (size_t)(n * N * S) * sizeof(float),
                                    cudaMemcpyDeviceToHost, ps));
@@ -852,6 +903,20 @@ int32_t diral_host_trace(void *handle, double *out_us, int32_t n)
     const int m = std::min<int>(n, h->trace_n);
     for (int i = 0; i < m; ++i) out_us[i] = h->trace_us[i];
     return m;
+}
+
+int diral_materialize_x(void *handle, double *out, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!out) return fail(DIRAL_ERR_ARG, "out is NULL");
+    if (!h->cfg.add_piggy) return fail(DIRAL_ERR_ARG, "this configuration keeps no neighbour tables");
+    DeviceGuard g(h->device);
+    diral::Params p = h->base;
+    p.tick = (int)h->ticks;
+    DIRAL_CUDA(diral::launch_materialize_x(p, out, static_cast<cudaStream_t>(stream)));
+    h->launches += 1;
+    return DIRAL_OK;
 }
 
 int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes, const void *src, void *stream)

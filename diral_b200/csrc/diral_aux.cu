@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) obtain_state_kernel(const Params p, const
     const int N = p.N, R = p.R, B = p.B;
     const long long e = gid / N;
     const int u = (int)(gid - e * N);
-    const long long vbase = e * N, tbase = e * (long long)N * N;
+    const long long vbase = e * N;
     const double xu = p.pos_x[gid], yu = p.pos_y[gid];
     float *row = out + gid * p.S;
     int k = 0;
@@ -64,17 +64,19 @@ __global__ void __launch_bounds__(128) obtain_state_kernel(const Params p, const
         for (int q = 0; q < m; ++q) row[k++] = (float)__ddiv_rn(buf[q], max_dist);
     }
     if (p.piggy) {
-        const int32_t *seqp = p.tab_seq + tbase, *lup = p.tab_lu + tbase;
-        const double *xp = p.tab_x + tbase;
+        // (i = this vehicle, j = subject) through the layout-independent accessors of diral_dev.cuh
+        auto seq_at = [&](int j) { return p.tab_seq[tab_index(p, e, u, j)]; };
+        auto lu_at = [&](int j) { return p.tab_lu[tab_index(p, e, u, j)]; };
+        auto x_at = [&](int j) { return tab_xpos(p, e, u, j, p.tab_seq[tab_index(p, e, u, j)]); };
         if (p.pos_dist_type == 2 || !p.vpd_enabled) {        // network.py:473-513
             unsigned short hist[HIST_MAX_B];
             for (int b = 0; b < B; ++b) hist[b] = 0;
             int m = 0;
             if (p.vpd_enabled) {
                 for (int j = 0; j < N; ++j) {
-                    if (j == u || lup[j * N + u] >= p.age_threshold) continue;
-                    const double x1 = xp[j * N + u];
-                    const double y1 = seqp[j * N + u] > 0 ? p.pos_y[vbase + j] : 0.0;
+                    if (j == u || lu_at(j) >= p.age_threshold) continue;
+                    const double x1 = x_at(j);
+                    const double y1 = seq_at(j) > 0 ? p.pos_y[vbase + j] : 0.0;
                     const double d = dist2d(x1, y1, xu, yu);
                     if (d < p.W) {
                         const double s = (__dsub_rn(x1, xu) > 0.0) ? d : -d;
@@ -88,9 +90,9 @@ __global__ void __launch_bounds__(128) obtain_state_kernel(const Params p, const
         } else if (SORTED) {                                  // network.py:432-471 (type 1)
             int m = 0;
             for (int j = 0; j < N; ++j) {
-                if (j == u || lup[j * N + u] >= p.age_threshold) continue;
-                const double x1 = xp[j * N + u];
-                const double y1 = seqp[j * N + u] > 0 ? p.pos_y[vbase + j] : 0.0;
+                if (j == u || lu_at(j) >= p.age_threshold) continue;
+                const double x1 = x_at(j);
+                const double y1 = seq_at(j) > 0 ? p.pos_y[vbase + j] : 0.0;
                 const double d = dist2d(x1, y1, xu, yu);
                 buf[m++] = (__dsub_rn(x1, xu) > 0.0) ? d : -d;
             }
@@ -230,6 +232,18 @@ __global__ void __launch_bounds__(1024) episode_metrics_kernel(const Params p, d
     for (int i = tid; i < IA_BINS; i += T) out[10 + i] = (double)h[i];
 }
 
+// xpos of every table entry in the reference's own indexing, out[e][i][j] = vehicles[i].pos_of_neighbors[j]["xpos"]
+// (vehicle.py:30): a transpose for the subject-major layout, ring / spill look-ups for the row layout
+__global__ void materialize_x_kernel(const Params p, double *out)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long NN = (long long)p.N * p.N;
+    if (gid >= p.E * NN) return;
+    const long long e = gid / NN;
+    const int i = (int)((gid - e * NN) / p.N), j = (int)(gid - e * NN - (long long)i * p.N);
+    out[gid] = tab_xpos(p, e, i, j, p.tab_seq[tab_index(p, e, i, j)]);
+}
+
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -269,6 +283,12 @@ cudaError_t launch_update_velocity(const Params &p, double *vel, const int8_t *d
 cudaError_t launch_information_age(const Params &p, int32_t *out, cudaStream_t stream)
 {
     information_age_kernel<<<(unsigned)p.E, 128, 0, stream>>>(p, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_materialize_x(const Params &p, double *out, cudaStream_t stream)
+{
+    materialize_x_kernel<<<blocks_for(p.E * (long long)p.N * p.N, 256), 256, 0, stream>>>(p, out);
     return cudaGetLastError();
 }
 

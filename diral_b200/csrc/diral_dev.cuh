@@ -21,6 +21,8 @@ constexpr int ACC_COUNTS = 4;         // acc_count columns: received, in-range p
 // RNG stream tags (specification shared with oracle/diral_oracle.c, not code)
 constexpr uint32_t STREAM_ACTIONS = 1, STREAM_TOPOLOGY = 2, STREAM_VELOCITY = 3;
 
+struct Params;
+
 struct Params {
     // sizes
     long long E, env0;
@@ -56,7 +58,27 @@ struct Params {
     uint32_t *scratch;
     const double *trace; long long trace_len;
     const double *edges;      // [B+1] numpy.linspace(-W, W, B+1), computed on the host in float64
+    // table layout: 0 = SUBJECT-major [E][N][N] with a dense xpos table (lane-group kernel, round-1 block kernel);
+    // 1 = ROW layout (diral_step_row.cu): tab_seq / tab_lu OBSERVER-major [E][N][T], positions in ring [E][H][T] by
+    // tick mod H, tab_x = two spill halves [2][E][N][T] (spill_half elements apart) for entries older than H ticks
+    int layout, T, H;
+    double *ring;
+    long long spill_half;
 };
+
+// ---- table accessors that work for both layouts (standalone kernels) -------------------------------------------
+__device__ __forceinline__ long long tab_index(const Params &p, long long e, int i /*observer*/, int j /*subject*/)
+{
+    return p.layout ? (e * p.N + i) * (long long)p.T + j : (e * p.N + j) * (long long)p.N + i;
+}
+// xpos of vehicle i's entry about j (sequence number sn) as of the last completed slot (p.tick)
+__device__ __forceinline__ double tab_xpos(const Params &p, long long e, int i, int j, int sn)
+{
+    if (!p.layout) return p.tab_x[tab_index(p, e, i, j)];
+    if (sn <= 0) return 0.0;
+    if (p.tick - sn < p.H) return p.ring[(e * p.H + (sn & (p.H - 1))) * (long long)p.T + j];
+    return p.tab_x[((p.tick & 1) ? p.spill_half : 0) + tab_index(p, e, i, j)];
+}
 
 // per-slot caller epilogue (main_test.py:150-206): device pointers and switches of one call
 struct ShapingArgs {

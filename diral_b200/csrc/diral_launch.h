@@ -25,6 +25,15 @@ size_t step_block_scratch_words_per_env(int N);
 cudaError_t prepare_step_block(const Params &p);
 cudaError_t launch_step_block(const Params &p, cudaStream_t stream);
 
+// 32 < N <= 256, ROW layout: observer-major tables, positions in a ring, receiver-centric merges (diral_step_row.cu)
+bool step_row_supported(const Params &p);
+int step_row_stride(int N);             // T: padded row stride of the tables
+int step_row_ring_depth(int N);         // H: ticks the position ring holds
+size_t step_row_smem_bytes(const Params &p);
+size_t step_row_scratch_bytes(long long E, int N);
+cudaError_t prepare_step_row(const Params &p);
+cudaError_t launch_step_row(const Params &p, cudaStream_t stream);
+
 // standalone kernels (diral_aux.cu)
 cudaError_t launch_obtain_state(const Params &p, const float *obs, const int32_t *actions, const float *rews,
                                 float *out, cudaStream_t stream);
@@ -34,6 +43,7 @@ cudaError_t launch_update_velocity(const Params &p, double *vel, const int8_t *d
                                    cudaStream_t stream);
 cudaError_t launch_information_age(const Params &p, int32_t *out, cudaStream_t stream);
 cudaError_t launch_episode_metrics(const Params &p, double *out110, cudaStream_t stream);
+cudaError_t launch_materialize_x(const Params &p, double *out, cudaStream_t stream);
 cudaError_t launch_shape_rewards(const Params &p, const ShapingArgs &s, cudaStream_t stream);
 cudaError_t launch_ring_gather(const void *ring, long long capacity, long long agents, long long width, int elem_bytes,
                                const long long *start, int batch, int step, void *out, cudaStream_t stream);

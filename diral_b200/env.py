@@ -127,7 +127,12 @@ class TestEnv:
         with torch.cuda.device(self.device):
             check(self.lib.diral_create(C.byref(self.cfg), C.byref(self._handle)))
         if variant != "auto":
-            check(self.lib.diral_set_option(self._handle, b"variant", {"group": 1, "block": 2}[variant]))
+            check(self.lib.diral_set_option(self._handle, b"variant", {"group": 1, "block": 2, "block_v1": 3}[variant]))
+        # which kernel runs and how it wants its tables laid out (include/diral_env.h, "Table layouts")
+        self.kernel = {1: "group", 2: "block_v1", 3: "row"}[int(self.lib.diral_get_option(self._handle, b"kernel"))]
+        self.layout = int(self.lib.diral_get_option(self._handle, b"layout"))
+        self.T = int(self.lib.diral_get_option(self._handle, b"row_stride"))
+        self.H = int(self.lib.diral_get_option(self._handle, b"ring_depth"))
         self.set_host_format(host_format, host_threads)
         self._alloc()
         self._trace = None
@@ -143,7 +148,16 @@ class TestEnv:
         self.pos_x = torch.zeros((E, N), dtype=f64, device=dev)
         self.pos_y = torch.zeros((E, N), dtype=f64, device=dev)
         self.vel = torch.zeros((E, N), dtype=f64, device=dev)
-        if self.cfg.add_piggy:
+        self._ring = None
+        if self.cfg.add_piggy and self.layout == 1:
+            # row layout: _tab_*[e, i, j] is vehicle i's entry about vehicle j (rows padded to T columns); positions
+            # live in _ring[e, tick % H, j], entries older than H ticks in the two spill halves of _tab_x
+            T = self.T
+            self._tab_seq = torch.zeros((E, N, T), dtype=i32, device=dev)
+            self._tab_lu = torch.zeros((E, N, T), dtype=i32, device=dev)
+            self._tab_x = torch.zeros((2, E, N, T), dtype=f64, device=dev)
+            self._ring = torch.zeros((E, self.H, T), dtype=f64, device=dev)
+        elif self.cfg.add_piggy:
             # subject-major storage: _tab_*[e, j, i] is vehicle i's entry about vehicle j
             self._tab_seq = torch.zeros((E, N, N), dtype=i32, device=dev)
             self._tab_lu = torch.zeros((E, N, N), dtype=i32, device=dev)
@@ -156,7 +170,7 @@ class TestEnv:
         self._state = torch.zeros((E, N, S), dtype=f32, device=dev)
         self._acc_reward = torch.zeros((E,), dtype=f64, device=dev)
         self._acc_count = torch.zeros((E, 4), dtype=torch.int64, device=dev)
-        nscratch = int(self.lib.diral_scratch_bytes(C.byref(self.cfg)))
+        nscratch = int(self.lib.diral_get_option(self._handle, b"scratch_bytes"))
         self._scratch = torch.zeros((nscratch // 4,), dtype=i32, device=dev) if nscratch else None
         self._metrics = torch.zeros((METRIC_LEN,), dtype=f64, device=dev)
         self._ia = torch.zeros((E, IA_BINS), dtype=i32, device=dev)
@@ -171,6 +185,7 @@ class TestEnv:
         b.acc_reward, b.acc_count, b.scratch = ptr(self._acc_reward), ptr(self._acc_count), ptr(self._scratch)
         b.trace = ptr(self._trace)
         b.trace_len = 0 if self._trace is None else int(self._trace.shape[0])
+        b.ring = ptr(self._ring)
         check(self.lib.diral_bind(self._handle, C.byref(b)))
 
     def close(self):
@@ -428,17 +443,24 @@ class TestEnv:
     def tab_seq(self):
         """``[E, i, j]`` = vehicles[i].pos_of_neighbors[j]["seq_number"] (vehicle.py:32)."""
         self._need_tables()
-        return self._tab_seq.transpose(1, 2)
+        return self._tab_seq[:, :, :self.N] if self.layout == 1 else self._tab_seq.transpose(1, 2)
 
     @property
     def tab_lu(self):
         self._need_tables()
-        return self._tab_lu.transpose(1, 2)
+        return self._tab_lu[:, :, :self.N] if self.layout == 1 else self._tab_lu.transpose(1, 2)
 
     @property
     def tab_x(self):
+        """``[E, i, j]`` = vehicles[i].pos_of_neighbors[j]["xpos"] (vehicle.py:30).  The row layout keeps positions in a
+        ring by tick, so the table is rebuilt on demand (diral_materialize_x)."""
         self._need_tables()
-        return self._tab_x.transpose(1, 2)
+        if self.layout == 0:
+            return self._tab_x.transpose(1, 2)
+        out = torch.empty((self.E, self.N, self.N), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.diral_materialize_x(self._handle, out.data_ptr(), self._stream()))
+        return out
 
     @property
     def tab_y(self):
@@ -449,7 +471,7 @@ class TestEnv:
                            torch.zeros((), dtype=torch.float64, device=self.device))
 
     # ------------------------------------------------------------------ checkpoint
-    _STATE_TENSORS = ("pos_x", "pos_y", "vel", "lat", "_tab_seq", "_tab_lu", "_tab_x", "_acc_reward", "_acc_count",
+    _STATE_TENSORS = ("pos_x", "pos_y", "vel", "lat", "_tab_seq", "_tab_lu", "_tab_x", "_ring", "_acc_reward", "_acc_count",
                       "_obs", "_rews", "_state")
 
     def state_dict(self):

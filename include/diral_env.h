@@ -83,7 +83,19 @@ typedef struct diral_buffers {
     uint32_t *scratch;         /* [diral_scratch_bytes/4] work space (may be NULL if that is 0) */
     const double *trace;       /* [trace_len][N] Network.x_positions (network.py:171-178) or NULL */
     int64_t trace_len;
+    double  *ring;             /* ROW layout only (diral_get_option "layout" == 1, see below): [E][H][T] position of
+                                  every vehicle at tick mod H; NULL otherwise                                        */
 } diral_buffers;
+
+/* Table layouts.  diral_get_option(handle, "layout") says which one the handle's kernel uses; it is fixed by the
+ * configuration and the "variant" option, so query it after diral_create / diral_set_option and before allocating.
+ *   0  SUBJECT-major, dense xpos (lane-group kernel N <= 32, round-1 one-CTA-per-env kernel): tab_seq / tab_lu / tab_x
+ *      are [E][N][N] with tab_*[e][j][i] = vehicle i's belief about vehicle j.
+ *   1  ROW layout (diral_step_row.cu, 32 < N <= 256): tab_seq / tab_lu are OBSERVER-major [E][N][T], T =
+ *      diral_get_option("row_stride") (N rounded up to a multiple of 64; columns >= N are padding).  xpos is not stored
+ *      per entry: an entry's position is pos_x[subject] at the tick that produced its sequence number, kept in
+ *      ring [E][H][T] (H = "ring_depth"); entries older than H ticks live in tab_x, here two spill halves
+ *      [2][E][N][T] used alternately.  diral_materialize_x rebuilds the reference's xpos table from either layout. */
 
 /* Bytes of device memory behind diral_buffers for this configuration (tables + outputs). */
 size_t diral_state_bytes(const diral_cfg *cfg);
@@ -234,16 +246,23 @@ int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t 
  * Returns the number of values written (<= n).  Measurement aid: says what bounds the end-to-end slot. */
 int32_t diral_host_trace(void *handle, double *out_us, int32_t n);
 
+/* vehicles[i].pos_of_neighbors[j]["xpos"] (vehicle.py:30) for every entry, out [E][N][N] float64 (device), indexed
+ * [e][i][j] like the reference, from whichever layout the handle uses. */
+int diral_materialize_x(void *handle, double *out, void *stream);
+
 /* One slot of a device-resident replay ring (Memory.add, utils/memory.py:169-175): ring[slot] = src, row_bytes
  * bytes device to device on `stream`. */
 int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes, const void *src, void *stream);
 
-/* Options.  Test/bench knobs: "variant" = 0 auto | 1 lane-group kernel (N <= 32) | 2 one-CTA-per-env kernel;
+/* Options.  Test/bench knobs: "variant" = 0 auto | 1 lane-group kernel (N <= 32) | 2 one-CTA-per-env kernel (the
+ * row-layout kernel where it applies, else round 1's) | 3 round 1's one-CTA-per-env kernel; set before diral_bind;
  * "track_lat" = 1 keeps last_arrival_time bookkeeping on even before the first my_step_ch call.
  * diral_step_host: "host_format" (0 full rows | 1 compact), "host_threads", "host_chunks" (env chunks pipelined per
  * call).  Checkpoint restore: "ticks" (table ticks since the reset = every vehicle's own sequence number) and
  * "lat_live" (a my_step_ch has stamped last_arrival_time); diral_get_option reads any of them back (-1: unknown),
- * plus "compact_ok" (1 when this State block has a compact host format). */
+ * plus "compact_ok" (1 when this State block has a compact host format), "kernel" (1 lane-group, 2 round-1
+ * one-CTA-per-env, 3 row layout), "layout", "row_stride", "ring_depth" and "scratch_bytes" (what `scratch` must hold
+ * for the handle's kernel). */
 int diral_set_option(void *handle, const char *name, int64_t value);
 int64_t diral_get_option(void *handle, const char *name);
 

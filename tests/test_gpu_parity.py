@@ -36,7 +36,9 @@ def _close32(got, ref64, what, t, exact=False):
 
 
 def _variants(n):
-    return ["group", "block"] if n <= 32 else ["block"]
+    # "block" = the one-CTA-per-env family: the row-layout kernel where it applies (32 < N <= 256, fused State), else
+    # round 1's kernel, which "block_v1" pins
+    return ["group", "block"] if n <= 32 else ["block", "block_v1"]
 
 
 def _cases():
@@ -365,8 +367,9 @@ def test_long_run_with_stale_entries():
     assert stale.any(), "the scenario must contain entries older than the packed key range"
 
 
+@pytest.mark.parametrize("variant", ["block", "block_v1"])
 @pytest.mark.parametrize("n,r,length,T,packed_range", [(40, 6, 12000, 1100, 1023), (140, 8, 40000, 300, 255)])
-def test_block_kernel_stale_entries_take_the_32_bit_keys(n, r, length, T, packed_range):
+def test_block_kernel_stale_entries_take_the_32_bit_keys(n, r, length, T, packed_range, variant):
     """The one-CTA-per-env kernel packs keys into 16 bits while every entry is within 2^(16 - log2 N) - 1 slots of
     the newest one; on a sparse highway older entries appear and those environments fall back to 32-bit keys
     (shared memory up to 128 vehicles, the L2 scratch slice beyond).  Integer state bit-exact throughout."""
@@ -376,7 +379,7 @@ def test_block_kernel_stale_entries_take_the_32_bit_keys(n, r, length, T, packed
     E, seed = 3, 33
     orc = COracle(num_envs=E, **kw)
     orc.reset_philox(seed)
-    env = _env(E, variant="block", seed=seed, **kw)
+    env = _env(E, variant=variant, seed=seed, **kw)
     for t in range(T):
         a = orc.philox_actions(seed, t)
         o_ref, r_ref = orc.step("my_step", a, t)
