@@ -46,7 +46,7 @@ __host__ __device__ constexpr size_t align16r(size_t x) { return (x + 15) & ~(si
 // Shared-memory carve-up (bytes) of the T-vehicle instantiation; the host computes the same numbers.
 struct RowSmem {
     size_t off_sx, off_sy, off_sxn, off_rewd, off_sa, off_aux, off_rew, off_recv, off_flag, off_order, off_base, off_txm, off_inr,
-        off_own, off_rmask, off_cmask, off_src, off_keys, off_ring, off_whist, off_edges, off_misc, bytes;
+        off_rmask, off_cmask, off_any, off_src, off_keys, off_ring, off_whist, off_edges, off_misc, bytes;
     __host__ __device__ RowSmem(int T, int R, int B, int H, int nwarps)
     {
         const int NW = T / 32, NWP = NW | 1, RW = (R + 31) / 32;
@@ -64,13 +64,13 @@ struct RowSmem {
         off_base = o;  o += align16r(4 * (size_t)(R + 1));
         off_txm = o;   o += align16r(4 * (size_t)R * NWP);
         off_inr = o;   o += align16r(4 * (size_t)T * NWP);
-        off_own = o;   o += align16r(4 * (size_t)T * NWP);
         off_rmask = o; o += align16r(4 * (size_t)T * RW);
         off_cmask = o; o += align16r(4 * (size_t)T * RW);
+        off_any = o;   o += align16r(4 * (size_t)RW);
         off_src = o;   o += align16r((size_t)T * R);
         off_keys = o;  o += align16r(2 * (size_t)T * T);
         off_ring = o;  o += align16r(8 * (size_t)H * T);
-        off_whist = o; o += align16r(4 * (size_t)nwarps * B);
+        off_whist = o; o += align16r(4 * (size_t)nwarps * (B + 1));     // + 1: the bin of samples that do not count
         off_edges = o; o += align16r(8 * (size_t)(B + 1));
         off_misc = o;  o += 256;
         bytes = o;
@@ -192,13 +192,13 @@ step_row_kernel(const Params p, const int SB)
     int *base_s = reinterpret_cast<int *>(smem_raw + lay.off_base);
     unsigned *txm_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_txm);       // [R][NWP]
     unsigned *inr_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_inr);       // [T][NWP]
-    unsigned *own_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_own);       // [T][NWP]
     unsigned *rmask_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_rmask);   // [T][RW] resources heard
     unsigned *cmask_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_cmask);   // [T][RW] resources with >= 2 candidates
     unsigned char *src_s = smem_raw + lay.off_src;                                // [T][R] whom u hears on r
     unsigned *K = reinterpret_cast<unsigned *>(smem_raw + lay.off_keys);          // [T][T2] packed 16-bit keys
     double *ring_s = reinterpret_cast<double *>(smem_raw + lay.off_ring);         // [H][T]
-    unsigned *whist = reinterpret_cast<unsigned *>(smem_raw + lay.off_whist) + warp * B;
+    unsigned *whist = reinterpret_cast<unsigned *>(smem_raw + lay.off_whist) + warp * (B + 1);
+    unsigned *any_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_any);       // [RW] resources with a transmitter
     double *s_edges = reinterpret_cast<double *>(smem_raw + lay.off_edges);
     double *s_red = reinterpret_cast<double *>(smem_raw + lay.off_misc);          // [8]
     unsigned *s_tot = reinterpret_cast<unsigned *>(smem_raw + lay.off_misc + 64);   // received, pairs, bad
@@ -321,7 +321,6 @@ step_row_kernel(const Params p, const int SB)
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 own[w] = txm_s[a_me * NWP + w]; inr[w] = inr_s[tid * NWP + w]; my_tot += __popc(own[w]);
-                own_s[tid * NWP + w] = own[w];
             }
             if (mode == MODE_STEP) {
                 if (my_tot <= 1) rew = 1.0;
@@ -361,6 +360,23 @@ step_row_kernel(const Params p, const int SB)
             }
             s_rewd[tid] = rew; s_aux[tid] = my_tot | (in_range << 16);
         }
+        // channel observations before any reception (test_env.py:203-240 / :305-306 / :431): one warp per vehicle,
+        // coalesced rows; a reception then overwrites its own entry with the distance (after the barrier below)
+        float *og = p.obs + vbase * R;
+        const bool want_d = mode == MODE_STEP && p.state_type == 2;
+        {
+            const float basev = (mode != MODE_STEP || p.state_type == 1) ? 1.0f : (p.state_type == 2 ? (float)sentinel : 0.0f);
+            for (int g = 0; g < RW; ++g) {
+                const int r = g * 32 + lane;
+                unsigned busy = 0u;
+                if (r < R) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) busy |= txm_s[r * NWP + w];
+                }
+                if (r < R)
+                    for (int u = warp; u < N; u += NWARPS) og[(long long)u * R + r] = (busy != 0u && sa[u] != r) ? basev : 0.0f;
+            }
+        }
         if (warp == 0) {     // exclusive scan of the transmitters per resource: where a resource's vehicles start in transmit order
             int carry = 0;
             for (int r0 = 0; r0 < R; r0 += 32) {
@@ -374,6 +390,8 @@ step_row_kernel(const Params p, const int SB)
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
                 if (r < R) base_s[r] = carry + inc - c;
+                const unsigned busy = __ballot_sync(FULL, c > 0);
+                if (lane == 0) any_s[r0 >> 5] = busy;
                 carry += __shfl_sync(FULL, inc, 31);
             }
         }
@@ -390,8 +408,9 @@ step_row_kernel(const Params p, const int SB)
         // network.py:378-398) unless another in-range vehicle shares t's resource; those (u, resource) pairs are marked
         // and resolved below.
         int n_recv = 0, n_pairs = 0;
-        auto reception = [&](int u, int t, int at) {                 // u hears t on resource at
+        auto reception = [&](int u, int t, int at, double d) {       // u hears t on resource at, d metres away
             ++n_recv;
+            if (want_d) og[(long long)u * R + at] = (float)d;
             if (mode == MODE_CH) {
                 atomicAdd(&recv_s[t], 1u);                                                 // test_env.py:396-397
                 if (p.track_lat) p.lat[e * (long long)N * N + (long long)t * N + u] = (int32_t)p.timestep;   // test_env.py:436
@@ -421,20 +440,21 @@ step_row_kernel(const Params p, const int SB)
                     int ncand = 0, lower = 0;
 #pragma unroll
                     for (int w2 = 0; w2 < NW; ++w2) {
-                        const unsigned cw = inr[w2] & own_s[t * NWP + w2];
+                        const unsigned cw = inr[w2] & txm_s[at * NWP + w2];      // in-range vehicles sharing t's resource
                         ncand += __popc(cw);
                         lower += w2 < w ? __popc(cw) : (w2 == w ? __popc(cw & ((1u << bit) - 1u)) : 0);
                     }
                     n_pairs += 1;
                     if (ncand == 1) {
                         const double d = flat ? fabs(__dsub_rn(xu, sx[t])) : dist2d(sx[t], sy[t], xu, yu);
-                        if (d < sentinel) reception(u, t, at);       // best starts at the sentinel (network.py:380)
+                        if (d < sentinel) reception(u, t, at, d);    // best starts at the sentinel (network.py:380)
                     } else if (lower == 0) {
                         atomicOr(&cmask_s[u * RW + (at >> 5)], 1u << (at & 31));   // several candidates: resolved once, below
                     }
                 }
                 if (p.track_lat) {                                                       // network.py:394
-                    const unsigned live = (w * 32 + 32 <= N) ? 0xffffffffu : ((1u << (N - w * 32)) - 1u);
+                    const int nlive = N - w * 32;               // (T is padded to 64: whole words may lie beyond N)
+                    const unsigned live = nlive >= 32 ? 0xffffffffu : (nlive > 0 ? (1u << nlive) - 1u : 0u);
                     for (unsigned c = ~mine_w & live & part_mask; c; c &= c - 1) {
                         const int t = w * 32 + __ffs(c) - 1;
                         if (sa[t] != au) p.lat[e * (long long)N * N + (long long)t * N + u] = -1;
@@ -456,7 +476,7 @@ step_row_kernel(const Params p, const int SB)
                         const double d2 = flat ? fabs(__dsub_rn(xu, sx[t2])) : dist2d(sx[t2], sy[t2], xu, yu);
                         if (d2 < best) { best = d2; tstar = t2; }
                     }
-                if (tstar >= 0) reception(u, tstar, r);
+                if (tstar >= 0) reception(u, tstar, r, best);
             }
         }
 #pragma unroll
@@ -469,28 +489,6 @@ step_row_kernel(const Params p, const int SB)
             if (n_pairs) atomicAdd(&s_tot[1], (unsigned)n_pairs);
         }
         __syncthreads();
-
-        // channel observations (test_env.py:203-240 / :305-306 / :431): one coalesced pass over [N][R]
-        float *og = p.obs + vbase * R;
-        {
-            const float basev = (mode != MODE_STEP || p.state_type == 1) ? 1.0f : (p.state_type == 2 ? (float)sentinel : 0.0f);
-            const bool want_d = mode == MODE_STEP && p.state_type == 2;
-            for (int it = tid; it < N * R; it += TT) {
-                const int u = it / R, r = it - u * R;
-                unsigned any = 0u;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) any |= txm_s[r * NWP + w];
-                float val = 0.0f;
-                if (any != 0u && sa[u] != r) {
-                    val = basev;
-                    if (want_d && ((rmask_s[u * RW + (r >> 5)] >> (r & 31)) & 1u)) {
-                        const int t = src_s[u * R + r];
-                        val = (float)(flat ? fabs(__dsub_rn(sx[u], sx[t])) : dist2d(sx[t], sy[t], sx[u], sy[u]));
-                    }
-                }
-                og[it] = val;
-            }
-        }
 
         // ---- D: rewards out, mobility (Network.update_positions, network.py:189-206) ---------------------------------
         if (act) {
@@ -532,11 +530,13 @@ step_row_kernel(const Params p, const int SB)
         const int n_act = p.add_action ? (p.action_binary ? R : 1) : 0;
         const int o_vpd = n_act + (p.add_channel_obs ? R : 0);
         const int o_tail = o_vpd + B;
+        const bool vec_rows = o_tail == S && (S & 3) == 0 && (n_act & 3) == 0 && (B & 3) == 0 && (!p.add_channel_obs || (R & 3) == 0);
         const double W = p.W, inv_binw = p.inv_binw;
         const int age_thr = p.age_threshold;
 
-        auto tables = [&](auto wide_c) {
+        auto tables = [&](auto wide_c, auto flat_c) {
             constexpr bool WIDE = decltype(wide_c)::value;
+            constexpr bool FL0 = decltype(flat_c)::value;            // every vehicle (and every phantom entry) on lane y = 0
             constexpr int NK = WIDE ? KPL : WPL;                     // key words per lane
             auto row_ptr = [&](int i) -> unsigned * { return WIDE ? Kw + (size_t)i * T + lane * KPL : K + i * T2 + lane * WPL; };
             auto merge_from = [&](unsigned (&my)[NK], int s) {       // Vehicle.received_update (vehicle.py:35-47) on a whole row
@@ -545,6 +545,7 @@ step_row_kernel(const Params p, const int SB)
 #pragma unroll
                 for (int q = 0; q < NK; ++q) my[q] = WIDE ? max(my[q], o[q]) : __vmaxu2(my[q], o[q]);
             };
+            volatile int *vflag = flag_s;
             // phase 1: snapshots in transmit order
             if (merge_mode) {
                 for (int pidx = warp; pidx < N; pidx += NWARPS) {
@@ -555,9 +556,11 @@ step_row_kernel(const Params p, const int SB)
                     for (int g = 0; g * 32 < at; ++g) {
                         unsigned m = rmask_s[t * RW + g];
                         if (at - g * 32 < 32) m &= (1u << (at - g * 32)) - 1u;      // passes before t's own
+                        const int sb = src_s[t * R + min(g * 32 + lane, R - 1)];     // whom t hears on resource g*32 + lane
                         for (; m; m &= m - 1) {
-                            const int s = src_s[t * R + g * 32 + __ffs(m) - 1];
-                            while (ld_acquire_smem(flag_s + s) == 0) { }            // s sorts before t: it will be published
+                            const int s = __shfl_sync(FULL, sb, __ffs(m) - 1);
+                            while (vflag[s] == 0) { }                               // s sorts before t: it will be published
+                            asm volatile("" ::: "memory");
                             merge_from(my, s);
                             changed = true;
                         }
@@ -565,7 +568,7 @@ step_row_kernel(const Params p, const int SB)
                     if (changed) store_words<NK, WIDE>(row_ptr(t), my);
                     if (WIDE) __threadfence_block();
                     __syncwarp();
-                    if (lane == 0) { __threadfence_block(); st_release_smem(flag_s + t, 1); }
+                    if (lane == 0) { __threadfence_block(); vflag[t] = 1; }
                 }
             }
             __syncthreads();
@@ -584,90 +587,141 @@ step_row_kernel(const Params p, const int SB)
                     for (int g = ai >> 5; g < RW; ++g) {
                         unsigned m = rmask_s[i * RW + g];
                         if (g == (ai >> 5)) m &= ~((2u << (ai & 31)) - 1u);          // passes after i's own
-                        for (; m; m &= m - 1) merge_from(my, src_s[i * R + g * 32 + __ffs(m) - 1]);
+                        const int sb = src_s[i * R + min(g * 32 + lane, R - 1)];
+                        for (; m; m &= m - 1) merge_from(my, __shfl_sync(FULL, sb, __ffs(m) - 1));
                     }
                 }
-                if (vpd) { for (int b = lane; b < B; b += 32) whist[b] = 0u; __syncwarp(); }
+                if (vpd) { for (int b = lane; b <= B; b += 32) whist[b] = 0u; __syncwarp(); }
                 const double xi = sxn[i], yi = sy[i];
-                int m_cnt = 0;
+                // Straight-line per entry: decode, age, position from the ring, bin.  Entries whose version is older than the
+                // ring (sparse highways) or whose sample sits within 1e-6 of a bin edge are only flagged here and redone
+                // exactly below -- the common path has no branch, samples that do not count go to bin B.
+                unsigned slow = 0u;
 #pragma unroll
                 for (int q = 0; q < KPL; ++q) {
                     const int c = lane * KPL + q;
-                    int sn; unsigned org;
-                    if (WIDE) { sn = (int)(my[q] >> SB); org = my[q] & srcmask; }
+                    int sn;
+                    if (WIDE) sn = (int)(my[q] >> SB);
                     else {
                         const unsigned hk = (q & 1) ? (my[q >> 1] >> 16) : (my[q >> 1] & 0xffffu), f = hk >> SB;
-                        sn = f ? (int)f + kbase : 0; org = hk & srcmask;
+                        sn = f ? (int)f + kbase : 0;
                     }
                     // vehicle.py:41-47 / :56-70: a strictly newer version (or the own tick) resets the age, everything else ages
                     const int lun = (sn != (int)s0[q]) ? 0 : (int)lu[q] + 1;
                     s0[q] = (unsigned)sn; lu[q] = (unsigned)lun;
-                    // position of that version: the ring while it is younger than H ticks, else the spill table
-                    const int age = tick - sn;
-                    double xn = 0.0;
-                    if (sn > 0) {
-                        if (age < H) xn = ring_s[(sn & (H - 1)) * T + c];
-                        else xn = spill_prev[(long long)org * T + c];
-                        if (age >= H - 1) spill_cur[(long long)i * T + c] = xn;
-                    }
+                    const bool old = sn > 0 && tick - sn >= H - 1;                   // leaves (or has left) the ring
+                    const double xr = ring_s[(sn & (H - 1)) * T + c];
+                    const double xn = sn > 0 ? xr : 0.0;
                     if (vpd) {
-                        bool in = c != i && c < N && lun < age_thr;                              // network.py:547
+                        bool in = c != i && c < N && lun < age_thr;                  // network.py:547
                         double sv;
-                        if (flat0) { sv = __dsub_rn(xn, xi); in = in && fabs(sv) < W; }
+                        if (FL0) { sv = __dsub_rn(xn, xi); in = in && fabs(sv) < W; }       // network.py:487
                         else {
                             const double d = dist2d(xn, sn > 0 ? sy[min(c, N - 1)] : 0.0, xi, yi);
-                            in = in && d < W;                                                    // network.py:487
+                            in = in && d < W;
                             sv = (__dsub_rn(xn, xi) > 0.0) ? d : -d;
                         }
                         // trunc(t) is NumPy's edge-corrected bin unless t is within 1e-6 of an edge
-                        const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
-                        const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
-                        int kb = min(max(__double2int_rz(t), 0), B - 1);
-                        if (in && fabs(__dsub_rn(t, rt)) < 1e-6) kb = vpd_bin(sv, W, inv_binw, B, s_edges);
-                        if (in) atomicAdd(&whist[kb], 1u);
-                        m_cnt += __popc(__ballot_sync(FULL, in));
-                    }
+                        const double tt = __dmul_rn(__dadd_rn(sv, W), inv_binw);
+                        const double rt = __dadd_rn(__dadd_rn(tt, 6755399441055744.0), -6755399441055744.0);
+                        const bool near = fabs(__dsub_rn(tt, rt)) < 1e-6;
+                        const bool again = old || (in && near);
+                        const int kb = (in && !again) ? min(max(__double2int_rz(tt), 0), B - 1) : B;
+                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_addr(whist + kb)));
+                        slow |= again ? 1u << q : 0u;
+                    } else slow |= old ? 1u << q : 0u;
                 }
                 store_words<KPL, false>(reinterpret_cast<unsigned *>(seqg + (long long)i * T + lane * KPL), s0);
                 store_words<KPL, false>(reinterpret_cast<unsigned *>(lug + (long long)i * T + lane * KPL), lu);
+                if (__any_sync(FULL, slow != 0u)) {
+#pragma unroll
+                    for (int q = 0; q < KPL; ++q) {
+                        if (!((slow >> q) & 1u)) continue;
+                        const int c = lane * KPL + q, sn = (int)s0[q];
+                        unsigned org;
+                        if (WIDE) org = my[q] & srcmask;
+                        else org = ((q & 1) ? (my[q >> 1] >> 16) : my[q >> 1]) & srcmask;
+                        double xn = 0.0;
+                        if (sn > 0) {       // position of that version: the ring while it is younger than H ticks, else the spill table
+                            xn = (tick - sn < H) ? ring_s[(sn & (H - 1)) * T + c] : spill_prev[(long long)org * T + c];
+                            if (tick - sn >= H - 1) spill_cur[(long long)i * T + c] = xn;
+                        }
+                        if (vpd) {
+                            bool in = c != i && c < N && (int)lu[q] < age_thr;
+                            double sv;
+                            if (FL0) { sv = __dsub_rn(xn, xi); in = in && fabs(sv) < W; }
+                            else {
+                                const double d = dist2d(xn, sn > 0 ? sy[min(c, N - 1)] : 0.0, xi, yi);
+                                in = in && d < W;
+                                sv = (__dsub_rn(xn, xi) > 0.0) ? d : -d;
+                            }
+                            if (in) atomicAdd(&whist[vpd_bin(sv, W, inv_binw, B, s_edges)], 1u);
+                        }
+                    }
+                }
 
                 // state row (TestEnv.obtain_state, test_env.py:527-583)
                 if (want_state) {
                     __syncwarp();
+                    unsigned cnt0 = 0u;                               // this lane's bins (b = lane, lane + 32, ..): their sum
+                    if (vpd) for (int b = lane; b < B; b += 32) cnt0 += whist[b];
+                    int m_cnt = (int)cnt0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m_cnt += __shfl_xor_sync(FULL, m_cnt, o);
                     const float den = (float)m_cnt, rcp = __frcp_rn(den);
                     const bool have = vpd && m_cnt > 0;
                     float *srow = p.state + (vbase + i) * S;
-                    if (p.add_action) {
-                        if (p.action_binary) { for (int s = lane; s < R; s += 32) srow[s] = (ai == s) ? 1.0f : 0.0f; }
-                        else if (lane == 0) srow[0] = (float)ai;
-                    }
-                    if (p.add_channel_obs) for (int s = lane; s < R; s += 32) srow[n_act + s] = __ldcg(og + (long long)i * R + s);
-                    for (int b = lane; b < B; b += 32) {
-                        float val = 0.0f; unsigned cnt = 0u;
-                        if (have) {
-                            cnt = whist[b];
-                            const float cf = (float)cnt;
-                            const float q0 = __fmul_rn(cf, rcp);
-                            val = __fmaf_rn(__fmaf_rn(-q0, den, cf), rcp, q0);
+                    auto quotient = [&](unsigned cnt) {            // counts / len, exact (tests/test_host.py)
+                        const float cf = (float)cnt, q0 = __fmul_rn(cf, rcp);
+                        return have ? __fmaf_rn(__fmaf_rn(-q0, den, cf), rcp, q0) : 0.0f;
+                    };
+                    if (vec_rows) {           // every block is whole float4 groups: 16-byte stores straight from registers
+                        for (int f4 = lane; f4 < (S >> 2); f4 += 32) {
+                            const int s4 = f4 << 2;
+                            float4 v;
+                            if (s4 < n_act) {
+                                const int d = ai - s4;
+                                v = make_float4(d == 0 ? 1.0f : 0.0f, d == 1 ? 1.0f : 0.0f, d == 2 ? 1.0f : 0.0f, d == 3 ? 1.0f : 0.0f);
+                            } else if (s4 < o_vpd) {
+                                v = __ldcg(reinterpret_cast<const float4 *>(og + (long long)i * R + (s4 - n_act)));
+                            } else {
+                                const int b = s4 - o_vpd;
+                                const unsigned c0 = have ? whist[b] : 0u, c1 = have ? whist[b + 1] : 0u, c2 = have ? whist[b + 2] : 0u,
+                                               c3 = have ? whist[b + 3] : 0u;
+                                v = make_float4(quotient(c0), quotient(c1), quotient(c2), quotient(c3));
+                                if (p.vpd_counts)
+                                    *reinterpret_cast<unsigned *>(p.vpd_counts + (vbase + i) * p.rec_stride + b) = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+                            }
+                            *reinterpret_cast<float4 *>(srow + s4) = v;
                         }
-                        srow[o_vpd + b] = val;
-                        if (p.vpd_counts) p.vpd_counts[(vbase + i) * p.rec_stride + b] = (unsigned char)cnt;
-                    }
-                    if (lane < S - o_tail) {
-                        float val = 0.0f; int kk = lane;
-                        if (p.add_reward)   { if (kk == 0) val = s_rew[i]; --kk; }
-                        if (p.add_index)    { if (kk == 0) val = (float)(i + 1); --kk; }
-                        if (p.add_position) { if (kk == 0) val = (float)__ddiv_rn(xi, p.L); if (kk == 1) val = (float)__ddiv_rn(yi, 2.0); kk -= 2; }
-                        if (p.add_velocity) { if (kk == 0) val = (float)p.vel[vbase + i]; --kk; }
-                        if (p.fingerprint)  { if (kk == 0) val = (float)p.episode; if (kk == 1) val = (float)p.epsilon; kk -= 2; }
-                        srow[o_tail + lane] = val;
+                    } else {
+                        if (p.add_action) {
+                            if (p.action_binary) { for (int s = lane; s < R; s += 32) srow[s] = (ai == s) ? 1.0f : 0.0f; }
+                            else if (lane == 0) srow[0] = (float)ai;
+                        }
+                        if (p.add_channel_obs) for (int s = lane; s < R; s += 32) srow[n_act + s] = __ldcg(og + (long long)i * R + s);
+                        for (int b = lane; b < B; b += 32) {
+                            const unsigned cnt = have ? whist[b] : 0u;
+                            srow[o_vpd + b] = quotient(cnt);
+                            if (p.vpd_counts) p.vpd_counts[(vbase + i) * p.rec_stride + b] = (unsigned char)cnt;
+                        }
+                        if (lane < S - o_tail) {
+                            float val = 0.0f; int kk = lane;
+                            if (p.add_reward)   { if (kk == 0) val = s_rew[i]; --kk; }
+                            if (p.add_index)    { if (kk == 0) val = (float)(i + 1); --kk; }
+                            if (p.add_position) { if (kk == 0) val = (float)__ddiv_rn(xi, p.L); if (kk == 1) val = (float)__ddiv_rn(yi, 2.0); kk -= 2; }
+                            if (p.add_velocity) { if (kk == 0) val = (float)p.vel[vbase + i]; --kk; }
+                            if (p.fingerprint)  { if (kk == 0) val = (float)p.episode; if (kk == 1) val = (float)p.epsilon; kk -= 2; }
+                            srow[o_tail + lane] = val;
+                        }
                     }
                     __syncwarp();
                 }
             }
         };
         __syncthreads();                          // ring row, sxn, og, reception tables complete
-        if (wide) tables(std::true_type{}); else tables(std::false_type{});
+        if (wide) { if (flat0) tables(std::true_type{}, std::true_type{}); else tables(std::true_type{}, std::false_type{}); }
+        else { if (flat0) tables(std::false_type{}, std::true_type{}); else tables(std::false_type{}, std::false_type{}); }
 
         // ---- per-env metric accumulators (fixed-order block reduction for the reward sum) ----------------------------
         {
@@ -691,7 +745,7 @@ step_row_kernel(const Params p, const int SB)
 
 int row_nw2(int N) { return std::max(1, (N + 63) / 64); }
 
-int row_ring_depth(int N) { return row_nw2(N) == 1 ? 32 : 16; }
+int row_ring_depth(int N) { return row_nw2(N) == 1 ? 32 : (row_nw2(N) == 4 ? 8 : 16); }
 
 template <int NW2>
 cudaError_t prepare_t(size_t smem)
