@@ -38,7 +38,10 @@ int fail(int code, const char *fmt, ...)
             return fail(DIRAL_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
     } while (0)
 
-enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2, VARIANT_BLOCK_V1 = 3 };
+enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2, VARIANT_BLOCK_V1 = 3, VARIANT_ROW = 4 };
+// Measured on B200 (profiles/README.md): the row-layout kernel wins from ~100 vehicles on (1.07x at 128, 1.67x at 256);
+// below that its padded rows (T = 128 for 65..96 vehicles) and per-environment fixed costs lose to round 1's kernel.
+constexpr int ROW_MIN_N = 97;
 constexpr int MAX_HOST_CHUNKS = 32;
 
 struct Handle {
@@ -114,7 +117,7 @@ int check_cfg(const diral_cfg *c)
 
 bool use_group(const Handle *h)
 {
-    if (h->variant == VARIANT_BLOCK || h->variant == VARIANT_BLOCK_V1) return false;
+    if (h->variant == VARIANT_BLOCK || h->variant == VARIANT_BLOCK_V1 || h->variant == VARIANT_ROW) return false;
     if (h->variant == VARIANT_AUTO && !h->block_ok) return true;
     return h->group_ok;
 }
@@ -122,7 +125,8 @@ bool use_group(const Handle *h)
 // the row-layout kernel is the one-CTA-per-env kernel of choice wherever it applies; VARIANT_BLOCK_V1 pins round 1's
 bool use_row(const Handle *h)
 {
-    return h->row_ok && !use_group(h) && h->variant != VARIANT_BLOCK_V1;
+    if (!h->row_ok || use_group(h) || h->variant == VARIANT_BLOCK_V1) return false;
+    return h->variant == VARIANT_ROW || h->cfg.N >= ROW_MIN_N || !h->block_ok;
 }
 
 bool fused_state_ok(const diral_cfg &c)
@@ -478,7 +482,9 @@ int diral_set_option(void *handle, const char *name, int64_t value)
     Handle *h = as_handle(handle);
     if (!h || !name) return fail(DIRAL_ERR_ARG, "handle/name is NULL");
     if (!strcmp(name, "variant")) {
-        if (value < 0 || value > 3) return fail(DIRAL_ERR_ARG, "variant must be 0 (auto), 1 (group), 2 (block) or 3 (round-1 block kernel)");
+        if (value < 0 || value > 4) return fail(DIRAL_ERR_ARG, "variant must be 0 (auto), 1 (group), 2 (block), 3 (round-1 block kernel) or 4 (row layout)");
+        if (value == VARIANT_ROW && !h->row_ok)
+            return fail(DIRAL_ERR_UNSUPPORTED, "the row-layout kernel takes 33..256 vehicles with neighbour tables and a fused State block");
         if (h->bound) return fail(DIRAL_ERR_ARG, "the kernel variant fixes the table layout: choose it before diral_bind()");
         if (value == VARIANT_GROUP && h->cfg.N > diral::GROUP_MAX_N)
             return fail(DIRAL_ERR_ARG, "the group kernel handles num_users <= %d", diral::GROUP_MAX_N);

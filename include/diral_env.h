@@ -255,7 +255,8 @@ int diral_materialize_x(void *handle, double *out, void *stream);
 int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes, const void *src, void *stream);
 
 /* Options.  Test/bench knobs: "variant" = 0 auto | 1 lane-group kernel (N <= 32) | 2 one-CTA-per-env kernel (the
- * row-layout kernel where it applies, else round 1's) | 3 round 1's one-CTA-per-env kernel; set before diral_bind;
+ * row-layout kernel from 97 vehicles on, else round 1's) | 3 round 1's one-CTA-per-env kernel | 4 the row-layout
+ * kernel (33..256 vehicles, fused State block); set before diral_bind;
  * "track_lat" = 1 keeps last_arrival_time bookkeeping on even before the first my_step_ch call.
  * diral_step_host: "host_format" (0 full rows | 1 compact), "host_threads", "host_chunks" (env chunks pipelined per
  * call).  Checkpoint restore: "ticks" (table ticks since the reset = every vehicle's own sequence number) and
