@@ -151,7 +151,7 @@ __device__ __noinline__ int vpd_bin_edges(double s, double W, double inv_binw, i
 #define DIRAL_GROUP_WARPS 1      // tuning knob: warps (= environments at G == 32) per CTA for G >= 16
 #endif
 
-template <int G, bool FULL, int WARPS, int MODE, bool LAT, bool ROLL>
+template <int G, bool FULL, int WARPS, int MODE, bool LAT, bool ROLL, bool CNT>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS == DIRAL_GROUP_WARPS ? (DIRAL_MIN_BLOCKS + WARPS - 1) / WARPS : 1))
 step_group_kernel(const Params p)
 {
@@ -529,8 +529,6 @@ step_group_kernel(const Params p)
                     const double t = __dmul_rn(__dadd_rn(sv, W), inv_binw);
                     const double rt = __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
                     const bool near = fabs(__dsub_rn(t, rt)) < 1e-6;
-                    // samples that do not count (or wait for the exact re-binning) go to a dummy row, so
-                    // the reduction is unconditional and the column code stays branch-free
                     const int kb = (in && !near) ? min(max((int)t, 0), B - 1) : B;
                     smem_red_inc(&hist[kb * G + u]);
                     if (in && near) fix |= 1u << q;
@@ -569,7 +567,7 @@ step_group_kernel(const Params p)
         }
     }
     if (act) p.rews[vbase + u] = (float)rew;
-    if (act && p.vpd_counts) *reinterpret_cast<float *>(p.vpd_counts + (vbase + u + 1) * p.rec_stride - 4) = (float)rew;
+    if (CNT && act) *reinterpret_cast<float *>(p.vpd_counts + (vbase + u + 1) * p.rec_stride - 4) = (float)rew;
 
     // ---- F: state rows (TestEnv.obtain_state) in shared memory -----------------------------------
     // Row u sits at st[u*S .. u*S+S) exactly as in global memory, so the copy-out is a plain
@@ -598,7 +596,7 @@ step_group_kernel(const Params p)
                 unsigned hv[8]; float f[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) hv[i] = (have && b0 + i < B) ? hist[(b0 + i) * G + u] : 0u;
-                if (p.vpd_counts) {                  // compact host format: the counts themselves, one byte per bin
+                if (CNT) {                           // compact host format: the counts themselves, one byte per bin
                     unsigned char *cp = p.vpd_counts + (vbase + u) * p.rec_stride + b0;
                     if ((B & 3) == 0) {
                         *reinterpret_cast<unsigned *>(cp) = hv[0] | (hv[1] << 8) | (hv[2] << 16) | (hv[3] << 24);
@@ -662,15 +660,18 @@ cudaError_t prepare_k(const Params &p)
     Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for
     const size_t smem = smem_bytes<G>(q, WarpsFor<G>::v);
     if (smem <= 48 * 1024) return cudaSuccess;
-    cudaError_t err = cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, false>,
+    cudaError_t err = cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, false, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    return cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, true>,
+    err = cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, false, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    return cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, true, false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 // CTAs of this instantiation the current device holds at once (cached per instantiation, device and smem size)
-template <int G, bool FULL, int W, int MODE, bool LAT, bool ROLL>
+template <int G, bool FULL, int W, int MODE, bool LAT, bool ROLL, bool CNT>
 long long resident_ctas(size_t smem)
 {
     constexpr int MAX_DEV = 64;
@@ -683,7 +684,7 @@ long long resident_ctas(size_t smem)
     if (cached[slot] == 0 || smem != cached_smem[slot] || slot != dev) {
         int sms = 148, per_sm = 16;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_group_kernel<G, FULL, W, MODE, LAT, ROLL>, W * 32, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_group_kernel<G, FULL, W, MODE, LAT, ROLL, CNT>, W * 32, smem) != cudaSuccess)
             per_sm = 16;
         cached[slot] = (long long)sms * std::max(per_sm, 1); cached_smem[slot] = smem;
     }
@@ -698,11 +699,17 @@ cudaError_t launch_k(const Params &p, cudaStream_t stream)
     const long long grid = (p.E + envs_per_cta - 1) / envs_per_cta;
     size_t smem = smem_bytes<G>(p, W);
     Params q = p;
-    const bool roll = p.n_slots > 1;
-    q.prefetch_ahead = (int)((roll ? resident_ctas<G, FULL, W, MODE, LAT, true>(smem)
-                                   : resident_ctas<G, FULL, W, MODE, LAT, false>(smem)) * envs_per_cta);
-    if (roll) step_group_kernel<G, FULL, W, MODE, LAT, true><<<(unsigned)grid, W * 32, smem, stream>>>(q);
-    else step_group_kernel<G, FULL, W, MODE, LAT, false><<<(unsigned)grid, W * 32, smem, stream>>>(q);
+    const bool roll = p.n_slots > 1, cnt = p.vpd_counts != nullptr;     // (the fused rollout has no host-record output)
+    if (roll) {
+        q.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT, true, false>(smem) * envs_per_cta);
+        step_group_kernel<G, FULL, W, MODE, LAT, true, false><<<(unsigned)grid, W * 32, smem, stream>>>(q);
+    } else if (cnt) {
+        q.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT, false, true>(smem) * envs_per_cta);
+        step_group_kernel<G, FULL, W, MODE, LAT, false, true><<<(unsigned)grid, W * 32, smem, stream>>>(q);
+    } else {
+        q.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT, false, false>(smem) * envs_per_cta);
+        step_group_kernel<G, FULL, W, MODE, LAT, false, false><<<(unsigned)grid, W * 32, smem, stream>>>(q);
+    }
     return cudaGetLastError();
 }
 

@@ -154,13 +154,19 @@ __device__ __forceinline__ void store_words(unsigned *ptr, const unsigned (&v)[N
     }
 }
 
+#ifndef DIRAL_ROW_THREADS_64
+#define DIRAL_ROW_THREADS_64 256      // tuning knob: threads per CTA of the 64-vehicle instantiation
+#endif
+__host__ __device__ constexpr int row_threads(int nw2) { return nw2 == 1 ? DIRAL_ROW_THREADS_64 : 256 * nw2; }
+__host__ __device__ constexpr int row_min_ctas(int nw2) { return nw2 == 1 ? 1024 / DIRAL_ROW_THREADS_64 : (nw2 == 2 ? 2 : 1); }
+
 template <int NW2>
-__global__ void __launch_bounds__(256 * NW2, NW2 == 1 ? 4 : (NW2 == 2 ? 2 : 1))
+__global__ void __launch_bounds__(row_threads(NW2), row_min_ctas(NW2))
 step_row_kernel(const Params p, const int SB)
 {
     constexpr int T = 64 * NW2;                   // padded vehicle count = row stride of the tables
     constexpr int NW = 2 * NW2, NWP = NW | 1;     // 32-bit words of a vehicle bit mask (odd stride in shared memory)
-    constexpr int TT = 256 * NW2, NWARPS = TT / 32, RPW = T / NWARPS;   // 8 rows per warp
+    constexpr int TT = row_threads(NW2), NWARPS = TT / 32, RPW = T / NWARPS;   // rows per warp (8; 16 with 128-thread CTAs)
     constexpr int KPL = NW;                       // table columns per lane of a row warp (T / 32)
     constexpr int WPL = NW2;                      // packed key words per lane (two 16-bit keys per word)
     constexpr int T2 = T / 2;                     // packed key words per row
@@ -531,7 +537,7 @@ step_row_kernel(const Params p, const int SB)
         const int o_vpd = n_act + (p.add_channel_obs ? R : 0);
         const int o_tail = o_vpd + B;
         const bool vec_rows = o_tail == S && (S & 3) == 0 && (n_act & 3) == 0 && (B & 3) == 0 && (!p.add_channel_obs || (R & 3) == 0);
-        const double W = p.W, inv_binw = p.inv_binw;
+        const double W = p.W, inv_binw = p.inv_binw, inv_binw_s = p.inv_binw * 1048576.0;
         const int age_thr = p.age_threshold;
 
         auto tables = [&](auto wide_c, auto flat_c) {
@@ -622,11 +628,11 @@ step_row_kernel(const Params p, const int SB)
                             sv = (__dsub_rn(xn, xi) > 0.0) ? d : -d;
                         }
                         // trunc(t) is NumPy's edge-corrected bin unless t is within 1e-6 of an edge
-                        const double tt = __dmul_rn(__dadd_rn(sv, W), inv_binw);
-                        const double rt = __dadd_rn(__dadd_rn(tt, 6755399441055744.0), -6755399441055744.0);
-                        const bool near = fabs(__dsub_rn(tt, rt)) < 1e-6;
+                        // (12.20 fixed point: integer part = bin, fraction within 2^-19 of an integer = near an edge)
+                        const int ti = __double2int_rz(__dmul_rn(__dadd_rn(sv, W), inv_binw_s));
+                        const bool near = ((unsigned)(ti + 2) & 0xfffffu) < 4u;
                         const bool again = old || (in && near);
-                        const int kb = (in && !again) ? min(max(__double2int_rz(tt), 0), B - 1) : B;
+                        const int kb = (in && !again) ? (ti >> 20) : B;
                         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_addr(whist + kb)));
                         slow |= again ? 1u << q : 0u;
                     } else slow |= old ? 1u << q : 0u;
@@ -760,11 +766,11 @@ cudaError_t launch_t(const Params &p, size_t smem, int SB, cudaStream_t stream)
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_row_kernel<NW2>, 256 * NW2, smem);
+    if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_row_kernel<NW2>, row_threads(NW2), smem);
     if (err != cudaSuccess) return err;
     const long long resident = (long long)sms * std::max(per_sm, 1);
     const unsigned grid = (unsigned)std::min<long long>(p.E, resident);
-    step_row_kernel<NW2><<<grid, 256 * NW2, smem, stream>>>(p, SB);
+    step_row_kernel<NW2><<<grid, row_threads(NW2), smem, stream>>>(p, SB);
     return cudaGetLastError();
 }
 
@@ -777,7 +783,7 @@ int step_row_ring_depth(int N) { return row_ring_depth(N); }
 size_t step_row_smem_bytes(const Params &p)
 {
     const int nw2 = row_nw2(p.N);
-    return RowSmem(64 * nw2, p.R, p.B, row_ring_depth(p.N), 8 * nw2).bytes;
+    return RowSmem(64 * nw2, p.R, p.B, row_ring_depth(p.N), row_threads(nw2) / 32).bytes;
 }
 
 // The row kernel takes every configuration with neighbour tables and a fused state build between 33 and 256 vehicles

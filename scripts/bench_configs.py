@@ -41,7 +41,7 @@ def main():
         if only and only not in name:
             continue
         kw = dict(dict(reward_design=2, communication_range=250, mobility=True, bin_range=500, State=STATE), **kw)
-        env = TestEnv(num_envs=E, device="cuda", seed=1, **kw)
+        env = TestEnv(num_envs=E, device="cuda", seed=1, variant=os.environ.get("DIRAL_VARIANT", "auto"), **kw)
         for t in range(30):
             env._step(mode, None, t, True)
         steps = 50
@@ -53,7 +53,7 @@ def main():
         ms = sum(a.elapsed_time(b) for a, b in ev) / steps
         n, r, b = env.N, env.R, env.B
         alg = (32 * n * n + n * (36 + 8 * r + 4 * b) + (8 * n * n if mode == "my_step_ch" else 0)) * E
-        row = {"config": name, "envs": E, "mode": mode, "us_per_slot": ms * 1e3,
+        row = {"config": name, "kernel": env.kernel, "envs": E, "mode": mode, "us_per_slot": ms * 1e3,
                "agent_steps_per_s": E * n / (ms / 1e3), "algorithmic_GBps": alg / (ms / 1e3) / 1e9,
                "roofline_frac": alg / (ms / 1e3) / 1e9 / peak}
         if n <= 32:
