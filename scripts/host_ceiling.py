@@ -88,6 +88,7 @@ def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, nt=-1, reps=40)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--quick", action="store_true", help="copy ceilings and the row-assembly rate only (multi-GPU boxes are charged per GPU)")
     args = ap.parse_args()
     cpus = len(os.sched_getaffinity(0))
     out = {"cpu_model": cpu_model(), "cpus_usable": cpus, "cpu_count": os.cpu_count(), "d2h": [], "expander": [], "step_host": []}
@@ -101,6 +102,9 @@ def main():
     for th in sorted({1, 2, 4, 8, 12, max(cpus - 2, 1), max(cpus - 1, 1)}):
         out["expander"].append(dict(expander(th), stores="ordinary"))
         out["expander"].append(dict(expander(-th), stores="non-temporal"))
+    if args.quick:
+        print(json.dumps(out, indent=1))
+        return
     env = TestEnv(num_envs=E_PER_GPU, device="cuda:0", seed=1234, **ENV_KW)
     acts = [env.sample(t) for t in range(8)]
     for t in range(60):
