@@ -65,6 +65,7 @@ struct Handle {
     int host_format = 0;            // 0 = full rows over PCIe, 1 = compact record + host-side row assembly
     int host_threads = 0;           // 0 = pick from the CPUs this process may run on
     int host_chunks = 8;
+    int tail_split = 1;             // see Params::tail_split
     int host_nt = -1;               // output-row stores: 1 non-temporal, 0 ordinary, -1 by output size per thread
     diral::HostPool *pool = nullptr;
     uint8_t *d_counts = nullptr;    // [E][N][B] device
@@ -156,7 +157,7 @@ void fill_base(Handle *h)
     const diral_cfg &c = h->cfg;
     diral::Params &p = h->base;
     p = diral::Params{};
-    p.n_slots = 1;
+    p.n_slots = 1; p.tail_split = h->tail_split;
     p.E = c.E; p.env0 = c.env0; p.N = c.N; p.R = c.R; p.B = c.B; p.S = state_space(c);
     p.L = c.L; p.C = c.C; p.C2 = 2 * c.C; p.W = c.W; p.sentinel = c.sentinel;
     p.inv_binw = (double)c.B / (2.0 * c.W);
@@ -509,6 +510,11 @@ int diral_set_option(void *handle, const char *name, int64_t value)
         h->host_threads = (int)value;
         return DIRAL_OK;
     }
+    if (!strcmp(name, "tail_split")) {
+        if (value < 0 || value > 2) return fail(DIRAL_ERR_ARG, "tail_split must be 0 (off), 1 (auto) or 2 (always)");
+        h->tail_split = (int)value; h->base.tail_split = (int)value;
+        return DIRAL_OK;
+    }
     if (!strcmp(name, "host_nt")) {
         if (value < -1 || value > 1) return fail(DIRAL_ERR_ARG, "host_nt must be -1 (auto), 0 or 1");
         h->host_nt = (int)value;
@@ -544,6 +550,7 @@ int64_t diral_get_option(void *handle, const char *name)
     if (!strcmp(name, "host_threads")) return h->pool ? h->pool->threads() : h->host_threads;
     if (!strcmp(name, "host_chunks")) return h->host_chunks;
     if (!strcmp(name, "host_nt")) return h->host_nt;
+    if (!strcmp(name, "tail_split")) return h->tail_split;
     if (!strcmp(name, "ticks")) return h->ticks;
     if (!strcmp(name, "lat_live")) return h->lat_live ? 1 : 0;
     if (!strcmp(name, "compact_ok")) return compact_ok(h->cfg) ? 1 : 0;

@@ -39,6 +39,7 @@ struct Params {
     // per-call
     int mode, track_lat, build_state, gen_actions;
     int prefetch_ahead;       // envs between this CTA's env and the one that will reuse its SM slot
+    int tail_split;           // lane-group kernel, 32 lanes: 0 never split an environment over warps, 1 the tail of a batch, 2 always
     int n_slots;              // consecutive slots one launch of the lane-group kernel runs (fused rollout), >= 1
     long long timestep;
     int tick;                 // table ticks since the reset including this slot (= every vehicle's own seq)

@@ -71,13 +71,14 @@ __host__ __device__ inline bool group_direct_rows(const Params &p)
 }
 
 struct GroupSmem {
-    int off_sx, off_sy, off_script, off_txm, off_recv, off_obs, off_hist, off_st, bytes;
+    int off_sx, off_sy, off_script, off_txm, off_recv, off_mcnt, off_obs, off_hist, off_st, bytes;
     __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd, bool direct)
     {
         int o = 0;
         off_script = o; o += align16i(G * (R + 1));    // merge script: one byte per (pass, lane), + 1 spare row
         off_txm = o;    o += align16i(4 * R);          // transmitter mask of every resource
         off_recv = o;   o += align16i(4 * G);          // packets received per transmitter (my_step_ch)
+        off_mcnt = o;   o += align16i(4 * G);          // VPD sample counts summed over the warps of a split environment
         off_sx = o;   o += align16i(8 * G);
         off_sy = o;   o += align16i(8 * G);
         off_obs = o;  o += align16i(4 * G * R);
@@ -151,16 +152,24 @@ __device__ __noinline__ int vpd_bin_edges(double s, double W, double inv_binw, i
 #define DIRAL_GROUP_WARPS 1      // tuning knob: warps (= environments at G == 32) per CTA for G >= 16
 #endif
 
-template <int G, bool FULL, int WARPS, int MODE, bool LAT, bool ROLL, bool CNT>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == DIRAL_GROUP_WARPS ? (DIRAL_MIN_BLOCKS + WARPS - 1) / WARPS : 1))
+// SP ("split"): the WARPS warps of the CTA share ONE environment.  Every warp runs the decision phase for itself (no
+// cross-warp hazards: the merge script, observation rows and masks are per-warp copies), then takes every WARPS-th
+// slab of table columns; the positional-distribution histogram is shared (it is filled by reductions anyway), and
+// warp 0 alone writes rewards, state rows and the episode accumulators.  Latency of one environment drops to the
+// decision phase plus 1 / WARPS of the table phase -- what the launch uses for the tail of a batch that does not
+// fill the device a whole number of times (launch_k).
+template <int G, bool FULL, int WARPS, int MODE, bool LAT, bool ROLL, bool CNT, bool SP = false>
+__global__ void __launch_bounds__(WARPS * 32, ((ROLL || G < 16) ? 1 : (DIRAL_MIN_BLOCKS + WARPS - 1) / WARPS))
 step_group_kernel(const Params p)
 {
+    static_assert(!SP || (G == 32 && !ROLL), "split environments: 32-lane groups, single slot");
     constexpr int EPW = 32 / G;              // environments per warp
     constexpr int SB = Log2<G>::v;           // low key bits holding the origin row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int u = lane & (G - 1), sub = lane / G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
-    const long long e = ((long long)blockIdx.x * WARPS + warp) * EPW + sub;
+    const long long e = SP ? (long long)blockIdx.x : ((long long)blockIdx.x * WARPS + warp) * EPW + sub;
+    const bool lead = !SP || warp == 0;      // the warp that owns an environment's outputs
     const int N = FULL ? G : p.N;
     const int R = p.R, B = p.B, S = p.S;
 
@@ -181,7 +190,9 @@ step_group_kernel(const Params p)
     unsigned char *script = gbase + lay.off_script;                    // [passes][G]
     unsigned *txm_s = reinterpret_cast<unsigned *>(gbase + lay.off_txm);
     unsigned *recv_s = reinterpret_cast<unsigned *>(gbase + lay.off_recv);
-    unsigned *hist = reinterpret_cast<unsigned *>(gbase + lay.off_hist);
+    unsigned char *gbase0 = SP ? smem_raw + align16i(8 * (B + 1)) : gbase;   // split: histogram / counts live in warp 0's area
+    unsigned *hist = reinterpret_cast<unsigned *>(gbase0 + lay.off_hist);
+    unsigned *mcnt_s = reinterpret_cast<unsigned *>(gbase0 + lay.off_mcnt);
     float *st = reinterpret_cast<float *>(gbase + lay.off_st);         // [N][S], rows rotated (see F)
 
     const bool act = FULL ? true : (u < N);
@@ -207,13 +218,15 @@ step_group_kernel(const Params p)
         x = p.pos_x[vbase + u]; y = p.pos_y[vbase + u]; v = p.vel[vbase + u];
     }
     int s_next[SL];                          // seq column of the upcoming slab (loaded one slab ahead)
+    constexpr int SLAB_STEP = SP ? WARPS * SL : SL;      // a split environment's warps interleave slabs
+    const int slab0 = SP ? warp * SL : 0;
 #pragma unroll
-    for (int q = 0; q < SL; ++q) s_next[q] = (p.piggy && (FULL || (q < N && act))) ? seqp[q * N] : 0;
+    for (int q = 0; q < SL; ++q) s_next[q] = (p.piggy && (FULL || (slab0 + q < N && act))) ? seqp[(slab0 + q) * N] : 0;
     {
         // the CTA that will take over this slot most likely handles env e + (resident CTAs); start its
         // per-vehicle inputs towards L2 now so that its first dependent instruction does not wait on HBM
         const long long en = e + (long long)p.prefetch_ahead;
-        if (u == 0 && en < p.E) {
+        if (u == 0 && lead && en < p.E) {
             if (!p.gen_actions) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + en * N));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pos_x + en * N));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pos_y + en * N));
@@ -232,7 +245,7 @@ step_group_kernel(const Params p)
         const char *b1 = reinterpret_cast<const char *>(p.tab_lu + tbase);
         const char *b2 = reinterpret_cast<const char *>(p.tab_x + tbase);
         const int bytes4 = N * N * 4;
-        for (int o = u * 128; o < bytes4; o += G * 128) {
+        for (int o = (SP ? warp * G + u : u) * 128; o < bytes4; o += (SP ? WARPS : 1) * G * 128) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + o));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + o));
@@ -242,7 +255,7 @@ step_group_kernel(const Params p)
     if (act) {
         if (p.gen_actions) a = philox_action(p.seed, u, p.env0 + e, timestep, R);
         if (a < 0 || a >= R) { bad = 1; a = min(max(a, 0), R - 1); }
-        if (p.gen_actions && p.actions_out) p.actions_out[vbase + u] = a;
+        if (p.gen_actions && p.actions_out && lead) p.actions_out[vbase + u] = a;
     }
     sx[u] = x; sy[u] = y;
 
@@ -409,13 +422,15 @@ step_group_kernel(const Params p)
 
     // ---- D: mobility -------------------------------------------------------------------------------
     const double x_new = act ? mobility_step_at(p, x, v, u, timestep) : 0.0;
-    if (act && p.mobility) p.pos_x[vbase + u] = x_new;
 
     // ---- C2/E: per slab -- tick, replay the merge script, gather xpos, age, write back, VPD ---------
     int m_cnt = 0;
-    if (vpd) {
+    if (vpd && lead) {
         for (int k = 0; k < B; ++k) hist[k * G + u] = 0u;
+        if (SP) mcnt_s[u] = 0u;
     }
+    if (SP) __syncthreads();                 // every warp has read the old positions; the shared histogram is clear
+    if (act && p.mobility && lead) p.pos_x[vbase + u] = x_new;
     __syncwarp(gmask);                       // script rows written by every lane are read by its own lane only,
                                              // but the histogram zeroing above must precede the slab updates
     const double W = p.W, inv_binw = p.inv_binw;
@@ -431,10 +446,10 @@ step_group_kernel(const Params p)
             if (FULL || (j < N && act)) { lb[q] = lup[j * N]; xb[q] = xp[j * N]; }
             else { lb[q] = 0; xb[q] = 0.0; }
         }
-        if (jbase + SL < G) {
+        if (jbase + SLAB_STEP < G) {
 #pragma unroll
             for (int q = 0; q < SL; ++q) {
-                const int j = jbase + SL + q;
+                const int j = jbase + SLAB_STEP + q;
                 s_next[q] = (FULL || (j < N && act)) ? seqp[j * N] : 0;
             }
         }
@@ -546,7 +561,13 @@ step_group_kernel(const Params p)
     };
     if (p.piggy) {
 #pragma unroll 1
-        for (int jbase = 0; jbase < G; jbase += SL) do_slab(jbase);
+        for (int jbase = slab0; jbase < G; jbase += SLAB_STEP) do_slab(jbase);
+    }
+    if (SP) {                                // the other warps' columns are in the histogram once the CTA has met
+        if (vpd) atomicAdd(&mcnt_s[u], (unsigned)m_cnt);
+        __syncthreads();
+        if (!lead) return;
+        if (vpd) m_cnt = (int)mcnt_s[u];
     }
 
     // ---- per-env metric accumulators -------------------------------------------------------------
@@ -654,6 +675,25 @@ size_t smem_bytes(const Params &p, int warps)
 // small groups pack 4 warps so that a CTA still carries a useful number of environments
 template <int G> struct WarpsFor { static constexpr int v = G >= 16 ? DIRAL_GROUP_WARPS : 4; };
 
+constexpr int SPLIT_WARPS = 4;      // warps that share one environment of a batch's tail (one 8-column slab each at 32 vehicles)
+
+// the same parameter block restricted to envs [e0, e0 + n) (every per-env array the lane-group kernel touches)
+Params env_slice(const Params &p, long long e0, long long n)
+{
+    Params q = p;
+    const long long N = p.N, NN = N * N;
+    q.E = n; q.env0 = p.env0 + e0;
+    if (q.actions) q.actions += e0 * N;
+    if (q.actions_out) q.actions_out += e0 * N;
+    q.pos_x += e0 * N; q.pos_y += e0 * N; q.vel += e0 * N;
+    if (q.tab_seq) { q.tab_seq += e0 * NN; q.tab_lu += e0 * NN; q.tab_x += e0 * NN; }
+    if (q.lat) q.lat += e0 * NN;
+    q.obs += e0 * N * p.R; q.rews += e0 * N; q.state += e0 * N * p.S;
+    if (q.vpd_counts) q.vpd_counts += e0 * N * p.rec_stride;
+    q.acc_reward += e0; q.acc_count += e0 * ACC_COUNTS;
+    return q;
+}
+
 template <int G, bool FULL, int MODE, bool LAT>
 cudaError_t prepare_k(const Params &p)
 {
@@ -666,12 +706,22 @@ cudaError_t prepare_k(const Params &p)
     err = cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, false, true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    return cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, true, false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    err = cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, true, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if constexpr (G == 32) {
+        const size_t smem_sp = smem_bytes<G>(q, SPLIT_WARPS);
+        if (err == cudaSuccess && smem_sp > 48 * 1024)
+            err = cudaFuncSetAttribute(step_group_kernel<G, FULL, SPLIT_WARPS, MODE, LAT, false, false, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);
+        if (err == cudaSuccess && smem_sp > 48 * 1024)
+            err = cudaFuncSetAttribute(step_group_kernel<G, FULL, SPLIT_WARPS, MODE, LAT, false, true, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);
+    }
+    return err;
 }
 
 // CTAs of this instantiation the current device holds at once (cached per instantiation, device and smem size)
-template <int G, bool FULL, int W, int MODE, bool LAT, bool ROLL, bool CNT>
+template <int G, bool FULL, int W, int MODE, bool LAT, bool ROLL, bool CNT, bool SP = false>
 long long resident_ctas(size_t smem)
 {
     constexpr int MAX_DEV = 64;
@@ -684,7 +734,7 @@ long long resident_ctas(size_t smem)
     if (cached[slot] == 0 || smem != cached_smem[slot] || slot != dev) {
         int sms = 148, per_sm = 16;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_group_kernel<G, FULL, W, MODE, LAT, ROLL, CNT>, W * 32, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_group_kernel<G, FULL, W, MODE, LAT, ROLL, CNT, SP>, W * 32, smem) != cudaSuccess)
             per_sm = 16;
         cached[slot] = (long long)sms * std::max(per_sm, 1); cached_smem[slot] = smem;
     }
@@ -703,13 +753,35 @@ cudaError_t launch_k(const Params &p, cudaStream_t stream)
     if (roll) {
         q.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT, true, false>(smem) * envs_per_cta);
         step_group_kernel<G, FULL, W, MODE, LAT, true, false><<<(unsigned)grid, W * 32, smem, stream>>>(q);
-    } else if (cnt) {
-        q.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT, false, true>(smem) * envs_per_cta);
-        step_group_kernel<G, FULL, W, MODE, LAT, false, true><<<(unsigned)grid, W * 32, smem, stream>>>(q);
-    } else {
-        q.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT, false, false>(smem) * envs_per_cta);
-        step_group_kernel<G, FULL, W, MODE, LAT, false, false><<<(unsigned)grid, W * 32, smem, stream>>>(q);
+        return cudaGetLastError();
     }
+    auto launch_one = [&](const Params &r, auto cnt_c) {
+        constexpr bool C = decltype(cnt_c)::value;
+        Params t = r;
+        t.prefetch_ahead = (int)(resident_ctas<G, FULL, W, MODE, LAT, false, C>(smem) * envs_per_cta);
+        const long long g = (r.E + envs_per_cta - 1) / envs_per_cta;
+        step_group_kernel<G, FULL, W, MODE, LAT, false, C><<<(unsigned)g, W * 32, smem, stream>>>(t);
+    };
+    if constexpr (G == 32) {
+        // Tail splitting.  One warp per environment makes a slot cost `waves x (latency of one environment)`: a batch
+        // that fills the device 1.x times pays for 2.  The whole waves run one warp per environment; the remainder
+        // runs SPLIT_WARPS warps per environment (shorter latency) when those fit the device at once.
+        const long long slots = cnt ? resident_ctas<G, FULL, W, MODE, LAT, false, true>(smem)
+                                    : resident_ctas<G, FULL, W, MODE, LAT, false, false>(smem);
+        const long long full = p.tail_split == 2 ? 0 : (p.E / slots) * slots, rem = p.E - full;
+        const size_t smem_sp = smem_bytes<G>(p, SPLIT_WARPS);
+        const long long slots_sp = cnt ? resident_ctas<G, FULL, SPLIT_WARPS, MODE, LAT, false, true, true>(smem_sp)
+                                       : resident_ctas<G, FULL, SPLIT_WARPS, MODE, LAT, false, false, true>(smem_sp);
+        if (p.tail_split != 0 && rem > 0 && (p.tail_split == 2 || (full > 0 && rem <= slots_sp))) {
+            if (full > 0) { const Params a = env_slice(p, 0, full); if (cnt) launch_one(a, std::true_type{}); else launch_one(a, std::false_type{}); }
+            Params b = env_slice(p, full, rem);
+            b.prefetch_ahead = 0;
+            if (cnt) step_group_kernel<G, FULL, SPLIT_WARPS, MODE, LAT, false, true, true><<<(unsigned)rem, SPLIT_WARPS * 32, smem_sp, stream>>>(b);
+            else step_group_kernel<G, FULL, SPLIT_WARPS, MODE, LAT, false, false, true><<<(unsigned)rem, SPLIT_WARPS * 32, smem_sp, stream>>>(b);
+            return cudaGetLastError();
+        }
+    }
+    if (cnt) launch_one(q, std::true_type{}); else launch_one(q, std::false_type{});
     return cudaGetLastError();
 }
 

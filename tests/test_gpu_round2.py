@@ -268,3 +268,66 @@ def test_partial_groups_keep_the_packed_replay(n, T):
             assert (_np(env.tab_seq) == orc.tab_seq).all() and (_np(env.tab_lu) == orc.tab_lu).all()
             assert (_np(env.tab_x) == orc.tab_x).all()
     env.close()
+
+
+# ---- split environments (tail of a batch that does not fill the device a whole number of times) ----------------------
+
+def _set_tail_split(env, mode):
+    from diral_b200._lib import check
+    check(env.lib.diral_set_option(env._handle, b"tail_split", mode))
+
+
+@pytest.mark.parametrize("name", ["c3_32x20_my_step", "c3_32x20_ch_d3", "c3_32x20_step_design", "c3_32x20_my_step_chanobs",
+                                  "sparse_24x6_L6000_ch", "state_all_blocks_12x4"])
+def test_split_environment_kernel_reproduces_fixtures(name):
+    """tail_split = 2 sends EVERY environment through the 4-warps-per-environment instantiation of the lane-group
+    kernel (17..32 vehicles); the fixtures recorded from the reference must come out the same."""
+    from golden_util import fingerprint_args
+    g, m = load_golden(name)
+    if not 16 < m["num_users"] <= 32:
+        pytest.skip("split environments exist for 32-lane groups only")
+    E = 5
+    env = _env(E, variant="group", **kwargs_from_meta(m))
+    _set_tail_split(env, 2)
+    env.reset(init=(g["x0"], g["y0"], g["v0"]))
+    exact = m["reward_design"] in (1, 2, 5) or all(str(x) == "my_step_design" for x in g["modes"])
+    for t in range(g["actions"].shape[0]):
+        mode = str(g["modes"][t])
+        a = np.broadcast_to(g["actions"][t], (E, env.N))
+        ep, eps = fingerprint_args(m, t)
+        obs, rews = env._step(mode, a, t, True, ep, eps)
+        for e in (0, E - 1):
+            if exact:
+                _eq32(_np(rews)[e], g["rews"][t], "rews", t)
+            else:
+                assert np.allclose(_np(rews)[e], g["rews"][t].astype(np.float32), rtol=1e-6, atol=1e-6)
+            assert np.allclose(_np(obs)[e], g["obs"][t].astype(np.float32), rtol=1e-6, atol=1e-6)
+            assert np.allclose(_np(env._state)[e], g["state"][t].astype(np.float32), rtol=1e-6, atol=1e-6), t
+            assert (_np(env.pos_x)[e] == g["pos_x"][t]).all()
+            if m["add_positional_dist_piggy"]:
+                assert (_np(env.tab_seq)[e] == g["tab_seq"][t]).all() and (_np(env.tab_lu)[e] == g["tab_lu"][t]).all()
+                assert (_np(env.tab_x)[e] == g["tab_x"][t]).all()
+            assert (_np(env.lat)[e] == g["lat"][t]).all(), "last_arrival_time, slot %d" % t
+    env.close()
+
+
+@pytest.mark.parametrize("mode,E", [("my_step", 4096), ("my_step_ch", 4096), ("my_step", 5000), ("my_step_design", 2500)])
+def test_tail_split_launch_is_bit_identical(mode, E):
+    """The default launch (whole waves one warp per environment + the remainder split over 4 warps each) against
+    tail_split = 0 and tail_split = 2 on the same batch: every buffer, table and accumulator identical."""
+    kw = dict(num_users=32, num_channels=20, highway_length=800, reward_design=3 if mode == "my_step_ch" else 2,
+              communication_range=250, mobility=True, bin_range=500, State=_state(add_channel_obs=(E == 5000)))
+    envs = [_env(E, seed=21, **kw) for _ in range(3)]
+    for k, env in enumerate(envs):
+        _set_tail_split(env, k)
+    for t in range(14):
+        for env in envs:
+            env._step(mode, None, t, True)
+        for env in envs[1:]:
+            for name in ("_state", "_rews", "_obs", "_tab_seq", "_tab_lu", "_tab_x", "lat", "pos_x"):
+                assert torch.equal(getattr(envs[0], name), getattr(env, name)), (name, t)
+    m0 = envs[0].episode_metrics()
+    for env in envs[1:]:
+        assert torch.equal(m0, env.episode_metrics())
+    for env in envs:
+        env.close()
