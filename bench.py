@@ -174,6 +174,9 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def reset(self):
+        self.samples, self.reasons = [], set()
+
     def start(self):
         if self.nv:
             self._thread = threading.Thread(target=self._loop, daemon=True)
@@ -291,15 +294,16 @@ def run_gpu(args):
     if world > 1:                                 # communicator set-up is not part of any timed interval
         warm_vec = env.episode_metrics().clone()
         all_reduce_metrics(warm_vec)
+    clocks = ClockSampler(local)
+    clocks.start()                                # (NVML's first queries are slow: they happen during the warm-up)
     for _ in range(warmup):
         flush(); env.step(actions[0])
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     pending = []
-    clocks = ClockSampler(local)
     launches0 = env.launch_count()
     barrier()
-    clocks.start()
+    clocks.reset()                                # only samples taken inside the timed region are reported
     # a short spin kernel lets the host run ahead of the device, so that no timed interval contains the
     # host's own launch latency (with 8 ranks per box the host loop is the slower one at first)
     if hasattr(torch.cuda, "_sleep"):
