@@ -272,6 +272,8 @@ def run_gpu(args):
     steps, warmup = args.steps, max(args.warmup, 3)
 
     env = TestEnv(num_envs=E_PER_GPU, device=dev, seed=1234, env_offset=rank * E_PER_GPU, **ENV_KW)
+    if os.environ.get("DIRAL_TAIL_SPLIT"):        # tuning runs only (scripts/tune_variants.sh)
+        env.lib.diral_set_option(env._handle, b"tail_split", int(os.environ["DIRAL_TAIL_SPLIT"]))
     stream = torch.cuda.current_stream(dev)
     flush_w = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush_r = torch.ones(64 << 20, dtype=torch.float32, device=dev)     # 256 MiB

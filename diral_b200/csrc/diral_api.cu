@@ -65,7 +65,7 @@ struct Handle {
     int host_format = 0;            // 0 = full rows over PCIe, 1 = compact record + host-side row assembly
     int host_threads = 0;           // 0 = pick from the CPUs this process may run on
     int host_chunks = 8;
-    int tail_split = 1;             // see Params::tail_split
+    int tail_split = 0;             // see Params::tail_split (opt-in: it shortens a small tail wave, not a saturated device)
     int host_nt = -1;               // output-row stores: 1 non-temporal, 0 ordinary, -1 by output size per thread
     diral::HostPool *pool = nullptr;
     uint8_t *d_counts = nullptr;    // [E][N][B] device

@@ -675,7 +675,10 @@ size_t smem_bytes(const Params &p, int warps)
 // small groups pack 4 warps so that a CTA still carries a useful number of environments
 template <int G> struct WarpsFor { static constexpr int v = G >= 16 ? DIRAL_GROUP_WARPS : 4; };
 
-constexpr int SPLIT_WARPS = 4;      // warps that share one environment of a batch's tail (one 8-column slab each at 32 vehicles)
+#ifndef DIRAL_SPLIT_WARPS
+#define DIRAL_SPLIT_WARPS 4
+#endif
+constexpr int SPLIT_WARPS = DIRAL_SPLIT_WARPS;      // warps that share one environment of a batch's tail (one 8-column slab each at 32 vehicles)
 
 // the same parameter block restricted to envs [e0, e0 + n) (every per-env array the lane-group kernel touches)
 Params env_slice(const Params &p, long long e0, long long n)

@@ -313,8 +313,9 @@ def test_split_environment_kernel_reproduces_fixtures(name):
 
 @pytest.mark.parametrize("mode,E", [("my_step", 4096), ("my_step_ch", 4096), ("my_step", 5000), ("my_step_design", 2500)])
 def test_tail_split_launch_is_bit_identical(mode, E):
-    """The default launch (whole waves one warp per environment + the remainder split over 4 warps each) against
-    tail_split = 0 and tail_split = 2 on the same batch: every buffer, table and accumulator identical."""
+    """tail_split = 1 (whole waves one warp per environment + the remainder split over 4 warps each, where that remainder
+    fits the device at once) and tail_split = 2 against the default single launch on the same batch: every buffer,
+    table and accumulator identical."""
     kw = dict(num_users=32, num_channels=20, highway_length=800, reward_design=3 if mode == "my_step_ch" else 2,
               communication_range=250, mobility=True, bin_range=500, State=_state(add_channel_obs=(E == 5000)))
     envs = [_env(E, seed=21, **kw) for _ in range(3)]
