@@ -246,7 +246,7 @@ def run_extra_configs(torch, dist, TestEnv, dev, rank, world, flush, peak, slots
                + (8 * n * n if mode == "my_step_ch" else 0)) * E
         row = {"config": name, "envs_per_gpu": E, "mode": mode, "us_per_slot": ms * 1e3,
                "agent_steps_per_s": world * E * n / (ms / 1e3), "roofline_frac": alg / (ms / 1e3) / 1e9 / peak,
-               "kernel": {"group": "step_group_kernel", "block_v1": "step_block_kernel", "row": "step_row_kernel"}[env.kernel]
+               "kernel": {"group": "step_group_kernel", "block_v1": "step_block_kernel", "row": "step_row_kernel", "pair": "step_pair_kernel"}[env.kernel]
                          + ("" if env.lib.diral_get_option(env._handle, b"compact_ok") else " + obtain_state_kernel")}
         if alg < 32e6:
             row["note"] = "launch / latency bound: %.1f MB of state per slot" % (alg / 1e6)

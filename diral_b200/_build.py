@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libdiral_env.so")
-SOURCES = ["diral_api.cu", "diral_step_group.cu", "diral_step_block.cu", "diral_step_row.cu", "diral_aux.cu", "diral_wire.cu",
+SOURCES = ["diral_api.cu", "diral_step_group.cu", "diral_step_block.cu", "diral_step_row.cu", "diral_step_pair.cu", "diral_aux.cu", "diral_wire.cu",
            "diral_host.cpp"]
 HEADERS = [os.path.join(CSRC, "diral_dev.cuh"), os.path.join(CSRC, "diral_launch.h"), os.path.join(CSRC, "diral_host.h"),
            os.path.join(os.path.dirname(HERE), "include", "diral_env.h")]

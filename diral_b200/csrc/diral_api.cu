@@ -38,7 +38,7 @@ int fail(int code, const char *fmt, ...)
             return fail(DIRAL_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
     } while (0)
 
-enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2, VARIANT_BLOCK_V1 = 3, VARIANT_ROW = 4 };
+enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2, VARIANT_BLOCK_V1 = 3, VARIANT_ROW = 4, VARIANT_PAIR = 5 };
 // Measured on B200 (profiles/README.md): the row-layout kernel wins from ~100 vehicles on (1.07x at 128, 1.67x at 256);
 // below that its padded rows (T = 128 for 65..96 vehicles) and per-environment fixed costs lose to round 1's kernel.
 constexpr int ROW_MIN_N = 97;
@@ -51,6 +51,7 @@ struct Handle {
     bool bound = false;
     bool group_ok = false, block_ok = false;   // which slot kernels this configuration's shared-memory carve-up fits
     bool row_ok = false;            // the row-layout kernel (diral_step_row.cu) takes this configuration
+    bool pair_ok = false;           // the two-rows-per-lane warp kernel (diral_step_pair.cu, 33..64 vehicles) does
     int device = 0;
     int variant = VARIANT_AUTO;
     int force_track_lat = 0;
@@ -118,16 +119,23 @@ int check_cfg(const diral_cfg *c)
 
 bool use_group(const Handle *h)
 {
-    if (h->variant == VARIANT_BLOCK || h->variant == VARIANT_BLOCK_V1 || h->variant == VARIANT_ROW) return false;
+    if (h->variant == VARIANT_BLOCK || h->variant == VARIANT_BLOCK_V1 || h->variant == VARIANT_ROW || h->variant == VARIANT_PAIR) return false;
     if (h->variant == VARIANT_AUTO && !h->block_ok) return true;
     return h->group_ok;
 }
 
 // the row-layout kernel is the one-CTA-per-env kernel of choice wherever it applies; VARIANT_BLOCK_V1 pins round 1's
+bool use_pair(const Handle *h)
+{
+    if (!h->pair_ok || use_group(h)) return false;
+    return h->variant == VARIANT_PAIR || h->variant == VARIANT_AUTO || h->variant == VARIANT_BLOCK;
+}
+
 bool use_row(const Handle *h)
 {
-    if (!h->row_ok || use_group(h) || h->variant == VARIANT_BLOCK_V1) return false;
-    return h->variant == VARIANT_ROW || h->cfg.N >= ROW_MIN_N || !h->block_ok;
+    if (!h->row_ok || use_group(h) || h->variant == VARIANT_BLOCK_V1 || h->variant == VARIANT_PAIR) return false;
+    if (h->variant == VARIANT_ROW) return true;
+    return !use_pair(h) && (h->cfg.N >= ROW_MIN_N || !h->block_ok);
 }
 
 bool fused_state_ok(const diral_cfg &c)
@@ -187,7 +195,7 @@ void set_layout(Handle *h)
 
 size_t handle_scratch_bytes(const Handle *h)
 {
-    if (!h->cfg.add_piggy || use_group(h)) return 0;
+    if (!h->cfg.add_piggy || use_group(h) || use_pair(h)) return 0;
     if (use_row(h)) return diral::step_row_scratch_bytes(h->cfg.E, h->cfg.N);
     return diral_scratch_bytes(&h->cfg);
 }
@@ -195,6 +203,7 @@ size_t handle_scratch_bytes(const Handle *h)
 cudaError_t launch_slot(const Handle *h, const diral::Params &p, cudaStream_t s)
 {
     if (use_group(h)) return diral::launch_step_group(p, s);
+    if (use_pair(h)) return diral::launch_step_pair(p, s);
     return use_row(h) ? diral::launch_step_row(p, s) : diral::launch_step_block(p, s);
 }
 
@@ -452,6 +461,8 @@ int diral_create(const diral_cfg *cfg, void **handle)
     h->group_ok = group_fits; h->block_ok = block_fits;
     h->row_ok = diral::step_row_supported(h->base) && diral::step_row_smem_bytes(q) <= (size_t)prop.sharedMemPerBlockOptin;
     if (err == cudaSuccess && h->row_ok) err = diral::prepare_step_row(h->base);
+    h->pair_ok = diral::step_pair_supported(h->base) && diral::step_pair_smem_bytes(h->base) <= (size_t)prop.sharedMemPerBlockOptin;
+    if (err == cudaSuccess && h->pair_ok) err = diral::prepare_step_pair(h->base);
     set_layout(h);
     if (err != cudaSuccess) { cudaFree(h->d_edges); delete h; return fail(DIRAL_ERR_CUDA, "kernel attribute setup: %s", cudaGetErrorString(err)); }
     *handle = h;
@@ -483,7 +494,10 @@ int diral_set_option(void *handle, const char *name, int64_t value)
     Handle *h = as_handle(handle);
     if (!h || !name) return fail(DIRAL_ERR_ARG, "handle/name is NULL");
     if (!strcmp(name, "variant")) {
-        if (value < 0 || value > 4) return fail(DIRAL_ERR_ARG, "variant must be 0 (auto), 1 (group), 2 (block), 3 (round-1 block kernel) or 4 (row layout)");
+        if (value < 0 || value > 5)
+            return fail(DIRAL_ERR_ARG, "variant must be 0 (auto), 1 (group), 2 (block), 3 (round-1 block kernel), 4 (row layout) or 5 (pair)");
+        if (value == VARIANT_PAIR && !h->pair_ok)
+            return fail(DIRAL_ERR_UNSUPPORTED, "the two-rows-per-lane kernel takes 33..64 vehicles");
         if (value == VARIANT_ROW && !h->row_ok)
             return fail(DIRAL_ERR_UNSUPPORTED, "the row-layout kernel takes 33..256 vehicles with neighbour tables and a fused State block");
         if (h->bound) return fail(DIRAL_ERR_ARG, "the kernel variant fixes the table layout: choose it before diral_bind()");
@@ -491,7 +505,7 @@ int diral_set_option(void *handle, const char *name, int64_t value)
             return fail(DIRAL_ERR_ARG, "the group kernel handles num_users <= %d", diral::GROUP_MAX_N);
         if (value == VARIANT_GROUP && !h->group_ok)
             return fail(DIRAL_ERR_UNSUPPORTED, "the group kernel's shared-memory carve-up does not fit at R=%d", h->cfg.R);
-        if ((value == VARIANT_BLOCK && !h->block_ok && !h->row_ok) || (value == VARIANT_BLOCK_V1 && !h->block_ok))
+        if ((value == VARIANT_BLOCK && !h->block_ok && !h->row_ok && !h->pair_ok) || (value == VARIANT_BLOCK_V1 && !h->block_ok))
             return fail(DIRAL_ERR_UNSUPPORTED, "the one-CTA-per-env kernel's shared-memory carve-up does not fit this configuration");
         if (value == VARIANT_AUTO && !h->group_ok) value = VARIANT_BLOCK;
         h->variant = (int)value;
@@ -540,7 +554,7 @@ int64_t diral_get_option(void *handle, const char *name)
     Handle *h = as_handle(handle);
     if (!h || !name) return -1;
     if (!strcmp(name, "variant")) return use_group(h) ? VARIANT_GROUP : VARIANT_BLOCK;
-    if (!strcmp(name, "kernel")) return use_group(h) ? 1 : (use_row(h) ? 3 : 2);      // 1 lane-group, 2 round-1 block, 3 row layout
+    if (!strcmp(name, "kernel")) return use_group(h) ? 1 : (use_pair(h) ? 4 : (use_row(h) ? 3 : 2));   // 1 lane-group, 2 round-1 block, 3 row layout, 4 pair
     if (!strcmp(name, "layout")) return h->base.layout;
     if (!strcmp(name, "row_stride")) return h->base.T;
     if (!strcmp(name, "ring_depth")) return h->base.H;

@@ -25,6 +25,12 @@ size_t step_block_scratch_words_per_env(int N);
 cudaError_t prepare_step_block(const Params &p);
 cudaError_t launch_step_block(const Params &p, cudaStream_t stream);
 
+// 33 <= N <= 64: one warp per environment, two table rows per lane (diral_step_pair.cu); subject-major layout like the group kernel
+bool step_pair_supported(const Params &p);
+size_t step_pair_smem_bytes(const Params &p);
+cudaError_t prepare_step_pair(const Params &p);
+cudaError_t launch_step_pair(const Params &p, cudaStream_t stream);
+
 // 32 < N <= 256, ROW layout: observer-major tables, positions in a ring, receiver-centric merges (diral_step_row.cu)
 bool step_row_supported(const Params &p);
 int step_row_stride(int N);             // T: padded row stride of the tables

@@ -127,9 +127,9 @@ class TestEnv:
         with torch.cuda.device(self.device):
             check(self.lib.diral_create(C.byref(self.cfg), C.byref(self._handle)))
         if variant != "auto":
-            check(self.lib.diral_set_option(self._handle, b"variant", {"group": 1, "block": 2, "block_v1": 3, "row": 4}[variant]))
+            check(self.lib.diral_set_option(self._handle, b"variant", {"group": 1, "block": 2, "block_v1": 3, "row": 4, "pair": 5}[variant]))
         # which kernel runs and how it wants its tables laid out (include/diral_env.h, "Table layouts")
-        self.kernel = {1: "group", 2: "block_v1", 3: "row"}[int(self.lib.diral_get_option(self._handle, b"kernel"))]
+        self.kernel = {1: "group", 2: "block_v1", 3: "row", 4: "pair"}[int(self.lib.diral_get_option(self._handle, b"kernel"))]
         self.layout = int(self.lib.diral_get_option(self._handle, b"layout"))
         self.T = int(self.lib.diral_get_option(self._handle, b"row_stride"))
         self.H = int(self.lib.diral_get_option(self._handle, b"ring_depth"))

@@ -17,9 +17,9 @@ pytestmark = pytest.mark.gpu
 
 def _env(E, variant="auto", **kw):
     from diral_b200 import DiralError, TestEnv
-    if variant == "row":          # where the row-layout kernel does not apply (un-fused State blocks, no tables, R > 256)
-        try:                      # the configuration is covered by round 1's kernel
-            return TestEnv(num_envs=E, device="cuda", variant="row", **kw)
+    if variant in ("row", "pair"):   # where the kernel does not apply (row: un-fused State blocks, no tables, R > 256;
+        try:                         # pair: resource counts beyond its shared memory) round 1's kernel covers the case
+            return TestEnv(num_envs=E, device="cuda", variant=variant, **kw)
         except DiralError as exc:
             assert exc.code == -5, exc
             variant = "block_v1"
@@ -44,7 +44,7 @@ def _close32(got, ref64, what, t, exact=False):
 def _variants(n):
     # one CTA per environment: round 1's kernel ("block_v1") and the row-layout kernel ("row": 33..256 vehicles, fused
     # State block; TestEnv falls back to block_v1 where it does not apply)
-    return ["group", "block"] if n <= 32 else ["block_v1", "row"]
+    return ["group", "block"] if n <= 32 else (["block_v1", "row", "pair"] if n <= 64 else ["block_v1", "row"])
 
 
 def _cases():
