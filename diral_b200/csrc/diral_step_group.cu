@@ -678,6 +678,7 @@ template <int G> struct WarpsFor { static constexpr int v = G >= 16 ? DIRAL_GROU
 #ifndef DIRAL_SPLIT_WARPS
 #define DIRAL_SPLIT_WARPS 4
 #endif
+constexpr size_t SPLIT_SMEM_LIMIT = 227 * 1024;
 constexpr int SPLIT_WARPS = DIRAL_SPLIT_WARPS;      // warps that share one environment of a batch's tail (one 8-column slab each at 32 vehicles)
 
 // the same parameter block restricted to envs [e0, e0 + n) (every per-env array the lane-group kernel touches)
@@ -712,11 +713,11 @@ cudaError_t prepare_k(const Params &p)
     err = cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, true, false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if constexpr (G == 32) {
-        const size_t smem_sp = smem_bytes<G>(q, SPLIT_WARPS);
-        if (err == cudaSuccess && smem_sp > 48 * 1024)
+        const size_t smem_sp = smem_bytes<G>(q, SPLIT_WARPS);          // (beyond the limit: launch_k never splits)
+        if (err == cudaSuccess && smem_sp > 48 * 1024 && smem_sp <= SPLIT_SMEM_LIMIT)
             err = cudaFuncSetAttribute(step_group_kernel<G, FULL, SPLIT_WARPS, MODE, LAT, false, false, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);
-        if (err == cudaSuccess && smem_sp > 48 * 1024)
+        if (err == cudaSuccess && smem_sp > 48 * 1024 && smem_sp <= SPLIT_SMEM_LIMIT)
             err = cudaFuncSetAttribute(step_group_kernel<G, FULL, SPLIT_WARPS, MODE, LAT, false, true, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);
     }
@@ -765,7 +766,7 @@ cudaError_t launch_k(const Params &p, cudaStream_t stream)
         const long long g = (r.E + envs_per_cta - 1) / envs_per_cta;
         step_group_kernel<G, FULL, W, MODE, LAT, false, C><<<(unsigned)g, W * 32, smem, stream>>>(t);
     };
-    if constexpr (G == 32) {
+    if constexpr (G == 32) if (p.tail_split != 0 && smem_bytes<G>(p, SPLIT_WARPS) <= SPLIT_SMEM_LIMIT) {
         // Tail splitting.  One warp per environment makes a slot cost `waves x (latency of one environment)`: a batch
         // that fills the device 1.x times pays for 2.  The whole waves run one warp per environment; the remainder
         // runs SPLIT_WARPS warps per environment (shorter latency) when those fit the device at once.

@@ -39,7 +39,7 @@ constexpr unsigned PFULL = 0xffffffffu;
 __host__ __device__ inline int align16p(int x) { return (x + 15) & ~15; }
 
 struct PairSmem {
-    int off_sx, off_sy, off_sa, off_txm, off_passof, off_recv, off_script, off_obs, off_hist, off_colx, off_edges, bytes;
+    int off_sx, off_sy, off_sa, off_txm, off_passof, off_recv, off_script, off_hist, off_colx, off_edges, bytes;
     __host__ __device__ PairSmem(int R, int B, bool vpd)
     {
         int o = 0;
@@ -52,7 +52,6 @@ struct PairSmem {
         off_txm = o;    o += align16p(8 * R);              // two words per resource
         off_passof = o; o += align16p(2 * R);              // index of a resource among the non-empty ones
         off_script = o; o += align16p(PV * R);             // [pass][row]
-        off_obs = o;    o += align16p(4 * PV * R);         // [row][R], same layout as global
         off_hist = o;   o += vpd ? align16p(4 * PV * (B + 1)) : 0;     // [bin][row], + 1 dummy bin
         bytes = o;
     }
@@ -94,12 +93,14 @@ __device__ __forceinline__ void pair_red_inc(unsigned *addr)
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(addr)));
 }
 
-template <int MODE>
+// FULL (N == 64) drops every "does this row / column exist" predicate and turns the table strides into constants.
+template <int MODE, bool FULL>
 __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
 {
     const int u = threadIdx.x;
     const long long e = blockIdx.x;
-    const int N = p.N, R = p.R, B = p.B, S = p.S;
+    const int N = FULL ? PV : p.N;
+    const int R = p.R, B = p.B, S = p.S;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const bool want_state = p.build_state != 0;
     const bool vpd = want_state && p.vpd_enabled;
@@ -113,12 +114,12 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
     unsigned *txm_s = reinterpret_cast<unsigned *>(smem_raw + lay.off_txm);               // [R][2]
     unsigned short *passof = reinterpret_cast<unsigned short *>(smem_raw + lay.off_passof);
     unsigned char *script = smem_raw + lay.off_script;                                    // [pass][64]
-    float *obsS = reinterpret_cast<float *>(smem_raw + lay.off_obs);
+    float *obsS = p.obs + e * (long long)N * R;                                           // [row][R], written in place (L1 / L2 resident)
     unsigned *hist = reinterpret_cast<unsigned *>(smem_raw + lay.off_hist);               // [B + 1][64]
 
     const bool lat_on = p.track_lat != 0 && p.lat != nullptr;
     const long long vbase = e * N, tbase = e * (long long)N * N;
-    const bool act1 = u + 32 < N;             // row u always exists (N > 32)
+    const bool act1 = FULL ? true : (u + 32 < N);   // row u always exists (N > 32)
     const long long timestep = p.timestep;
     const int tick = p.tick;
     const double Cr = p.C, sentinel = p.sentinel;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
     }
     // who is within communication range of my two vehicles (Network.check_communicaiton_range, network.py:595-607)
     unsigned inr[2][2] = {{0u, 0u}, {0u, 0u}};
-    const unsigned live1 = N >= 64 ? PFULL : ((1u << (N - 32)) - 1u);
+    const unsigned live1 = (FULL || N >= 64) ? PFULL : ((1u << (N - 32)) - 1u);
     auto in_range_masks = [&](auto flat_c) {
         constexpr bool FL = decltype(flat_c)::value;
 #pragma unroll 4
@@ -341,26 +342,30 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
         const int age_thr = p.age_threshold;
         constexpr int FMAX = (1 << (16 - PSB)) - 1;
         const int base = tick - FMAX;
-#pragma unroll 1
-        for (int jbase = 0; jbase < N; jbase += PSL) {
-            int sb[2][PSL], lb[2][PSL]; double xb[2][PSL];
-            unsigned oldest = 0xffffffffu;
+        auto load_slab = [&](int jb, int (&sbn)[2][PSL], int (&lbn)[2][PSL], double (&xbn)[2][PSL]) {
 #pragma unroll
             for (int q = 0; q < PSL; ++q) {
-                const int j = jbase + q;
+                const int j = jb + q;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int i = u + 32 * h;
-                    const bool ok = j < N && (h == 0 || act1);
-                    if (ok) { sb[h][q] = seqg[j * N + i]; lb[h][q] = lug[j * N + i]; xb[h][q] = xg[j * N + i]; }
-                    else { sb[h][q] = 0; lb[h][q] = 0; xb[h][q] = 0.0; }
+                    const bool ok = FULL || (j < N && (h == 0 || act1));
+                    if (ok) { sbn[h][q] = seqg[j * N + i]; lbn[h][q] = lug[j * N + i]; xbn[h][q] = xg[j * N + i]; }
+                    else { sbn[h][q] = 0; lbn[h][q] = 0; xbn[h][q] = 0.0; }
                 }
             }
+        };
+        // one slab: `sb, lb, xb` hold its entries (loaded one slab earlier); the next slab's loads are issued into
+        // `sbn, lbn, xbn` before the replay loop, whose latency chain hides them
+        auto do_slab = [&](int jbase, int (&sb)[2][PSL], int (&lb)[2][PSL], double (&xb)[2][PSL],
+                           int (&sbn)[2][PSL], int (&lbn)[2][PSL], double (&xbn)[2][PSL]) {
+            unsigned oldest = 0xffffffffu;
+            if (jbase + PSL < N) load_slab(jbase + PSL, sbn, lbn, xbn);
 #pragma unroll
             for (int q = 0; q < PSL; ++q)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    if (jbase + q == u + 32 * h && (h == 0 || act1)) sb[h][q] += 1;        // vehicle.py:58 (tick)
+                    if (jbase + q == u + 32 * h && (FULL || h == 0 || act1)) sb[h][q] += 1;        // vehicle.py:58 (tick)
                     oldest = min(oldest, (unsigned)(sb[h][q] - 1));
                 }
             const bool narrow = base <= 0 || oldest >= (unsigned)base;
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int i = u + 32 * h;
-                    if (j < N && (h == 0 || act1)) { seqg[j * N + i] = sb[h][q]; lug[j * N + i] = lb[h][q]; xg[j * N + i] = xb[h][q]; }
+                    if (FULL || (j < N && (h == 0 || act1))) { seqg[j * N + i] = sb[h][q]; lug[j * N + i] = lb[h][q]; xg[j * N + i] = xb[h][q]; }
                 }
             }
             if (vpd) {
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int i = u + 32 * h;
-                            bool in = j < N && (h == 0 || act1) && j != i && lb[h][q] < age_thr;      // network.py:547
+                            bool in = (FULL || (j < N && (h == 0 || act1))) && j != i && lb[h][q] < age_thr;      // network.py:547
                             double sv;
                             if (FL0) { sv = __dsub_rn(xb[h][q], x_new[h]); in = in && fabs(sv) < W; }  // network.py:487
                             else {
@@ -482,6 +487,13 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
                                 pair_red_inc(&hist[vpd_bin(xb[h][q], W, inv_binw, B, s_edges) * PV + u + 32 * h]);
                 }
             }
+        };
+        int sbA[2][PSL], lbA[2][PSL], sbB[2][PSL], lbB[2][PSL]; double xbA[2][PSL], xbB[2][PSL];
+        load_slab(0, sbA, lbA, xbA);
+#pragma unroll 1
+        for (int jbase = 0; jbase < N; jbase += 2 * PSL) {
+            do_slab(jbase, sbA, lbA, xbA, sbB, lbB, xbB);
+            if (jbase + PSL < N) do_slab(jbase + PSL, sbB, lbB, xbB, sbA, lbA, xbA);
         }
     }
 
@@ -525,7 +537,7 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
                 for (; r < R; ++r) *wp++ = (ai == r) ? 1.0f : 0.0f;
             } else *wp++ = (float)ai;
         }
-        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) *wp++ = obsS[i * R + r]; }
+        if (p.add_channel_obs) { for (int r = 0; r < R; ++r) *wp++ = __ldcg(obsS + i * R + r); }
         if (p.piggy) {
             const float den = (float)m_cnt[h], rcp = __frcp_rn(den);
             const bool have = vpd && m_cnt[h] > 0;
@@ -543,13 +555,6 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
         if (p.add_velocity) *wp++ = (float)v[h];
         if (p.fingerprint) { *wp++ = (float)p.episode; *wp++ = (float)p.epsilon; }
     }
-    // coalesced copy-out of the [N][R] observation block
-    {
-        float *dst = p.obs + vbase * R;
-        const int n = N * R;
-        if ((n & 3) == 0) { for (int k = u; k < n / 4; k += 32) reinterpret_cast<float4 *>(dst)[k] = reinterpret_cast<const float4 *>(obsS)[k]; }
-        else { for (int k = u; k < n; k += 32) dst[k] = obsS[k]; }
-    }
 }
 
 size_t pair_smem(const Params &p) { return (size_t)PairSmem(p.R, p.B, p.vpd_enabled != 0).bytes; }
@@ -558,7 +563,16 @@ template <int MODE>
 cudaError_t pair_prepare(size_t smem)
 {
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(step_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = cudaFuncSetAttribute(step_pair_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(step_pair_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return err;
+}
+
+template <int MODE>
+void pair_launch(const Params &p, size_t smem, cudaStream_t stream)
+{
+    if (p.N == PV) step_pair_kernel<MODE, true><<<(unsigned)p.E, 32, smem, stream>>>(p);
+    else step_pair_kernel<MODE, false><<<(unsigned)p.E, 32, smem, stream>>>(p);
 }
 
 }  // namespace
@@ -584,10 +598,9 @@ cudaError_t prepare_step_pair(const Params &p)
 cudaError_t launch_step_pair(const Params &p, cudaStream_t stream)
 {
     const size_t smem = pair_smem(p);
-    const unsigned grid = (unsigned)p.E;
-    if (p.mode == MODE_STEP) step_pair_kernel<MODE_STEP><<<grid, 32, smem, stream>>>(p);
-    else if (p.mode == MODE_DESIGN) step_pair_kernel<MODE_DESIGN><<<grid, 32, smem, stream>>>(p);
-    else step_pair_kernel<MODE_CH><<<grid, 32, smem, stream>>>(p);
+    if (p.mode == MODE_STEP) pair_launch<MODE_STEP>(p, smem, stream);
+    else if (p.mode == MODE_DESIGN) pair_launch<MODE_DESIGN>(p, smem, stream);
+    else pair_launch<MODE_CH>(p, smem, stream);
     return cudaGetLastError();
 }
 
