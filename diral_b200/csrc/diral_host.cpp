@@ -145,10 +145,80 @@ inline void expand_rows_vector_impl(const HostLayout &lay, const HostJob &job, l
     if (NT) _mm_sfence();
 }
 
+
+// AVX2 + FMA flavour of the same row assembly: eight floats per step (one 4-float step closes a block whose length is
+// 4 mod 8), the sample count from one SAD over the count bytes, bytes widened with one VPMOVZXBD.
+// a block may start 16 (not 32) bytes into a row: 32-byte non-temporal stores need 32-byte addresses
+template <bool NT>
+DIRAL_TARGET_FMA inline void store8_avx(float *d, __m256 v, bool rows32)
+{
+    if (!NT) _mm256_storeu_ps(d, v);
+    else if (rows32 && (reinterpret_cast<uintptr_t>(d) & 31) == 0) _mm256_stream_ps(d, v);
+    else { _mm_stream_ps(d, _mm256_castps256_ps128(v)); _mm_stream_ps(d + 4, _mm256_extractf128_ps(v, 1)); }
+}
+
+template <bool NT>
+DIRAL_TARGET_FMA void expand_rows_avx2(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
+{
+    const int R = lay.R, B = lay.B, S = lay.S;
+    const __m256i lane8 = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7), eight = _mm256_set1_epi32(8);
+    const __m256i one8 = _mm256_castps_si256(_mm256_set1_ps(1.0f));
+    const __m128i one4 = _mm_castps_si128(_mm_set1_ps(1.0f));
+    const bool rows32 = ((reinterpret_cast<uintptr_t>(job.out) | (uintptr_t)(4 * S)) & 31) == 0;   // every row 32-byte aligned
+    for (long long a = a0; a < a1; ++a) {
+        float *w = job.out + a * S;
+        if (job.rews_out) job.rews_out[a] = rew_at(job, a);
+#define store8(d, v) store8_avx<NT>((d), (v), rows32)
+        if (lay.add_action) {
+            int act = job.actions[a];
+            act = act < 0 ? 0 : (act >= R ? R - 1 : act);
+            const __m256i av = _mm256_set1_epi32(act);
+            __m256i idx = lane8;
+            int r = 0;
+            for (; r + 8 <= R; r += 8, w += 8) {
+                store8(w, _mm256_castsi256_ps(_mm256_and_si256(_mm256_cmpeq_epi32(idx, av), one8)));
+                idx = _mm256_add_epi32(idx, eight);
+            }
+            if (r < R) { put4<NT>(w, _mm_and_si128(_mm_cmpeq_epi32(_mm256_castsi256_si128(idx), _mm256_castsi256_si128(av)), one4)); w += 4; }
+        }
+        if (lay.add_channel_obs) {
+            const float *o = job.obs + a * R;
+            int r = 0;
+            for (; r + 8 <= R; r += 8, w += 8) store8(w, _mm256_loadu_ps(o + r));
+            if (r < R) { put4<NT>(w, _mm_castps_si128(_mm_loadu_ps(o + r))); w += 4; }
+        }
+        if (lay.piggy) {
+            const uint8_t *c = job.counts + a * job.count_stride;
+            // len(s): sum of the B count bytes (SAD against zero, 16 / 8 / 4 bytes at a time)
+            __m128i acc = _mm_setzero_si128();
+            int b = 0;
+            for (; b + 16 <= B; b += 16) acc = _mm_add_epi64(acc, _mm_sad_epu8(_mm_loadu_si128(reinterpret_cast<const __m128i *>(c + b)), _mm_setzero_si128()));
+            for (; b + 8 <= B; b += 8) acc = _mm_add_epi64(acc, _mm_sad_epu8(_mm_loadl_epi64(reinterpret_cast<const __m128i *>(c + b)), _mm_setzero_si128()));
+            for (; b < B; b += 4) { int word; std::memcpy(&word, c + b, 4); acc = _mm_add_epi64(acc, _mm_sad_epu8(_mm_cvtsi32_si128(word), _mm_setzero_si128())); }
+            int m = _mm_cvtsi128_si32(acc) + _mm_extract_epi16(acc, 4);
+            // len == 0: every count is 0 too; dividing by 1 leaves the all-zero vector (network.py:502-505)
+            const float denf = (float)(m > 0 ? m : 1);
+            const __m256 den = _mm256_set1_ps(denf), rcp = _mm256_set1_ps(1.0f / denf);
+            for (b = 0; b + 8 <= B; b += 8, w += 8) {
+                const __m256 cf = _mm256_cvtepi32_ps(_mm256_cvtepu8_epi32(_mm_loadl_epi64(reinterpret_cast<const __m128i *>(c + b))));
+                const __m256 q0 = _mm256_mul_ps(cf, rcp);
+                store8(w, _mm256_fmadd_ps(_mm256_fnmadd_ps(q0, den, cf), rcp, q0));
+            }
+            if (b < B) {
+                int word; std::memcpy(&word, c + b, 4);
+                const __m128 cf = _mm_cvtepi32_ps(_mm_cvtepu8_epi32(_mm_cvtsi32_si128(word)));
+                const __m128 q0 = _mm_mul_ps(cf, _mm256_castps256_ps128(rcp));
+                put4<NT>(w, _mm_castps_si128(_mm_fmadd_ps(_mm_fnmadd_ps(q0, _mm256_castps256_ps128(den), cf), _mm256_castps256_ps128(rcp), q0)));
+                w += 4;
+            }
+        }
+    }
+    if (NT) _mm_sfence();
+#undef store8
+}
+
 void rows_sse_nt(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<true, false>(l, j, a0, a1); }
 void rows_sse_st(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<false, false>(l, j, a0, a1); }
-DIRAL_TARGET_FMA void rows_fma_nt(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<true, true>(l, j, a0, a1); }
-DIRAL_TARGET_FMA void rows_fma_st(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<false, true>(l, j, a0, a1); }
 
 bool cpu_has_fma()
 {
@@ -161,7 +231,7 @@ bool cpu_has_fma()
 void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
 {
     if (vector_rows_ok(lay, job)) {
-        if (cpu_has_fma()) { if (lay.nt_stores) rows_fma_nt(lay, job, a0, a1); else rows_fma_st(lay, job, a0, a1); }
+        if (cpu_has_fma()) { if (lay.nt_stores) expand_rows_avx2<true>(lay, job, a0, a1); else expand_rows_avx2<false>(lay, job, a0, a1); }
         else { if (lay.nt_stores) rows_sse_nt(lay, job, a0, a1); else rows_sse_st(lay, job, a0, a1); }
         return;
     }
