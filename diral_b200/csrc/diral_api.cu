@@ -63,7 +63,9 @@ struct Handle {
     cudaStream_t pipe[2] = {nullptr, nullptr};   // diral_step_host: env chunks alternate between these
     cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
     // compact host format of diral_step_host (see diral_host.h)
-    int host_format = 0;            // 0 = full rows over PCIe, 1 = compact record + host-side row assembly
+    int host_format = 0;            // 0 = full rows over PCIe, 1 = compact record + host-side row assembly,
+                                    // 2 = the same, records written by the kernel straight into mapped host memory
+    uint8_t *d_counts_mapped = nullptr;   // device address of h_counts (mapped pinned allocation)
     int host_threads = 0;           // 0 = pick from the CPUs this process may run on
     int host_chunks = 8;
     int tail_split = 0;             // see Params::tail_split (opt-in: it shortens a small tail wave, not a saturated device)
@@ -319,8 +321,12 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     const bool want_obs = c.add_channel_obs != 0, want_kin = c.add_position || c.add_velocity;
     if (!h->d_counts) {
         DIRAL_CUDA(cudaMalloc(&h->d_counts, (size_t)(A * rec)));
-        DIRAL_CUDA(cudaMallocHost(&h->h_counts, (size_t)(A * rec)));
+        DIRAL_CUDA(cudaHostAlloc(&h->h_counts, (size_t)(A * rec), cudaHostAllocMapped));
+        DIRAL_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_counts_mapped), h->h_counts, 0));
     }
+    // zero-copy: the lane-group kernel stages an environment's records in shared memory and writes them out as one
+    // coalesced stream, so they can go over PCIe as the kernel runs instead of through a copy engine afterwards
+    const bool zero_copy = h->host_format == 2 && group && h->d_counts_mapped != nullptr;
     if (want_obs && !h_obs && !h->h_obs_stage) DIRAL_CUDA(cudaMallocHost(&h->h_obs_stage, sizeof(float) * (size_t)(A * R)));
     if (want_kin && !h->h_kin) DIRAL_CUDA(cudaMallocHost(&h->h_kin, sizeof(double) * (size_t)(3 * A)));
     const int chunks = E >= 1024 ? h->host_chunks : 1;
@@ -339,7 +345,7 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     p.mode = mode; p.timestep = timestep; p.episode = episode; p.epsilon = epsilon; p.seed = 0;
     p.tick = (int)(h->ticks + 1);
     p.build_state = 1; p.actions = h->d_actions; p.gen_actions = 0; p.actions_out = nullptr;
-    p.vpd_counts = h->d_counts; p.rec_stride = (int)rec;
+    p.vpd_counts = zero_copy ? h->d_counts_mapped : h->d_counts; p.rec_stride = (int)rec;
     if (mode == DIRAL_MY_STEP_CH && h->bufs.lat) h->lat_live = true;
     p.track_lat = (h->bufs.lat && (h->lat_live || h->force_track_lat)) ? 1 : 0;
 
@@ -369,7 +375,8 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         const diral::Params q = env_range(p, e0, n / N);
         DIRAL_CUDA(launch_slot(h, q, ps));
         h->launches += 1;
-        DIRAL_CUDA(cudaMemcpyAsync(h->h_counts + a0 * rec, h->d_counts + a0 * rec, (size_t)(n * rec), cudaMemcpyDeviceToHost, ps));
+        if (!zero_copy)
+            DIRAL_CUDA(cudaMemcpyAsync(h->h_counts + a0 * rec, h->d_counts + a0 * rec, (size_t)(n * rec), cudaMemcpyDeviceToHost, ps));
         if (h_obs || want_obs)
             DIRAL_CUDA(cudaMemcpyAsync(obs_dst + a0 * R, h->bufs.obs + a0 * R, (size_t)(n * R) * sizeof(float), cudaMemcpyDeviceToHost, ps));
         if (c.add_position) {
@@ -514,7 +521,7 @@ int diral_set_option(void *handle, const char *name, int64_t value)
     }
     if (!strcmp(name, "track_lat")) { h->force_track_lat = value != 0; return DIRAL_OK; }
     if (!strcmp(name, "host_format")) {
-        if (value != 0 && value != 1) return fail(DIRAL_ERR_ARG, "host_format must be 0 (full rows) or 1 (compact)");
+        if (value < 0 || value > 2) return fail(DIRAL_ERR_ARG, "host_format must be 0 (full rows), 1 (compact) or 2 (compact, zero-copy records)");
         h->host_format = (int)value;
         return DIRAL_OK;
     }
@@ -835,7 +842,7 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
     if (int rc = ensure_actions_staging(h)) return rc;
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (h->host_format == 1 && compact_ok(h->cfg))
+    if (h->host_format >= 1 && compact_ok(h->cfg))
         return step_host_compact(h, mode, h_actions, timestep, episode, epsilon, h_state, h_rews, h_obs, s);
     const long long E = h->cfg.E, N = h->cfg.N, R = h->cfg.R, S = h->base.S;
     // Envs are independent, so the batch is cut into chunks that alternate between two internal

@@ -71,8 +71,8 @@ __host__ __device__ inline bool group_direct_rows(const Params &p)
 }
 
 struct GroupSmem {
-    int off_sx, off_sy, off_script, off_txm, off_recv, off_mcnt, off_obs, off_hist, off_st, bytes;
-    __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd, bool direct)
+    int off_sx, off_sy, off_script, off_txm, off_recv, off_mcnt, off_obs, off_hist, off_st, off_rec, bytes;
+    __host__ __device__ GroupSmem(int G, int R, int B, int S, bool state, bool vpd, bool direct, int rec_stride)
     {
         int o = 0;
         off_script = o; o += align16i(G * (R + 1));    // merge script: one byte per (pass, lane), + 1 spare row
@@ -84,6 +84,7 @@ struct GroupSmem {
         off_obs = o;  o += align16i(4 * G * R);
         off_hist = o; o += (state && vpd) ? align16i(4 * G * (B + 1)) : 0;   // + 1 dummy row
         off_st = o;   o += (state && !direct) ? align16i(4 * G * S) : 0;
+        off_rec = o;  o += align16i(G * rec_stride);   // compact host records of this environment (one coalesced copy-out)
         bytes = o;
     }
 };
@@ -182,7 +183,7 @@ step_group_kernel(const Params p)
     const bool want_state = p.build_state != 0;
     const bool vpd = want_state && p.vpd_enabled;
     const bool direct = group_direct_rows(p);
-    const GroupSmem lay(G, R, B, S, want_state, p.vpd_enabled, direct);
+    const GroupSmem lay(G, R, B, S, want_state, p.vpd_enabled, direct, (CNT && p.vpd_counts) ? p.rec_stride : 0);
     unsigned char *gbase = smem_raw + align16i(8 * (B + 1)) + (size_t)(warp * EPW + sub) * lay.bytes;
     double *sx = reinterpret_cast<double *>(gbase + lay.off_sx);
     double *sy = reinterpret_cast<double *>(gbase + lay.off_sy);
@@ -194,6 +195,7 @@ step_group_kernel(const Params p)
     unsigned *hist = reinterpret_cast<unsigned *>(gbase0 + lay.off_hist);
     unsigned *mcnt_s = reinterpret_cast<unsigned *>(gbase0 + lay.off_mcnt);
     float *st = reinterpret_cast<float *>(gbase + lay.off_st);         // [N][S], rows rotated (see F)
+    unsigned char *recS = gbase + lay.off_rec;                         // [N][rec_stride] (CNT)
 
     const bool act = FULL ? true : (u < N);
     const long long vbase = e * N;           // first vehicle of this env in the [E][N] arrays
@@ -588,7 +590,7 @@ step_group_kernel(const Params p)
         }
     }
     if (act) p.rews[vbase + u] = (float)rew;
-    if (CNT && act) *reinterpret_cast<float *>(p.vpd_counts + (vbase + u + 1) * p.rec_stride - 4) = (float)rew;
+    if (CNT && act) *reinterpret_cast<float *>(recS + (u + 1) * p.rec_stride - 4) = (float)rew;
 
     // ---- F: state rows (TestEnv.obtain_state) in shared memory -----------------------------------
     // Row u sits at st[u*S .. u*S+S) exactly as in global memory, so the copy-out is a plain
@@ -618,7 +620,7 @@ step_group_kernel(const Params p)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) hv[i] = (have && b0 + i < B) ? hist[(b0 + i) * G + u] : 0u;
                 if (CNT) {                           // compact host format: the counts themselves, one byte per bin
-                    unsigned char *cp = p.vpd_counts + (vbase + u) * p.rec_stride + b0;
+                    unsigned char *cp = recS + u * p.rec_stride + b0;
                     if ((B & 3) == 0) {
                         *reinterpret_cast<unsigned *>(cp) = hv[0] | (hv[1] << 8) | (hv[2] << 16) | (hv[3] << 24);
                         if (b0 + 4 < B) *reinterpret_cast<unsigned *>(cp + 4) = hv[4] | (hv[5] << 8) | (hv[6] << 16) | (hv[7] << 24);
@@ -660,6 +662,8 @@ step_group_kernel(const Params p)
     };
     copy_out(p.obs + vbase * R, obsS, N * R);
     if (want_state && !direct) copy_out(p.state + vbase * S, st, N * S);
+    // the environment's host records leave as one contiguous stream (they may sit in mapped host memory: 16-byte pieces)
+    if (CNT) copy_out(reinterpret_cast<float *>(p.vpd_counts + vbase * p.rec_stride), reinterpret_cast<const float *>(recS), N * (p.rec_stride >> 2));
     __syncwarp(gmask);                       // the next slot reuses the shared-memory staging
     }   // slot
 }
@@ -667,7 +671,7 @@ step_group_kernel(const Params p)
 template <int G>
 size_t smem_bytes(const Params &p, int warps)
 {
-    const GroupSmem lay(G, p.R, p.B, p.S, p.build_state != 0, p.vpd_enabled != 0, group_direct_rows(p));
+    const GroupSmem lay(G, p.R, p.B, p.S, p.build_state != 0, p.vpd_enabled != 0, group_direct_rows(p), p.vpd_counts ? p.rec_stride : 0);
     return (size_t)align16i(8 * (p.B + 1)) + (size_t)warps * (32 / G) * lay.bytes;
 }
 
@@ -701,7 +705,8 @@ Params env_slice(const Params &p, long long e0, long long n)
 template <int G, bool FULL, int MODE, bool LAT>
 cudaError_t prepare_k(const Params &p)
 {
-    Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for
+    Params q = p; q.build_state = 1;         // the largest carve-up this configuration can ask for (host records included)
+    q.vpd_counts = reinterpret_cast<uint8_t *>(1); q.rec_stride = (((p.piggy ? p.B : 0) + 3) & ~3) + 4;
     const size_t smem = smem_bytes<G>(q, WarpsFor<G>::v);
     if (smem <= 48 * 1024) return cudaSuccess;
     cudaError_t err = cudaFuncSetAttribute(step_group_kernel<G, FULL, WarpsFor<G>::v, MODE, LAT, false, false>,

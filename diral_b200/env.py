@@ -204,9 +204,9 @@ class TestEnv:
         PCIe; ``"compact"`` copies only what the host cannot know (VPD bin counts as bytes, rewards, ...) and lets
         ``host_threads`` library threads assemble the same rows in the caller's buffer (include/diral_env.h).
         ``host_threads=None``: the CPUs this process may use, shared between the ranks of a torchrun job."""
-        if host_format not in ("full", "compact"):
-            raise ValueError("host_format must be 'full' or 'compact'")
-        check(self.lib.diral_set_option(self._handle, b"host_format", int(host_format == "compact")))
+        if host_format not in ("full", "compact", "compact_zero_copy"):
+            raise ValueError("host_format must be 'full', 'compact' or 'compact_zero_copy'")
+        check(self.lib.diral_set_option(self._handle, b"host_format", {"full": 0, "compact": 1, "compact_zero_copy": 2}[host_format]))
         if host_threads is None:
             import os
             cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)

@@ -115,8 +115,8 @@ def main():
     out["step_host"].append(step_host(env, "full", 1, 4, h_act, h_state, h_rews))
     for th in sorted({8, 12, max(cpus - 3, 1), max(cpus - 2, 1)}):
         for ch in (2, 4, 8, 16):
-            for nt in (0, 1):
-                out["step_host"].append(step_host(env, "compact", th, ch, h_act, h_state, h_rews, nt))
+            for fmt in ("compact", "compact_zero_copy"):
+                out["step_host"].append(step_host(env, fmt, th, ch, h_act, h_state, h_rews, 0))
     print(json.dumps(out, indent=1))
 
 

@@ -156,6 +156,7 @@ def test_compact_host_format_is_bit_identical(n, r, E, state, extra):
         s, rw, info = dev.step(a, episode_number=t // 3, epsilon=0.5 ** t)
         full.step_host(ha, *bufs[0], episode_number=t // 3, epsilon=0.5 ** t)
         comp.lib.diral_set_option(comp._handle, b"host_nt", [-1, 0, 1][t % 3])       # every store flavour of the row assembly
+        comp.lib.diral_set_option(comp._handle, b"host_format", 1 + (t // 3) % 2)    # records by copy engine / zero-copy
         comp.step_host(ha, bufs[1][0], bufs[1][1], bufs[1][2] if t % 2 else None, episode_number=t // 3, epsilon=0.5 ** t)
         assert torch.equal(s.cpu(), bufs[0][0]) and torch.equal(rw.cpu(), bufs[0][1]) and torch.equal(info["obs"].cpu(), bufs[0][2])
         assert torch.equal(bufs[1][0], bufs[0][0]), "compact state rows, slot %d" % t
