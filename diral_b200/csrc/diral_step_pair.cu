@@ -20,6 +20,10 @@
 //      take 32-bit keys (one column per register)
 //   D  rewards (lane-local from the collision masks), mobility, state rows written by the lane that owns them.
 //
+// (Tried and dropped: the whole 16-bit key table in shared memory with row-wise LDS.128 / VIMNMX merges instead of the shuffle
+// replay -- 21 K instead of 27 K warp-instructions per environment, but 0.66 MB of shared-memory traffic per environment and a
+// dependent LDS -> max -> STS chain per pass: 566-586 us against 414 us, profiles/README.md.)
+//
 // Same arithmetic rules as the other slot kernels (diral_dev.cuh); same HBM layout as the lane-group kernel (layout 0).
 #include "diral_dev.cuh"
 #include "diral_launch.h"
@@ -342,25 +346,33 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
         const int age_thr = p.age_threshold;
         constexpr int FMAX = (1 << (16 - PSB)) - 1;
         const int base = tick - FMAX;
-        auto load_slab = [&](int jb, int (&sbn)[2][PSL], int (&lbn)[2][PSL], double (&xbn)[2][PSL]) {
+        // sequence numbers are loaded one slab ahead (the key formation needs them first); a slab's ages and positions are
+        // requested when the slab starts and consumed after the replay loop, whose latency chain hides them
+        int s_next[2][PSL];
+        auto load_seq = [&](int jb) {
 #pragma unroll
             for (int q = 0; q < PSL; ++q) {
                 const int j = jb + q;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int i = u + 32 * h;
-                    const bool ok = FULL || (j < N && (h == 0 || act1));
-                    if (ok) { sbn[h][q] = seqg[j * N + i]; lbn[h][q] = lug[j * N + i]; xbn[h][q] = xg[j * N + i]; }
-                    else { sbn[h][q] = 0; lbn[h][q] = 0; xbn[h][q] = 0.0; }
-                }
+                for (int h = 0; h < 2; ++h)
+                    s_next[h][q] = (FULL || (j < N && (h == 0 || act1))) ? seqg[j * N + u + 32 * h] : 0;
             }
         };
-        // one slab: `sb, lb, xb` hold its entries (loaded one slab earlier); the next slab's loads are issued into
-        // `sbn, lbn, xbn` before the replay loop, whose latency chain hides them
-        auto do_slab = [&](int jbase, int (&sb)[2][PSL], int (&lb)[2][PSL], double (&xb)[2][PSL],
-                           int (&sbn)[2][PSL], int (&lbn)[2][PSL], double (&xbn)[2][PSL]) {
+        auto do_slab = [&](int jbase) {
+            int sb[2][PSL], lb[2][PSL]; double xb[2][PSL];
             unsigned oldest = 0xffffffffu;
-            if (jbase + PSL < N) load_slab(jbase + PSL, sbn, lbn, xbn);
+#pragma unroll
+            for (int q = 0; q < PSL; ++q) {
+                const int j = jbase + q;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = u + 32 * h;
+                    sb[h][q] = s_next[h][q];
+                    if (FULL || (j < N && (h == 0 || act1))) { lb[h][q] = lug[j * N + i]; xb[h][q] = xg[j * N + i]; }
+                    else { lb[h][q] = 0; xb[h][q] = 0.0; }
+                }
+            }
+            if (jbase + PSL < N) load_seq(jbase + PSL);
 #pragma unroll
             for (int q = 0; q < PSL; ++q)
 #pragma unroll
@@ -488,13 +500,9 @@ __global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
                 }
             }
         };
-        int sbA[2][PSL], lbA[2][PSL], sbB[2][PSL], lbB[2][PSL]; double xbA[2][PSL], xbB[2][PSL];
-        load_slab(0, sbA, lbA, xbA);
+        load_seq(0);
 #pragma unroll 1
-        for (int jbase = 0; jbase < N; jbase += 2 * PSL) {
-            do_slab(jbase, sbA, lbA, xbA, sbB, lbB, xbB);
-            if (jbase + PSL < N) do_slab(jbase + PSL, sbB, lbB, xbB, sbA, lbA, xbA);
-        }
+        for (int jbase = 0; jbase < N; jbase += PSL) do_slab(jbase);
     }
 
     // ---- per-env metric accumulators ----------------------------------------------------------------------------------------
