@@ -283,3 +283,27 @@ def test_reference_install_recipe_and_timing_harness():
     assert res["one_core"] > 0 and res["all_cores_P_processes"] > 0 and res["P"] == 2
     ignored = open(os.path.join(ROOT, ".gitignore")).read()
     assert "oracle/_ref/" in ignored
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys,
+    the C port as `value`, the unmodified Python reference beside it when oracle/_ref is installed."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "agent-steps/s" and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("configs[2]") and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["cpu_model"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    rp = cb["reference_python"]
+    assert "unavailable" in rp or (rp["one_core"] > 0 and rp["all_cores_P_processes"] > 0 and rp["P"] >= 1)
