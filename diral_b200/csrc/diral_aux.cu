@@ -13,7 +13,15 @@ namespace {
 constexpr int SORT_MAX_N = 256;      // per-thread local arrays of the sorted variants
 constexpr int HIST_MAX_B = 256;
 
-__device__ __forceinline__ void insertion_sort(double *a, int n)
+// A thread's scratch array of the sorted State variants: element k of thread t sits at base[k * stride + t] in SHARED
+// memory (conflict-free: consecutive threads, consecutive words).  Round 1 kept 256 doubles per thread in local memory
+// whatever the vehicle count, which made the sorted variants 3-4x the cost of the whole slot kernel.
+struct StridedBuf {
+    double *base; int stride;
+    __device__ __forceinline__ double &operator[](int k) const { return base[k * stride]; }
+};
+
+__device__ __forceinline__ void insertion_sort(const StridedBuf &a, int n)
 {
     for (int i = 1; i < n; ++i) {
         const double v = a[i];
@@ -50,7 +58,8 @@ __global__ void __launch_bounds__(128) obtain_state_kernel(const Params p, const
     }
     if (p.add_channel_obs) { for (int r = 0; r < R; ++r) row[k++] = obs[gid * R + r]; }
 
-    double buf[SORTED ? SORT_MAX_N : 1];
+    extern __shared__ double sort_scratch[];
+    const StridedBuf buf{sort_scratch + threadIdx.x, (int)blockDim.x};      // (only touched by the SORTED instantiation)
     if (SORTED && p.add_positional_dist) {          // network.py:409-430
         int m = 0; double max_dist = 0.0;
         for (int t = 0; t < N; ++t) {
@@ -252,11 +261,21 @@ cudaError_t launch_obtain_state(const Params &p, const float *obs, const int32_t
                                 float *out, cudaStream_t stream)
 {
     const bool sorted = p.add_positional_dist || (p.piggy && p.pos_dist_type == 1);
-    const unsigned grid = blocks_for(p.E * p.N, 128);
     // edges1 (linspace(-1, 1, B+1)) lives right behind edges in the same device allocation
     const double *edges1 = p.edges + (p.B + 1);
-    if (sorted) obtain_state_kernel<true><<<grid, 128, 0, stream>>>(p, obs, actions, rews, out, edges1);
-    else        obtain_state_kernel<false><<<grid, 128, 0, stream>>>(p, obs, actions, rews, out, edges1);
+    if (!sorted) {
+        obtain_state_kernel<false><<<blocks_for(p.E * p.N, 128), 128, 0, stream>>>(p, obs, actions, rews, out, edges1);
+        return cudaGetLastError();
+    }
+    // N doubles of shared-memory scratch per thread: as many threads per CTA as 200 KB allow, at most 128
+    int threads = 128;
+    while (threads > 32 && (size_t)threads * p.N * sizeof(double) > (size_t)200 * 1024) threads -= 32;
+    const size_t smem = (size_t)threads * p.N * sizeof(double);
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(obtain_state_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+    }
+    obtain_state_kernel<true><<<blocks_for(p.E * p.N, threads), threads, smem, stream>>>(p, obs, actions, rews, out, edges1);
     return cudaGetLastError();
 }
 

@@ -98,7 +98,7 @@ class TestEnv:
     __test__ = False     # not a pytest class, whatever the name says
 
     def __init__(self, num_envs=1, device="cuda", seed=0, env_offset=0, init=None, variant="auto",
-                 host_format="full", host_threads=None, **kwargs):
+                 host_format="compact", host_threads=None, **kwargs):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():

@@ -245,7 +245,7 @@ def test_bad_actions_are_counted_and_errors_are_loud():
 
 
 def test_host_buffer_step_matches_device_step():
-    """diral_step_host (chunked, pipelined over two internal streams) == diral_step on the same actions."""
+    """diral_step_host (env chunks pipelined over internal streams; default host format) == diral_step on the same actions."""
     kw = dict(num_users=32, num_channels=20, highway_length=800, reward_design=2, communication_range=250,
               mobility=True, bin_range=500, State=_shipped_state(add_channel_obs=True))
     E = 2048
