@@ -386,8 +386,9 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         if (c.add_velocity)
             DIRAL_CUDA(cudaMemcpyAsync(h->h_kin + 2 * A + a0, h->bufs.vel + a0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ps));
         DIRAL_CUDA(cudaEventRecord(h->chunk_ev[k], ps));
-        DIRAL_CUDA(cudaStreamWaitEvent(s, h->chunk_ev[k], 0));    // the caller's stream sees the step as done
     }
+    // (the caller's stream needs no wait on the chunk streams: this call returns only after every chunk event has been
+    //  synchronised on the host, so whatever the caller enqueues next is ordered after the whole slot)
     if (c.add_piggy) h->ticks += 1;
     h->trace_us[1] = since();                                      // everything enqueued
     for (int k = 0; k < chunks; ++k) {                             // rows of chunk k are assembled while k+1.. are in flight
