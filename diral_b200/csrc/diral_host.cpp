@@ -8,6 +8,7 @@
 #include "diral_host.h"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -284,8 +285,8 @@ struct HostPool::Impl {
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv;
-    unsigned long long job_seq = 0;      // guarded by mu
-    bool stop = false;
+    std::atomic<unsigned long long> job_seq{0};
+    bool stop = false;                   // guarded by mu
     // the running job (written by begin() before job_seq moves)
     HostLayout lay{};
     HostJob job{};
@@ -298,12 +299,21 @@ struct HostPool::Impl {
     {
         unsigned long long seen = 0;
         for (;;) {
-            {
-                std::unique_lock<std::mutex> lock(mu);
-                cv.wait(lock, [&] { return stop || job_seq != seen; });
-                if (stop) return;
-                seen = job_seq;
+            // A caller stepping in a loop comes back within tens of microseconds: stay hot for a while (no futex wake,
+            // no scheduler latency on the next call), then go to sleep on the condition variable.
+            bool have = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int spins = 0; ; ++spins) {
+                if (job_seq.load(std::memory_order_acquire) != seen) { have = true; break; }
+                _mm_pause();
+                if ((spins & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
             }
+            if (!have) {
+                std::unique_lock<std::mutex> lock(mu);
+                cv.wait(lock, [&] { return stop || job_seq.load(std::memory_order_acquire) != seen; });
+                if (stop) return;
+            }
+            seen = job_seq.load(std::memory_order_acquire);
             for (int c = 0; c < nchunks; ++c) {
                 int spins = 0;
                 while (ready.load(std::memory_order_acquire) <= c) {
@@ -349,8 +359,8 @@ void HostPool::begin(const HostLayout &lay, const HostJob &job, const long long 
     impl->ready.store(0, std::memory_order_relaxed);
     impl->done.store(0, std::memory_order_relaxed);
     {
-        std::lock_guard<std::mutex> lock(impl->mu);
-        impl->job_seq += 1;
+        std::lock_guard<std::mutex> lock(impl->mu);          // (a worker between its spin phase and cv.wait sees the new value)
+        impl->job_seq.fetch_add(1, std::memory_order_release);
     }
     impl->cv.notify_all();
 }
