@@ -172,7 +172,7 @@ class ClockSampler:
                         self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(0.01)
 
     def reset(self):
         self.samples, self.reasons = [], set()
@@ -306,10 +306,13 @@ def run_gpu(args):
     launches0 = env.launch_count()
     barrier()
     clocks.reset()                                # only samples taken inside the timed region are reported
-    # a short spin kernel lets the host run ahead of the device, so that no timed interval contains the
-    # host's own launch latency (with 8 ranks per box the host loop is the slower one at first)
+    # A spin kernel lets the host run ahead of the device, so that no timed interval contains the host's own launch
+    # latency.  The host loop (two flush kernels, two event records, one launch: 130-220 us of Python per step) is no
+    # faster than the device (161 us per step incl. the untimed flush), and on a busy box single iterations stall for
+    # milliseconds (NVML queries of the clock sampler and of the driver's own monitor contend with launches): the head
+    # start therefore covers the WHOLE enqueue loop -- 1.5 ms of spinning per timed step, at least 30 ms.
     if hasattr(torch.cuda, "_sleep"):
-        torch.cuda._sleep(int(2.0e7))
+        torch.cuda._sleep(int(max(6.0e7, steps * 3.0e6)))
     t_host0 = time.perf_counter()
     for k in range(steps):
         flush()
@@ -333,7 +336,8 @@ def run_gpu(args):
     clk = clocks.stop()
     gpu_launches = env.launch_count() - launches0
     allreduce_us = [a.elapsed_time(b) * 1e3 for _, a, b in pending]
-    ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    ms = sum(step_ms)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
@@ -427,6 +431,7 @@ def run_gpu(args):
                                             "note": "110-double metric vector: clone + all-reduce(sum) on a side stream "
                                                     "(NCCL when world > 1), every 25 slots and after the last one"}}}
     line["extra"]["host_enqueue_us_per_step"] = host_us_per_step
+    line["extra"]["step_us_min_median_max"] = [min(step_ms) * 1e3, statistics.median(step_ms) * 1e3, max(step_ms) * 1e3]
     if configs is not None:
         line["extra"]["configs"] = configs
     if per_rank is not None:

@@ -294,6 +294,7 @@ struct HostPool::Impl {
     int nchunks = 0;
     std::atomic<int> ready{0};           // chunks whose inputs are in host memory
     std::atomic<int> done{0};            // workers that have finished the job
+    int hot_us = 200;                    // how long a worker keeps polling for the next job before it sleeps
 
     void run(int idx, int nthreads)
     {
@@ -306,7 +307,7 @@ struct HostPool::Impl {
             for (int spins = 0; ; ++spins) {
                 if (job_seq.load(std::memory_order_acquire) != seen) { have = true; break; }
                 _mm_pause();
-                if ((spins & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+                if ((spins & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(hot_us)) break;
             }
             if (!have) {
                 std::unique_lock<std::mutex> lock(mu);
@@ -333,6 +334,7 @@ struct HostPool::Impl {
 
 HostPool::HostPool(int threads) : impl(new Impl)
 {
+    if (const char *v = getenv("DIRAL_HOST_HOT_US")) impl->hot_us = atoi(v);       // measurement knob
     const int n = threads < 1 ? 1 : threads;
     vpd_quotients();
     for (int i = 0; i < n; ++i) impl->workers.emplace_back([this, i, n] { impl->run(i, n); });
