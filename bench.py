@@ -172,7 +172,7 @@ class ClockSampler:
                         self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def reset(self):
         self.samples, self.reasons = [], set()
@@ -185,6 +185,11 @@ class ClockSampler:
     def stop(self):
         if self._thread:
             self._stop.set(); self._thread.join()
+        if self.nv and not self.samples:          # a stalled sampler thread must not leave the timed region unsampled
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            except Exception:  # noqa: BLE001
+                pass
         benign = {"GpuIdle", "None", "ApplicationsClocksSetting"}
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(r for r in self.reasons if r not in benign), "samples": len(self.samples)}
