@@ -236,6 +236,9 @@ def run_extra_configs(torch, dist, TestEnv, dev, rank, world, flush, peak, slots
         for t in range(warm):
             env._step(mode, None, t, True)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(slots)]
+        torch.cuda.synchronize(dev)
+        if hasattr(torch.cuda, "_sleep"):
+            torch.cuda._sleep(int(slots * 3.0e6))     # head start for the host (see run_gpu)
         for k in range(slots):
             flush()
             ev[k][0].record(); env._step(mode, None, warm + k, True); ev[k][1].record()
