@@ -157,8 +157,11 @@ __device__ __forceinline__ void store_words(unsigned *ptr, const unsigned (&v)[N
 #ifndef DIRAL_ROW_THREADS_64
 #define DIRAL_ROW_THREADS_64 256      // tuning knob: threads per CTA of the 64-vehicle instantiation
 #endif
-__host__ __device__ constexpr int row_threads(int nw2) { return nw2 == 1 ? DIRAL_ROW_THREADS_64 : 256 * nw2; }
-__host__ __device__ constexpr int row_min_ctas(int nw2) { return nw2 == 1 ? 1024 / DIRAL_ROW_THREADS_64 : (nw2 == 2 ? 2 : 1); }
+#ifndef DIRAL_ROW_THREADS_128
+#define DIRAL_ROW_THREADS_128 512     // tuning knob: threads per CTA of the 128-vehicle instantiation
+#endif
+__host__ __device__ constexpr int row_threads(int nw2) { return nw2 == 1 ? DIRAL_ROW_THREADS_64 : (nw2 == 2 ? DIRAL_ROW_THREADS_128 : 256 * nw2); }
+__host__ __device__ constexpr int row_min_ctas(int nw2) { return nw2 == 1 ? 1024 / DIRAL_ROW_THREADS_64 : (nw2 == 2 ? (DIRAL_ROW_THREADS_128 == 512 ? 2 : 3) : 1); }
 
 template <int NW2>
 __global__ void __launch_bounds__(row_threads(NW2), row_min_ctas(NW2))
