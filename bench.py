@@ -392,7 +392,9 @@ def run_gpu(args):
         return world * E_PER_GPU * N_UE * e2e_steps / float(t.item())
 
     e2e_full = e2e_leg("full")
-    e2e_value = e2e_leg("compact")
+    e2e_chunked = e2e_leg("compact")
+    e2e_value = e2e_leg("compact_stream")          # the library default
+    e2e_format = env.host_format
     host_threads = int(env.lib.diral_get_option(env._handle, b"host_threads"))
     h2d = E_PER_GPU * N_UE * 4
     d2h_full = E_PER_GPU * N_UE * (S + 1) * 4
@@ -423,9 +425,12 @@ def run_gpu(args):
             "data": "synthetic", "config": workload_config(world), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "host_threads": host_threads,
-                    "api": "diral_step_host (C ABI, pinned host buffers, synchronous), host_format=compact: VPD bin "
-                           "counts (1 B per bin) + rewards cross PCIe, the [E,N,S] float32 rows are assembled in the "
-                           "caller's buffer by the library's host threads inside the timed region"},
+                    "host_format": e2e_format,
+                    "api": "diral_step_host (C ABI, pinned host buffers, synchronous), host_format=compact_stream (the "
+                           "default): ONE launch per slot reads the pinned actions in place and writes per-agent records "
+                           "(1 B per VPD bin + the float32 reward) into mapped host memory, raising a flag per chunk of "
+                           "environments; the [E,N,S] float32 rows are assembled in the caller's buffer by the library's "
+                           "host threads inside the timed region"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "step_group_kernel<32>",
@@ -434,6 +439,9 @@ def run_gpu(args):
                       "note": "value_l2_resident_no_flush = same loop without the L2 flush (state fits the 126 MB L2)",
                       "e2e_full_format": {"value": e2e_full, "unit": UNIT, "d2h_bytes_per_step": d2h_full,
                                           "note": "same call, host_format=full: the float32 rows themselves cross PCIe"},
+                      "e2e_compact_chunked": {"value": e2e_chunked, "unit": UNIT, "d2h_bytes_per_step": d2h,
+                                              "note": "same call, host_format=compact: 8 env chunks, each on its own stream "
+                                                      "(copy in, slot kernel, records out through the copy engine)"},
                       "episode_allreduce": {"count_in_timed_loop": len(allreduce_us), "world": world,
                                             "side_stream_us": allreduce_us,
                                             "note": "110-double metric vector: clone + all-reduce(sum) on a side stream "

@@ -7,10 +7,12 @@
 #include "diral_launch.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <immintrin.h>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -42,7 +44,7 @@ enum Variant { VARIANT_AUTO = 0, VARIANT_GROUP = 1, VARIANT_BLOCK = 2, VARIANT_B
 // Measured on B200 (profiles/README.md): the row-layout kernel wins from ~100 vehicles on (1.07x at 128, 1.67x at 256);
 // below that its padded rows (T = 128 for 65..96 vehicles) and per-environment fixed costs lose to round 1's kernel.
 constexpr int ROW_MIN_N = 97;
-constexpr int MAX_HOST_CHUNKS = 32;
+constexpr int MAX_HOST_CHUNKS = 64;
 
 struct Handle {
     diral_cfg cfg{};
@@ -64,7 +66,16 @@ struct Handle {
     cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
     // compact host format of diral_step_host (see diral_host.h)
     int host_format = 0;            // 0 = full rows over PCIe, 1 = compact record + host-side row assembly,
-                                    // 2 = the same, records written by the kernel straight into mapped host memory
+                                    // 2 = the same, records written by the kernel straight into mapped host memory,
+                                    // 3 = streamed: one launch, records into mapped host memory, per-chunk completion
+                                    //     flags raised by the kernel (lane-group kernel; other kernels run as format 1)
+    int stream_chunks = 16;         // format 3: chunks the assembly threads are released by
+    int actions_direct = 1;         // the kernel reads the caller's actions in place when they are pinned: 0 never, 1 format 3
+                                    // only (measured: -12 us there, +15 us for the chunked formats), 2 always
+    unsigned *d_chunk_count = nullptr;    // [MAX_HOST_CHUNKS] device counters (zero between slots)
+    unsigned *h_chunk_flag = nullptr;     // [MAX_HOST_CHUNKS] mapped pinned flags
+    unsigned *d_chunk_flag = nullptr;     // device address of the same
+    unsigned chunk_epoch = 0;
     uint8_t *d_counts_mapped = nullptr;   // device address of h_counts (mapped pinned allocation)
     int host_threads = 0;           // 0 = pick from the CPUs this process may run on
     int host_chunks = 8;
@@ -326,12 +337,25 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     }
     // zero-copy: the lane-group kernel stages an environment's records in shared memory and writes them out as one
     // coalesced stream, so they can go over PCIe as the kernel runs instead of through a copy engine afterwards
-    const bool zero_copy = h->host_format == 2 && group && h->d_counts_mapped != nullptr;
+    const bool streamed = h->host_format == 3 && group && h->d_counts_mapped != nullptr && !want_obs && !h_obs && !want_kin;
+    const bool zero_copy = (h->host_format == 2 || streamed) && group && h->d_counts_mapped != nullptr;
     if (want_obs && !h_obs && !h->h_obs_stage) DIRAL_CUDA(cudaMallocHost(&h->h_obs_stage, sizeof(float) * (size_t)(A * R)));
     if (want_kin && !h->h_kin) DIRAL_CUDA(cudaMallocHost(&h->h_kin, sizeof(double) * (size_t)(3 * A)));
-    const int chunks = E >= 1024 ? h->host_chunks : 1;
+    int chunks = E >= 1024 ? h->host_chunks : 1;
+    long long chunk_envs = 0;
+    if (streamed) {
+        chunk_envs = (E + h->stream_chunks - 1) / h->stream_chunks;
+        chunks = (int)((E + chunk_envs - 1) / chunk_envs);
+        if (!h->d_chunk_count) {
+            DIRAL_CUDA(cudaMalloc(&h->d_chunk_count, sizeof(unsigned) * MAX_HOST_CHUNKS));
+            DIRAL_CUDA(cudaMemset(h->d_chunk_count, 0, sizeof(unsigned) * MAX_HOST_CHUNKS));
+            DIRAL_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&h->h_chunk_flag), sizeof(unsigned) * MAX_HOST_CHUNKS, cudaHostAllocMapped));
+            memset(h->h_chunk_flag, 0, sizeof(unsigned) * MAX_HOST_CHUNKS);
+            DIRAL_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->d_chunk_flag), h->h_chunk_flag, 0));
+        }
+    }
     if (!h->pipe_ev[2]) DIRAL_CUDA(cudaEventCreateWithFlags(&h->pipe_ev[2], cudaEventDisableTiming));
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = 0; k < chunks && !streamed; ++k) {
         if (!h->chunk_stream[k]) DIRAL_CUDA(cudaStreamCreateWithFlags(&h->chunk_stream[k], cudaStreamNonBlocking));
         if (!h->chunk_ev[k]) DIRAL_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
     }
@@ -357,7 +381,7 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     job.pos_x = h->h_kin; job.pos_y = h->h_kin ? h->h_kin + A : nullptr; job.vel = h->h_kin ? h->h_kin + 2 * A : nullptr;
     job.episode = episode; job.epsilon = epsilon; job.out = h_state;
     long long bounds[MAX_HOST_CHUNKS + 1];
-    for (int k = 0; k <= chunks; ++k) bounds[k] = (E * k / chunks) * N;
+    for (int k = 0; k <= chunks; ++k) bounds[k] = (streamed ? std::min<long long>(E, chunk_envs * k) : E * k / chunks) * N;
     diral::HostLayout lay = host_layout(c);
     // a worker's share of the rows stays in its private L2 from call to call when it is small enough
     lay.nt_stores = h->host_nt >= 0 ? h->host_nt
@@ -366,12 +390,60 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     PoolJobGuard guard{h->pool, chunks};
     h->trace_us[0] = since();                                      // workers woken
 
-    DIRAL_CUDA(cudaEventRecord(h->pipe_ev[2], s));                 // everything queued on the caller's stream so far
+    // Pinned caller memory is read in place by the kernels (unified addressing: one PCIe read of 4 N bytes per environment
+    // at the start of its decision phase) -- no host-to-device copy to enqueue; pageable actions go through the staging copy.
+    bool direct = false;
+    if (h->actions_direct == 2 || (h->actions_direct == 1 && streamed)) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, h_actions) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+            p.actions = static_cast<const int32_t *>(attr.devicePointer); direct = true;
+        }
+        cudaGetLastError();                                        // (an unregistered pointer is not an error here)
+    }
+
+    if (streamed) {
+        // One launch on the caller's stream.  The kernel writes every environment's records into mapped host memory and
+        // raises a chunk's flag when its last environment is through (env_records_done); this thread forwards the flags
+        // to the assembly workers.
+        if (!direct) DIRAL_CUDA(cudaMemcpyAsync(h->d_actions, h_actions, (size_t)A * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        const unsigned epoch = ++h->chunk_epoch ? h->chunk_epoch : ++h->chunk_epoch;     // never 0: flags start there
+        p.chunk_count = h->d_chunk_count; p.chunk_flag = h->d_chunk_flag; p.chunk_envs = (int)chunk_envs; p.chunk_epoch = epoch;
+        DIRAL_CUDA(launch_slot(h, p, s));
+        h->launches += 1;
+        if (c.add_piggy) h->ticks += 1;
+        h->trace_us[1] = since();                                  // everything enqueued
+        volatile unsigned *flags = h->h_chunk_flag;
+        for (int k = 0; k < chunks; ++k) {
+            for (unsigned spins = 1; flags[k] != epoch; ++spins) {
+                _mm_pause();
+                if ((spins & 0xfff) == 0) {                        // every few tens of microseconds: is the launch still alive?
+                    const cudaError_t q = cudaStreamQuery(s);
+                    if (q != cudaSuccess && q != cudaErrorNotReady)
+                        return fail(DIRAL_ERR_CUDA, "slot kernel failed: %s", cudaGetErrorString(q));
+                    if (q == cudaSuccess && flags[k] != epoch)
+                        return fail(DIRAL_ERR_CUDA, "slot kernel finished without completing chunk %d", k);
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            h->pool->publish(k);
+            h->trace_us[2 + k] = since();                          // chunk k's records are in host memory
+        }
+        guard.close();
+        h->trace_us[2 + chunks] = since();                         // every row assembled
+        h->trace_n = 3 + chunks;
+        DIRAL_CUDA(cudaStreamSynchronize(s));                      // the launch itself retires (tables, accumulators)
+        return DIRAL_OK;
+    }
+
+    // the chunk streams start after whatever the caller queued on its stream -- nothing to order when that stream is idle
+    const bool caller_idle = cudaStreamQuery(s) == cudaSuccess;
+    if (!caller_idle) { cudaGetLastError(); DIRAL_CUDA(cudaEventRecord(h->pipe_ev[2], s)); }
+    int published = 0;
     for (int k = 0; k < chunks; ++k) {
         const long long a0 = bounds[k], n = bounds[k + 1] - a0, e0 = a0 / N;
         cudaStream_t ps = h->chunk_stream[k];
-        DIRAL_CUDA(cudaStreamWaitEvent(ps, h->pipe_ev[2], 0));
-        DIRAL_CUDA(cudaMemcpyAsync(h->d_actions + a0, h_actions + a0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ps));
+        if (!caller_idle) DIRAL_CUDA(cudaStreamWaitEvent(ps, h->pipe_ev[2], 0));
+        if (!direct) DIRAL_CUDA(cudaMemcpyAsync(h->d_actions + a0, h_actions + a0, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ps));
         const diral::Params q = env_range(p, e0, n / N);
         DIRAL_CUDA(launch_slot(h, q, ps));
         h->launches += 1;
@@ -386,12 +458,18 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         if (c.add_velocity)
             DIRAL_CUDA(cudaMemcpyAsync(h->h_kin + 2 * A + a0, h->bufs.vel + a0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ps));
         DIRAL_CUDA(cudaEventRecord(h->chunk_ev[k], ps));
+        // earlier chunks may have landed while this one was being enqueued: release their rows now
+        while (published < k && cudaEventQuery(h->chunk_ev[published]) == cudaSuccess) {
+            h->pool->publish(published);
+            h->trace_us[2 + published++] = since();
+        }
+        cudaGetLastError();                                        // (cudaErrorNotReady is not an error)
     }
     // (the caller's stream needs no wait on the chunk streams: this call returns only after every chunk event has been
     //  synchronised on the host, so whatever the caller enqueues next is ordered after the whole slot)
     if (c.add_piggy) h->ticks += 1;
     h->trace_us[1] = since();                                      // everything enqueued
-    for (int k = 0; k < chunks; ++k) {                             // rows of chunk k are assembled while k+1.. are in flight
+    for (int k = published; k < chunks; ++k) {                     // rows of chunk k are assembled while k+1.. are in flight
         DIRAL_CUDA(cudaEventSynchronize(h->chunk_ev[k]));
         h->pool->publish(k);
         h->trace_us[2 + k] = since();                              // chunk k's records are in host memory
@@ -490,6 +568,8 @@ int diral_destroy(void *handle)
     for (auto &st : h->chunk_stream) if (st) cudaStreamDestroy(st);
     delete h->pool;
     cudaFree(h->d_counts);
+    cudaFree(h->d_chunk_count);
+    if (h->h_chunk_flag) cudaFreeHost(h->h_chunk_flag);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_obs_stage) cudaFreeHost(h->h_obs_stage);
     if (h->h_kin) cudaFreeHost(h->h_kin);
@@ -522,7 +602,8 @@ int diral_set_option(void *handle, const char *name, int64_t value)
     }
     if (!strcmp(name, "track_lat")) { h->force_track_lat = value != 0; return DIRAL_OK; }
     if (!strcmp(name, "host_format")) {
-        if (value < 0 || value > 2) return fail(DIRAL_ERR_ARG, "host_format must be 0 (full rows), 1 (compact) or 2 (compact, zero-copy records)");
+        if (value < 0 || value > 3)
+            return fail(DIRAL_ERR_ARG, "host_format must be 0 (full rows), 1 (compact), 2 (compact, zero-copy records) or 3 (streamed records)");
         h->host_format = (int)value;
         return DIRAL_OK;
     }
@@ -543,8 +624,18 @@ int diral_set_option(void *handle, const char *name, int64_t value)
         return DIRAL_OK;
     }
     if (!strcmp(name, "host_chunks")) {
-        if (value < 1 || value > MAX_HOST_CHUNKS) return fail(DIRAL_ERR_ARG, "host_chunks must be in [1, %d]", MAX_HOST_CHUNKS);
+        if (value < 1 || value > 32) return fail(DIRAL_ERR_ARG, "host_chunks must be in [1, 32]");
         h->host_chunks = (int)value;
+        return DIRAL_OK;
+    }
+    if (!strcmp(name, "stream_chunks")) {
+        if (value < 1 || value > MAX_HOST_CHUNKS) return fail(DIRAL_ERR_ARG, "stream_chunks must be in [1, %d]", MAX_HOST_CHUNKS);
+        h->stream_chunks = (int)value;
+        return DIRAL_OK;
+    }
+    if (!strcmp(name, "actions_direct")) {
+        if (value < 0 || value > 2) return fail(DIRAL_ERR_ARG, "actions_direct must be 0 (never), 1 (streamed format only) or 2 (always)");
+        h->actions_direct = (int)value;
         return DIRAL_OK;
     }
     // checkpoint restore (TestEnv.load_state_dict): the slot counters the kernels derive keys and stamps from
@@ -571,6 +662,8 @@ int64_t diral_get_option(void *handle, const char *name)
     if (!strcmp(name, "host_format")) return h->host_format;
     if (!strcmp(name, "host_threads")) return h->pool ? h->pool->threads() : h->host_threads;
     if (!strcmp(name, "host_chunks")) return h->host_chunks;
+    if (!strcmp(name, "stream_chunks")) return h->stream_chunks;
+    if (!strcmp(name, "actions_direct")) return h->actions_direct;
     if (!strcmp(name, "host_nt")) return h->host_nt;
     if (!strcmp(name, "tail_split")) return h->tail_split;
     if (!strcmp(name, "ticks")) return h->ticks;

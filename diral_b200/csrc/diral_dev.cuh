@@ -55,6 +55,12 @@ struct Params {
     uint8_t *vpd_counts;      // compact host record per agent (diral_step_host) or NULL: B bin counts (one byte each, when
                               // piggy), padded to 4 bytes, then the float32 reward; rec_stride bytes apart
     int rec_stride;
+    // streamed host records (diral_step_host, host_format 3): ONE launch covers the batch, the records go straight to
+    // mapped host memory and the kernel tells the host which chunk of environments is complete (see env_records_done)
+    unsigned *chunk_count;    // [chunks] device counters, zero between slots
+    unsigned *chunk_flag;     // [chunks] mapped host words: = chunk_epoch once the chunk's records are in host memory
+    int chunk_envs;           // environments per chunk (the last chunk may be shorter)
+    unsigned chunk_epoch;     // this slot's flag value
     double *acc_reward; long long *acc_count;
     uint32_t *scratch;
     const double *trace; long long trace_len;
@@ -79,6 +85,23 @@ __device__ __forceinline__ double tab_xpos(const Params &p, long long e, int i, 
     if (sn <= 0) return 0.0;
     if (p.tick - sn < p.H) return p.ring[(e * p.H + (sn & (p.H - 1))) * (long long)p.T + j];
     return p.tab_x[((p.tick & 1) ? p.spill_half : 0) + tab_index(p, e, i, j)];
+}
+
+// Streamed host records: called by ONE thread of environment e after every thread's record stores were ordered before it
+// (__syncwarp / __syncthreads).  The system-scope fence makes the records visible to the host before the count moves;
+// whoever completes a chunk re-arms its counter and raises the chunk's flag in host memory, which the host threads that
+// assemble the state rows poll -- no copy engine, no event, no second launch between the kernel and the consumer.
+__device__ __forceinline__ void env_records_done(const Params &p, long long e)
+{
+    __threadfence_system();
+    const int k = (int)(e / p.chunk_envs);
+    const long long left = p.E - (long long)k * p.chunk_envs;
+    const unsigned size = (unsigned)(left < p.chunk_envs ? left : p.chunk_envs);
+    if (atomicAdd(p.chunk_count + k, 1u) + 1u == size) {
+        p.chunk_count[k] = 0u;               // the last environment of the chunk: nobody else touches it this slot
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned *>(p.chunk_flag + k) = p.chunk_epoch;
+    }
 }
 
 // per-slot caller epilogue (main_test.py:150-206): device pointers and switches of one call

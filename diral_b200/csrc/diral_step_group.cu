@@ -665,6 +665,7 @@ step_group_kernel(const Params p)
     // the environment's host records leave as one contiguous stream (they may sit in mapped host memory: 16-byte pieces)
     if (CNT) copy_out(reinterpret_cast<float *>(p.vpd_counts + vbase * p.rec_stride), reinterpret_cast<const float *>(recS), N * (p.rec_stride >> 2));
     __syncwarp(gmask);                       // the next slot reuses the shared-memory staging
+    if (CNT) { if (p.chunk_flag && u == 0) env_records_done(p, e); }
     }   // slot
 }
 

@@ -98,7 +98,7 @@ class TestEnv:
     __test__ = False     # not a pytest class, whatever the name says
 
     def __init__(self, num_envs=1, device="cuda", seed=0, env_offset=0, init=None, variant="auto",
-                 host_format="compact", host_threads=None, **kwargs):
+                 host_format="compact_stream", host_threads=None, **kwargs):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -199,14 +199,17 @@ class TestEnv:
         except Exception:
             pass
 
-    def set_host_format(self, host_format="compact", host_threads=None):
+    def set_host_format(self, host_format="compact_stream", host_threads=None):
         """How ``step_host`` moves a slot's results to the host: ``"full"`` copies the [E, N, S] float32 rows over
         PCIe; ``"compact"`` copies only what the host cannot know (VPD bin counts as bytes, rewards, ...) and lets
-        ``host_threads`` library threads assemble the same rows in the caller's buffer (include/diral_env.h).
+        ``host_threads`` library threads assemble the same rows in the caller's buffer (include/diral_env.h);
+        ``"compact_stream"`` is the same record written by ONE launch straight into mapped host memory, the kernel
+        raising a flag per chunk of environments that releases the assembly threads (lane-group kernel).
         ``host_threads=None``: the CPUs this process may use, shared between the ranks of a torchrun job."""
-        if host_format not in ("full", "compact", "compact_zero_copy"):
-            raise ValueError("host_format must be 'full', 'compact' or 'compact_zero_copy'")
-        check(self.lib.diral_set_option(self._handle, b"host_format", {"full": 0, "compact": 1, "compact_zero_copy": 2}[host_format]))
+        formats = {"full": 0, "compact": 1, "compact_zero_copy": 2, "compact_stream": 3}
+        if host_format not in formats:
+            raise ValueError("host_format must be one of %s" % ", ".join(repr(k) for k in formats))
+        check(self.lib.diral_set_option(self._handle, b"host_format", formats[host_format]))
         if host_threads is None:
             import os
             cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)

@@ -67,9 +67,10 @@ def expander(threads, reps=30):
     return {"threads": threads, "us": dt * 1e6, "GBps_written": A * S * 4 / dt / 1e9}
 
 
-def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, nt=-1, reps=40):
+def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, nt=-1, reps=40, direct=1):
     env.set_host_format(fmt, threads)
-    env.lib.diral_set_option(env._handle, b"host_chunks", chunks)
+    env.lib.diral_set_option(env._handle, b"stream_chunks" if fmt == "compact_stream" else b"host_chunks", chunks)
+    env.lib.diral_set_option(env._handle, b"actions_direct", direct)
     env.lib.diral_set_option(env._handle, b"host_nt", nt)
     for k in range(4):
         env.step_host(h_act[k % 8], h_state, h_rews)
@@ -79,9 +80,9 @@ def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, nt=-1, reps=40)
         env.step_host(h_act[k % 8], h_state, h_rews)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
-    tr = (C.c_double * 40)()
-    n = env.lib.diral_host_trace(env._handle, tr, 40)
-    return {"trace_us_last_call": [round(tr[i], 1) for i in range(n)], "format": fmt, "host_threads": threads, "chunks": chunks, "nt_stores": nt, "us_per_slot": dt * 1e6,
+    tr = (C.c_double * 68)()
+    n = env.lib.diral_host_trace(env._handle, tr, 68)
+    return {"trace_us_last_call": [round(tr[i], 1) for i in range(n)], "format": fmt, "actions_direct": direct, "host_threads": threads, "chunks": chunks, "nt_stores": nt, "us_per_slot": dt * 1e6,
             "agent_steps_per_s": E_PER_GPU * N_UE / dt}
 
 
@@ -89,17 +90,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--quick", action="store_true", help="copy ceilings and the row-assembly rate only (multi-GPU boxes are charged per GPU)")
+    ap.add_argument("--stream", action="store_true", help="diral_step_host only: chunked copy-engine format against the streamed one")
     args = ap.parse_args()
     cpus = len(os.sched_getaffinity(0))
     out = {"cpu_model": cpu_model(), "cpus_usable": cpus, "cpu_count": os.cpu_count(), "d2h": [], "expander": [], "step_host": []}
     full = E_PER_GPU * N_UE * 41 * 4
     compact = E_PER_GPU * N_UE * 24
-    n = 1
+    n = 1 if not args.stream else args.gpus + 1
     while n <= args.gpus:
         for nb in (full, compact, 256 << 20):
             out["d2h"].append(d2h_ceiling(n, nb))
         n *= 2
-    for th in sorted({1, 2, 4, 8, 12, max(cpus - 2, 1), max(cpus - 1, 1)}):
+    for th in ([] if args.stream else sorted({1, 2, 4, 8, 12, max(cpus - 2, 1), max(cpus - 1, 1)})):
         out["expander"].append(dict(expander(th), stores="ordinary"))
         out["expander"].append(dict(expander(-th), stores="non-temporal"))
     if args.quick:
@@ -113,6 +115,16 @@ def main():
     h_state = torch.empty((E_PER_GPU, N_UE, env.S), dtype=torch.float32).pin_memory()
     h_rews = torch.empty((E_PER_GPU, N_UE), dtype=torch.float32).pin_memory()
     out["step_host"].append(step_host(env, "full", 1, 4, h_act, h_state, h_rews))
+    if args.stream:
+        for rep in range(3):
+            for th in sorted({8, max(cpus - 4, 1), max(cpus - 3, 1), max(cpus - 2, 1), max(cpus - 1, 1)}):
+                for direct in (0, 1):
+                    out["step_host"].append(step_host(env, "compact", th, 8, h_act, h_state, h_rews, 0, direct=direct))
+                out["step_host"].append(step_host(env, "compact", th, 16, h_act, h_state, h_rews, 0, direct=1))
+                for ch in (16, 64):
+                    out["step_host"].append(step_host(env, "compact_stream", th, ch, h_act, h_state, h_rews, 0, direct=1))
+        print(json.dumps(out, indent=1))
+        return
     for th in sorted({8, 12, max(cpus - 3, 1), max(cpus - 2, 1)}):
         for ch in (2, 4, 8, 16):
             for fmt in ("compact", "compact_zero_copy"):

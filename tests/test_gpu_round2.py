@@ -156,12 +156,18 @@ def test_compact_host_format_is_bit_identical(n, r, E, state, extra):
         s, rw, info = dev.step(a, episode_number=t // 3, epsilon=0.5 ** t)
         full.step_host(ha, *bufs[0], episode_number=t // 3, epsilon=0.5 ** t)
         comp.lib.diral_set_option(comp._handle, b"host_nt", [-1, 0, 1][t % 3])       # every store flavour of the row assembly
-        comp.lib.diral_set_option(comp._handle, b"host_format", 1 + (t // 3) % 2)    # records by copy engine / zero-copy
-        comp.step_host(ha, bufs[1][0], bufs[1][1], bufs[1][2] if t % 2 else None, episode_number=t // 3, epsilon=0.5 ** t)
+        fmt = [1, 2, 3, 3, 1, 3, 2, 3][t]                # records by copy engine / zero-copy / streamed (one launch + flags)
+        comp.lib.diral_set_option(comp._handle, b"host_format", fmt)
+        comp.lib.diral_set_option(comp._handle, b"actions_direct", [0, 2, 1][t % 3])   # pinned actions read in place or staged
+        comp.lib.diral_set_option(comp._handle, b"stream_chunks", [32, 5, 64][t % 3])
+        with_obs = t == 7 or (t % 2 == 1 and fmt != 3)   # (an obs request sends format 3 down the chunked path)
+        src = a.cpu().numpy().copy() if t == 5 else ha   # pageable actions: always staged
+        bufs[1][0].fill_(-7.0)
+        comp.step_host(src, bufs[1][0], bufs[1][1], bufs[1][2] if with_obs else None, episode_number=t // 3, epsilon=0.5 ** t)
         assert torch.equal(s.cpu(), bufs[0][0]) and torch.equal(rw.cpu(), bufs[0][1]) and torch.equal(info["obs"].cpu(), bufs[0][2])
         assert torch.equal(bufs[1][0], bufs[0][0]), "compact state rows, slot %d" % t
         assert torch.equal(bufs[1][1], bufs[0][1])
-        if t % 2:
+        if with_obs:
             assert torch.equal(bufs[1][2], bufs[0][2])
     assert torch.equal(dev.episode_metrics(), comp.episode_metrics())
     if state["add_positional_dist_piggy"]:

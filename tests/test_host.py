@@ -215,6 +215,10 @@ def test_every_shipped_yaml_block_is_accepted(bins):
     (dict(action_index="real", num_bins=7, add_reward=True), dict(num_channels=5, num_users=13), 2),
     (dict(add_action=False, num_bins=12), dict(num_channels=9), -2),
     (dict(add_positional_dist_piggy=False, add_channel_obs=True), dict(num_channels=8), 2),
+    # layouts of the four-agents-per-step AVX-512 path: record block in two vectors, rows shorter than one vector,
+    # the widest block it takes, one-hot only
+    (dict(num_bins=28), dict(num_channels=12), 1), (dict(num_bins=8), dict(num_channels=4), 3),
+    (dict(num_bins=32), dict(num_channels=32), 2), (dict(add_positional_dist_piggy=False), dict(num_channels=16), 1),
 ])
 def test_host_row_assembly_matches_obtain_state_layout(state, extra, threads):
     """diral_expand_state_host -- the host half of the compact host format -- against the row layout of
@@ -234,7 +238,9 @@ def test_host_row_assembly_matches_obtain_state_layout(state, extra, threads):
     counts = (rs.randint(0, 4, (A, B)) * (rs.rand(A, 1) < 0.9)).astype(np.uint8)
     rews = rs.randn(A).astype(np.float32); obs = (rs.rand(A, R) * 300).astype(np.float32)
     px = rs.rand(A) * 800; py = rs.randint(0, 3, A).astype(np.float64); vel = rs.rand(A) + 1.1
-    out = np.full((A, S), np.nan, np.float32)
+    raw = np.full(A * S + 16, np.nan, np.float32)              # 64-byte aligned rows (the widest vector path needs them)
+    off = (-raw.ctypes.data % 64) // 4
+    out = raw[off:off + A * S].reshape(A, S)
     rc = lib.diral_expand_state_host(C.byref(cfg), A, act.ctypes.data, counts.ctypes.data, rews.ctypes.data, obs.ctypes.data,
                                      px.ctypes.data, py.ctypes.data, vel.ctypes.data, 3.0, 0.25, threads, out.ctypes.data)
     assert rc == 0, lib.diral_last_error()
