@@ -663,7 +663,23 @@ step_group_kernel(const Params p)
     copy_out(p.obs + vbase * R, obsS, N * R);
     if (want_state && !direct) copy_out(p.state + vbase * S, st, N * S);
     // the environment's host records leave as one contiguous stream (they may sit in mapped host memory: 16-byte pieces)
-    if (CNT) copy_out(reinterpret_cast<float *>(p.vpd_counts + vbase * p.rec_stride), reinterpret_cast<const float *>(recS), N * (p.rec_stride >> 2));
+    if (CNT) {
+        const unsigned rec_bytes = (unsigned)(N * p.rec_stride);
+        if ((rec_bytes & 15u) == 0u) {
+            // one bulk store per environment (TMA): the whole record block leaves shared memory as a single asynchronous
+            // copy -- towards mapped host memory that is one stream of full-line PCIe writes instead of 16-byte lane stores
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this lane's recS stores -> async proxy
+            __syncwarp(gmask);
+            if (u == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(p.vpd_counts + vbase * p.rec_stride), "r"((unsigned)__cvta_generic_to_shared(recS)), "r"(rec_bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // written, not merely read out of shared memory
+            }
+        } else {
+            copy_out(reinterpret_cast<float *>(p.vpd_counts + vbase * p.rec_stride), reinterpret_cast<const float *>(recS), N * (p.rec_stride >> 2));
+        }
+    }
     __syncwarp(gmask);                       // the next slot reuses the shared-memory staging
     if (CNT) { if (p.chunk_flag && u == 0) env_records_done(p, e); }
     }   // slot

@@ -117,12 +117,11 @@ def main():
     out["step_host"].append(step_host(env, "full", 1, 4, h_act, h_state, h_rews))
     if args.stream:
         for rep in range(3):
-            for th in sorted({8, max(cpus - 4, 1), max(cpus - 3, 1), max(cpus - 2, 1), max(cpus - 1, 1)}):
-                for direct in (0, 1):
-                    out["step_host"].append(step_host(env, "compact", th, 8, h_act, h_state, h_rews, 0, direct=direct))
-                out["step_host"].append(step_host(env, "compact", th, 16, h_act, h_state, h_rews, 0, direct=1))
-                for ch in (16, 64):
-                    out["step_host"].append(step_host(env, "compact_stream", th, ch, h_act, h_state, h_rews, 0, direct=1))
+            for th in sorted({8, max(cpus - 3, 1), max(cpus - 2, 1), max(cpus - 1, 1)}):
+                out["step_host"].append(step_host(env, "compact", th, 8, h_act, h_state, h_rews, 0))
+                out["step_host"].append(step_host(env, "compact_zero_copy", th, 8, h_act, h_state, h_rews, 0))
+                for ch in (8, 16, 32):
+                    out["step_host"].append(step_host(env, "compact_stream", th, ch, h_act, h_state, h_rews, 0))
         print(json.dumps(out, indent=1))
         return
     for th in sorted({8, 12, max(cpus - 3, 1), max(cpus - 2, 1)}):
