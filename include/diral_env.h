@@ -236,6 +236,13 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
  * = the CPUs the process may run on, minus one) assemble the [E][N][S] float32 rows in h_state, bit for bit what
  * host_format 0 delivers.  State blocks without a fused build (add_positional_dist, VPD type 1) keep format 0.
  *
+ * host_format 3 ("streamed", what diral_b200.TestEnv selects) moves the same records without a copy engine and with
+ * ONE launch per slot: the lane-group kernel reads pinned caller actions in place ("actions_direct"), stages an
+ * environment's records in shared memory, writes them into mapped host memory as one bulk store and -- after a
+ * system-scope fence -- counts the environment into its chunk; the environment that completes a chunk raises that
+ * chunk's flag in host memory, which releases the assembly threads ("stream_chunks" flags per slot, default 16).
+ * Configurations the lane-group kernel does not serve, and calls that also ask for obs, run as host_format 1.
+ *
  * diral_expand_state_host is that row assembly alone (no device involved): agents = E*N records in, rows out. */
 int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t *actions, const uint8_t *counts,
                             const float *rews, const float *obs, const double *pos_x, const double *pos_y,
@@ -258,8 +265,11 @@ int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes
  * row-layout kernel from 97 vehicles on, else round 1's) | 3 round 1's one-CTA-per-env kernel | 4 the row-layout
  * kernel (33..256 vehicles, fused State block); set before diral_bind;
  * "track_lat" = 1 keeps last_arrival_time bookkeeping on even before the first my_step_ch call.
- * diral_step_host: "host_format" (0 full rows | 1 compact), "host_threads", "host_chunks" (env chunks pipelined per
- * call).  Checkpoint restore: "ticks" (table ticks since the reset = every vehicle's own sequence number) and
+ * diral_step_host: "host_format" (0 full rows | 1 compact, records through the copy engine | 2 compact, records written
+ * by the kernels into mapped host memory | 3 streamed: one launch + per-chunk flags), "host_threads", "host_chunks" (env
+ * chunks pipelined per call, formats 1 and 2), "stream_chunks" (flags per slot, format 3), "actions_direct" (pinned
+ * actions read in place: 0 never | 1 format 3 only | 2 always), "host_nt" (row stores: -1 auto | 0 ordinary | 1
+ * non-temporal).  Checkpoint restore: "ticks" (table ticks since the reset = every vehicle's own sequence number) and
  * "lat_live" (a my_step_ch has stamped last_arrival_time); diral_get_option reads any of them back (-1: unknown),
  * plus "compact_ok" (1 when this State block has a compact host format), "kernel" (1 lane-group, 2 round-1
  * one-CTA-per-env, 3 row layout), "layout", "row_stride", "ring_depth" and "scratch_bytes" (what `scratch` must hold
