@@ -47,6 +47,7 @@ EPISODE = 25     # main_test.py:226 episode_interval
 STATE = dict(type=2, add_action=True, add_reward=False, add_index=False, add_velocity=False,
              action_index="binary", piggybacking=False, add_position=False, add_positional_dist=False,
              add_positional_dist_piggy=True, add_positional_dist_type=2, add_channel_obs=False, num_bins=N_BINS)
+PIPE_GROUPS = 4                                   # env groups of the pipelined e2e leg
 ENV_KW = dict(num_users=N_UE, num_channels=N_RES, highway_length=800, reward_design=2, communication_range=250,
               mobility=True, bin_range=500, State=STATE)
 
@@ -393,9 +394,51 @@ def run_gpu(args):
 
     e2e_full = e2e_leg("full")
     e2e_chunked = e2e_leg("compact")
-    e2e_value = e2e_leg("compact_stream")          # the library default
+    e2e_sync = e2e_leg("compact_stream")           # the library default, one synchronous call per slot
     e2e_format = env.host_format
+
+    # --- the same workload as PIPE_GROUPS groups of environments stepped with diral_step_host_begin / _wait: one group's
+    # kernel and PCIe records overlap the row assembly of the others (every group: host actions in, host rows out)
+    def e2e_pipelined():
+        Eg = E_PER_GPU // PIPE_GROUPS
+        genvs, gbufs = [], []
+        for g in range(PIPE_GROUPS):
+            ge = TestEnv(num_envs=Eg, device=dev, seed=1234, env_offset=rank * E_PER_GPU + g * Eg, **ENV_KW)
+            ge.set_host_format("compact_stream", host_threads, shared_pool=True)
+            ge.lib.diral_set_option(ge._handle, b"stream_chunks", 4)
+            ge.host_stream = torch.cuda.Stream(dev)
+            acts = [ge.sample(t) for t in range(8)]
+            for t in range(100):
+                ge.step(acts[t % 8])
+            genvs.append(ge)
+            gbufs.append(([a.cpu().pin_memory() for a in acts], torch.empty((Eg, N_UE, S), dtype=torch.float32).pin_memory(),
+                          torch.empty((Eg, N_UE), dtype=torch.float32).pin_memory()))
+        torch.cuda.synchronize(dev)
+
+        def run(n):
+            for g, ge in enumerate(genvs):
+                ge.step_host_begin(gbufs[g][0][0], gbufs[g][1], gbufs[g][2])
+            for k in range(1, n):
+                for g, ge in enumerate(genvs):
+                    ge.step_host_wait()
+                    ge.step_host_begin(gbufs[g][0][k % 8], gbufs[g][1], gbufs[g][2])
+            for ge in genvs:
+                ge.step_host_wait()
+
+        run(4)
+        barrier()
+        t0 = time.perf_counter()
+        run(e2e_steps)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for ge in genvs:
+            ge.close()
+        return world * Eg * PIPE_GROUPS * N_UE * e2e_steps / float(t.item())
+
     host_threads = int(env.lib.diral_get_option(env._handle, b"host_threads"))
+    e2e_value = e2e_pipelined()
     h2d = E_PER_GPU * N_UE * 4
     d2h_full = E_PER_GPU * N_UE * (S + 1) * 4
     d2h = E_PER_GPU * N_UE * (N_BINS + 4)          # one byte per VPD bin + the float32 reward
@@ -425,12 +468,16 @@ def run_gpu(args):
             "data": "synthetic", "config": workload_config(world), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "host_threads": host_threads,
-                    "host_format": e2e_format,
-                    "api": "diral_step_host (C ABI, pinned host buffers, synchronous), host_format=compact_stream (the "
-                           "default): ONE launch per slot reads the pinned actions in place and writes per-agent records "
+                    "host_format": e2e_format, "env_groups": PIPE_GROUPS,
+                    "api": "diral_step_host_begin / diral_step_host_wait (C ABI, pinned host buffers), host_format="
+                           "compact_stream: the %d environments of this GPU are stepped as %d groups of %d, round robin, "
+                           "so that one group's launch and PCIe records overlap the row assembly of the others.  Per "
+                           "group and slot: ONE launch reads the pinned actions in place and writes per-agent records "
                            "(1 B per VPD bin + the float32 reward) into mapped host memory, raising a flag per chunk of "
                            "environments; the [E,N,S] float32 rows are assembled in the caller's buffer by the library's "
-                           "host threads inside the timed region"},
+                           "host threads, all inside the timed region.  extra.e2e_synchronous is the same workload as "
+                           "one blocking diral_step_host call per slot"
+                           % (E_PER_GPU, PIPE_GROUPS, E_PER_GPU // PIPE_GROUPS)},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "step_group_kernel<32>",
@@ -439,6 +486,9 @@ def run_gpu(args):
                       "note": "value_l2_resident_no_flush = same loop without the L2 flush (state fits the 126 MB L2)",
                       "e2e_full_format": {"value": e2e_full, "unit": UNIT, "d2h_bytes_per_step": d2h_full,
                                           "note": "same call, host_format=full: the float32 rows themselves cross PCIe"},
+                      "e2e_synchronous": {"value": e2e_sync, "unit": UNIT, "d2h_bytes_per_step": d2h,
+                                          "note": "one blocking diral_step_host call per slot over all %d environments "
+                                                  "(host_format=compact_stream)" % E_PER_GPU},
                       "e2e_compact_chunked": {"value": e2e_chunked, "unit": UNIT, "d2h_bytes_per_step": d2h,
                                               "note": "same call, host_format=compact: 8 env chunks, each on its own stream "
                                                       "(copy in, slot kernel, records out through the copy engine)"},

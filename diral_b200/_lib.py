@@ -10,7 +10,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MODES = {"my_step": 0, "my_step_design": 1, "my_step_ch": 2}
 ERR_NAMES = {-1: "DIRAL_ERR_ARG", -2: "DIRAL_ERR_CUDA", -3: "DIRAL_ERR_UNBOUND", -4: "DIRAL_ERR_SEQ_RANGE",
              -5: "DIRAL_ERR_UNSUPPORTED"}
@@ -76,6 +76,8 @@ SYMBOLS = {
     "diral_wire_vpd": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _D, _I32, _P, _P]),
     "diral_sps_step": (C.c_int, [_I64, _I32, _P, C.POINTER(DiralSpsCfg), _P, _U64, _I64, _P, _P, _P, _P, _P]),
     "diral_step_host": (C.c_int, [_P, C.c_int, _P, _I64, _D, _D, _P, _P, _P, _P]),
+    "diral_step_host_begin": (C.c_int, [_P, C.c_int, _P, _I64, _D, _D, _P, _P, _P]),
+    "diral_step_host_wait": (C.c_int, [_P]),
     "diral_launch_count": (C.c_int64, [_P]),
     "diral_get_option": (C.c_int64, [_P, C.c_char_p]),
     "diral_reset_topology": (C.c_int, [_P, _P, _P, _P, _U64, _P]),

@@ -76,12 +76,17 @@ struct Handle {
     unsigned *h_chunk_flag = nullptr;     // [MAX_HOST_CHUNKS] mapped pinned flags
     unsigned *d_chunk_flag = nullptr;     // device address of the same
     unsigned chunk_epoch = 0;
+    bool async_pending = false;     // diral_step_host_begin without its diral_step_host_wait yet
+    cudaStream_t async_stream = nullptr;
     uint8_t *d_counts_mapped = nullptr;   // device address of h_counts (mapped pinned allocation)
     int host_threads = 0;           // 0 = pick from the CPUs this process may run on
     int host_chunks = 8;
     int tail_split = 0;             // see Params::tail_split (opt-in: it shortens a small tail wave, not a saturated device)
     int host_nt = -1;               // output-row stores: 1 non-temporal, 0 ordinary, -1 by output size per thread
     diral::HostPool *pool = nullptr;
+    bool pool_shared = false;       // `pool` is the process-wide one (not owned)
+    int want_shared_pool = 0;       // option "host_pool_shared"
+    unsigned long long job_id = 0;  // the pool job of the slot in flight
     uint8_t *d_counts = nullptr;    // [E][N][B] device
     uint8_t *h_counts = nullptr;    // pinned staging of the same
     float *h_obs_stage = nullptr;   // pinned [E][N][R] when the State block wants obs and the caller passes no h_obs
@@ -306,10 +311,21 @@ int usable_cpus()
 
 // ends a row-assembly job on every exit path: a worker must never be left spinning on a chunk that will not come
 struct PoolJobGuard {
-    diral::HostPool *pool; int chunks; bool closed = false;
-    void close() { if (!closed) { pool->publish(chunks - 1); pool->finish(); closed = true; } }
-    ~PoolJobGuard() { close(); }
+    diral::HostPool *pool; unsigned long long id; int chunks; bool closed = false;
+    void close() { if (!closed) { pool->publish(id, chunks - 1); pool->finish(id); closed = true; } }
+    ~PoolJobGuard() { if (!closed) { pool->abort(id); close(); } }     // error path: the missing chunks are skipped
 };
+
+// one process-wide pool for the handles that ask for it ("host_pool_shared"): groups of environments stepped with
+// diral_step_host_begin / _wait then take turns on ALL assembly threads instead of idling on a private share
+diral::HostPool *shared_pool(int threads)
+{
+    static std::mutex mu;
+    static std::unique_ptr<diral::HostPool> pool;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pool) pool.reset(new (std::nothrow) diral::HostPool(threads));
+    return pool.get();
+}
 
 // diral_step_host, compact host format: only the information of a slot crosses PCIe -- per agent one record of VPD
 // bin counts (one byte per bin) and the float32 reward, plus obs / positions / velocities when the State block
@@ -317,7 +333,7 @@ struct PoolJobGuard {
 // env chunks are still in flight.  A chunk is latency-bound on the device (copy in, one slot kernel, copy out: ~45 us
 // whatever its size), so every chunk runs on its own stream and all of them overlap.
 int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
-                      float *h_state, float *h_rews, float *h_obs, cudaStream_t s)
+                      float *h_state, float *h_rews, float *h_obs, cudaStream_t s, bool async_begin = false)
 {
     const auto t_entry = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_entry).count(); };
@@ -338,6 +354,9 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     // zero-copy: the lane-group kernel stages an environment's records in shared memory and writes them out as one
     // coalesced stream, so they can go over PCIe as the kernel runs instead of through a copy engine afterwards
     const bool streamed = h->host_format == 3 && group && h->d_counts_mapped != nullptr && !want_obs && !h_obs && !want_kin;
+    if (async_begin && !streamed)
+        return fail(DIRAL_ERR_UNSUPPORTED, "diral_step_host_begin needs host_format 3 on a configuration the lane-group kernel "
+                                           "serves (N <= 32, fused State block without obs / positions / velocities)");
     const bool zero_copy = (h->host_format == 2 || streamed) && group && h->d_counts_mapped != nullptr;
     if (want_obs && !h_obs && !h->h_obs_stage) DIRAL_CUDA(cudaMallocHost(&h->h_obs_stage, sizeof(float) * (size_t)(A * R)));
     if (want_kin && !h->h_kin) DIRAL_CUDA(cudaMallocHost(&h->h_kin, sizeof(double) * (size_t)(3 * A)));
@@ -361,7 +380,8 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     }
     if (!h->pool) {
         int n = h->host_threads > 0 ? h->host_threads : std::min(std::max(usable_cpus() - 2, 1), 32);
-        h->pool = new (std::nothrow) diral::HostPool(n);
+        h->pool_shared = h->want_shared_pool != 0;
+        h->pool = h->pool_shared ? shared_pool(n) : new (std::nothrow) diral::HostPool(n);
         if (!h->pool) return fail(DIRAL_ERR_ARG, "out of host memory");
     }
 
@@ -386,8 +406,11 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     // a worker's share of the rows stays in its private L2 from call to call when it is small enough
     lay.nt_stores = h->host_nt >= 0 ? h->host_nt
                                     : ((size_t)A * lay.S * sizeof(float) / (size_t)h->pool->threads() > (size_t)(1 << 20) + (1 << 19));
-    h->pool->begin(lay, job, bounds, chunks);
-    PoolJobGuard guard{h->pool, chunks};
+    unsigned epoch = 0;
+    if (streamed) epoch = ++h->chunk_epoch ? h->chunk_epoch : ++h->chunk_epoch;         // never 0: flags start there
+    // (asynchronous begin: the assembly threads watch the device-raised flags themselves)
+    h->job_id = h->pool->begin(lay, job, bounds, chunks, async_begin ? h->h_chunk_flag : nullptr, epoch);
+    PoolJobGuard guard{h->pool, h->job_id, chunks};
     h->trace_us[0] = since();                                      // workers woken
 
     // Pinned caller memory is read in place by the kernels (unified addressing: one PCIe read of 4 N bytes per environment
@@ -406,12 +429,17 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         // raises a chunk's flag when its last environment is through (env_records_done); this thread forwards the flags
         // to the assembly workers.
         if (!direct) DIRAL_CUDA(cudaMemcpyAsync(h->d_actions, h_actions, (size_t)A * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        const unsigned epoch = ++h->chunk_epoch ? h->chunk_epoch : ++h->chunk_epoch;     // never 0: flags start there
         p.chunk_count = h->d_chunk_count; p.chunk_flag = h->d_chunk_flag; p.chunk_envs = (int)chunk_envs; p.chunk_epoch = epoch;
         DIRAL_CUDA(launch_slot(h, p, s));
         h->launches += 1;
         if (c.add_piggy) h->ticks += 1;
         h->trace_us[1] = since();                                  // everything enqueued
+        if (async_begin) {                                         // diral_step_host_wait picks it up from here
+            guard.closed = true;
+            h->async_pending = true; h->async_stream = s;
+            h->trace_n = 2;
+            return DIRAL_OK;
+        }
         volatile unsigned *flags = h->h_chunk_flag;
         for (int k = 0; k < chunks; ++k) {
             for (unsigned spins = 1; flags[k] != epoch; ++spins) {
@@ -425,7 +453,7 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
                 }
             }
             std::atomic_thread_fence(std::memory_order_acquire);
-            h->pool->publish(k);
+            h->pool->publish(h->job_id, k);
             h->trace_us[2 + k] = since();                          // chunk k's records are in host memory
         }
         guard.close();
@@ -460,7 +488,7 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         DIRAL_CUDA(cudaEventRecord(h->chunk_ev[k], ps));
         // earlier chunks may have landed while this one was being enqueued: release their rows now
         while (published < k && cudaEventQuery(h->chunk_ev[published]) == cudaSuccess) {
-            h->pool->publish(published);
+            h->pool->publish(h->job_id, published);
             h->trace_us[2 + published++] = since();
         }
         cudaGetLastError();                                        // (cudaErrorNotReady is not an error)
@@ -471,7 +499,7 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
     h->trace_us[1] = since();                                      // everything enqueued
     for (int k = published; k < chunks; ++k) {                     // rows of chunk k are assembled while k+1.. are in flight
         DIRAL_CUDA(cudaEventSynchronize(h->chunk_ev[k]));
-        h->pool->publish(k);
+        h->pool->publish(h->job_id, k);
         h->trace_us[2 + k] = since();                              // chunk k's records are in host memory
     }
     guard.close();
@@ -566,7 +594,7 @@ int diral_destroy(void *handle)
     for (auto &ev : h->pipe_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->chunk_ev) if (ev) cudaEventDestroy(ev);
     for (auto &st : h->chunk_stream) if (st) cudaStreamDestroy(st);
-    delete h->pool;
+    if (!h->pool_shared) delete h->pool;
     cudaFree(h->d_counts);
     cudaFree(h->d_chunk_count);
     if (h->h_chunk_flag) cudaFreeHost(h->h_chunk_flag);
@@ -609,7 +637,7 @@ int diral_set_option(void *handle, const char *name, int64_t value)
     }
     if (!strcmp(name, "host_threads")) {
         if (value < 0 || value > 256) return fail(DIRAL_ERR_ARG, "host_threads must be in [0, 256]");
-        if (h->pool && h->pool->threads() != (int)value) { delete h->pool; h->pool = nullptr; }
+        if (h->pool && !h->pool_shared && h->pool->threads() != (int)value) { delete h->pool; h->pool = nullptr; }
         h->host_threads = (int)value;
         return DIRAL_OK;
     }
@@ -626,6 +654,11 @@ int diral_set_option(void *handle, const char *name, int64_t value)
     if (!strcmp(name, "host_chunks")) {
         if (value < 1 || value > 32) return fail(DIRAL_ERR_ARG, "host_chunks must be in [1, 32]");
         h->host_chunks = (int)value;
+        return DIRAL_OK;
+    }
+    if (!strcmp(name, "host_pool_shared")) {
+        if (h->pool && (value != 0) != h->pool_shared) { if (!h->pool_shared) delete h->pool; h->pool = nullptr; }
+        h->want_shared_pool = value != 0;
         return DIRAL_OK;
     }
     if (!strcmp(name, "stream_chunks")) {
@@ -663,6 +696,7 @@ int64_t diral_get_option(void *handle, const char *name)
     if (!strcmp(name, "host_threads")) return h->pool ? h->pool->threads() : h->host_threads;
     if (!strcmp(name, "host_chunks")) return h->host_chunks;
     if (!strcmp(name, "stream_chunks")) return h->stream_chunks;
+    if (!strcmp(name, "host_pool_shared")) return h->want_shared_pool;
     if (!strcmp(name, "actions_direct")) return h->actions_direct;
     if (!strcmp(name, "host_nt")) return h->host_nt;
     if (!strcmp(name, "tail_split")) return h->tail_split;
@@ -933,6 +967,7 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
     if (int rc = require_bound(h)) return rc;
     if (!h_actions || !h_state || !h_rews) return fail(DIRAL_ERR_ARG, "h_actions/h_state/h_rews must not be NULL");
     if (mode < DIRAL_MY_STEP || mode > DIRAL_MY_STEP_CH) return fail(DIRAL_ERR_ARG, "mode must be 0, 1 or 2 (got %d)", mode);
+    if (h->async_pending) return fail(DIRAL_ERR_ARG, "a begun slot is pending: call diral_step_host_wait first");
     if (int rc = ensure_actions_staging(h)) return rc;
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -990,6 +1025,43 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
     return DIRAL_OK;
 }
 
+int diral_step_host_begin(void *handle, int mode, const int32_t *h_actions, int64_t timestep, double episode, double epsilon,
+                          float *h_state, float *h_rews, void *stream)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!h_actions || !h_state || !h_rews) return fail(DIRAL_ERR_ARG, "h_actions/h_state/h_rews must not be NULL");
+    if (mode < DIRAL_MY_STEP || mode > DIRAL_MY_STEP_CH) return fail(DIRAL_ERR_ARG, "mode must be 0, 1 or 2 (got %d)", mode);
+    if (h->async_pending) return fail(DIRAL_ERR_ARG, "a begun slot is pending: call diral_step_host_wait first");
+    if (h->host_format != 3 || !compact_ok(h->cfg))
+        return fail(DIRAL_ERR_UNSUPPORTED, "diral_step_host_begin needs host_format 3 and a State block with a compact host format");
+    if (int rc = ensure_actions_staging(h)) return rc;
+    DeviceGuard g(h->device);
+    return step_host_compact(h, mode, h_actions, timestep, episode, epsilon, h_state, h_rews, nullptr,
+                             static_cast<cudaStream_t>(stream), true);
+}
+
+int diral_step_host_wait(void *handle)
+{
+    Handle *h = as_handle(handle);
+    if (int rc = require_bound(h)) return rc;
+    if (!h->async_pending) return DIRAL_OK;
+    DeviceGuard g(h->device);
+    h->async_pending = false;
+    for (unsigned spins = 1; !h->pool->done(h->job_id); ++spins) {
+        _mm_pause();
+        if ((spins & 0xfff) == 0) {                                // every few tens of microseconds: is the launch still alive?
+            const cudaError_t q = cudaStreamQuery(h->async_stream);
+            if (q == cudaSuccess || q == cudaErrorNotReady) { cudaGetLastError(); continue; }
+            h->pool->abort(h->job_id); h->pool->finish(h->job_id);
+            return fail(DIRAL_ERR_CUDA, "slot kernel failed: %s", cudaGetErrorString(q));
+        }
+    }
+    h->pool->finish(h->job_id);
+    DIRAL_CUDA(cudaStreamSynchronize(h->async_stream));            // the launch itself retires (tables, accumulators)
+    return DIRAL_OK;
+}
+
 int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t *actions, const uint8_t *counts,
                             const float *rews, const float *obs, const double *pos_x, const double *pos_y,
                             const double *vel, double episode, double epsilon, int32_t threads, float *out)
@@ -1015,12 +1087,15 @@ int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t 
     static std::vector<std::unique_ptr<diral::HostPool>> pools;
     std::lock_guard<std::mutex> lock(mu);
     diral::HostPool *pool = nullptr;
+    bool pool_shared = false;       // `pool` is the process-wide one (not owned)
+    int want_shared_pool = 0;       // option "host_pool_shared"
+    unsigned long long job_id = 0;  // the pool job of the slot in flight
     for (auto &q : pools) if (q->threads() == threads) pool = q.get();
     if (!pool) { pools.emplace_back(new diral::HostPool(threads)); pool = pools.back().get(); }
     const long long bounds[3] = {0, (agents / 2) & ~3ll, agents};      // two chunks: exercises the chunk hand-over too
-    pool->begin(lay, job, bounds, 2);
-    pool->publish(0); pool->publish(1);
-    pool->finish();
+    const unsigned long long id = pool->begin(lay, job, bounds, 2);
+    pool->publish(id, 0); pool->publish(id, 1);
+    pool->finish(id);
     return DIRAL_OK;
 }
 

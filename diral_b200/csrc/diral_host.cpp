@@ -407,19 +407,28 @@ void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long l
 }
 
 struct HostPool::Impl {
+    static constexpr int RING = 8;       // jobs that can be queued at once
+    struct Slot {
+        std::atomic<unsigned long long> id{0};   // the job in this slot
+        HostLayout lay{};
+        HostJob job{};
+        long long bounds[HostPool::MAX_CHUNKS + 1] = {};
+        int nchunks = 0;
+        std::atomic<int> ready{0};           // chunks whose inputs are in host memory ...
+        const volatile unsigned *flags = nullptr;   // ... or per-chunk words raised by the device (== epoch: chunk landed)
+        unsigned epoch = 0;
+        std::atomic<bool> aborted{false};
+        std::atomic<int> done{0};            // workers that have finished the job
+    };
     std::vector<std::thread> workers;
-    std::mutex mu;
+    std::mutex mu, post_mu;
     std::condition_variable cv;
-    std::atomic<unsigned long long> job_seq{0};
+    std::atomic<unsigned long long> posted{0};   // jobs queued so far (ids 1 .. posted)
     bool stop = false;                   // guarded by mu
-    // the running job (written by begin() before job_seq moves)
-    HostLayout lay{};
-    HostJob job{};
-    std::vector<long long> bounds;
-    int nchunks = 0;
-    std::atomic<int> ready{0};           // chunks whose inputs are in host memory
-    std::atomic<int> done{0};            // workers that have finished the job
+    Slot ring[RING];
     int hot_us = 200;                    // how long a worker keeps polling for the next job before it sleeps
+
+    Slot &slot(unsigned long long id) { return ring[id % RING]; }
 
     void run(int idx, int nthreads)
     {
@@ -430,29 +439,35 @@ struct HostPool::Impl {
             bool have = false;
             const auto t0 = std::chrono::steady_clock::now();
             for (int spins = 0; ; ++spins) {
-                if (job_seq.load(std::memory_order_acquire) != seen) { have = true; break; }
+                if (posted.load(std::memory_order_acquire) > seen) { have = true; break; }
                 _mm_pause();
                 if ((spins & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(hot_us)) break;
             }
             if (!have) {
                 std::unique_lock<std::mutex> lock(mu);
-                cv.wait(lock, [&] { return stop || job_seq.load(std::memory_order_acquire) != seen; });
+                cv.wait(lock, [&] { return stop || posted.load(std::memory_order_acquire) > seen; });
                 if (stop) return;
             }
-            seen = job_seq.load(std::memory_order_acquire);
-            for (int c = 0; c < nchunks; ++c) {
+            ++seen;
+            Slot &s = slot(seen);
+            const volatile unsigned *flags = s.flags;
+            for (int c = 0; c < s.nchunks; ++c) {
                 int spins = 0;
-                while (ready.load(std::memory_order_acquire) <= c) {
+                bool gone = false;
+                while (flags ? flags[c] != s.epoch : s.ready.load(std::memory_order_acquire) <= c) {
+                    if (s.aborted.load(std::memory_order_relaxed)) { gone = true; break; }
                     _mm_pause();
                     if (++spins > 20000) { std::this_thread::yield(); spins = 0; }
                 }
+                if (gone) break;
+                std::atomic_thread_fence(std::memory_order_acquire);
                 // this worker's share of chunk c, cut at multiples of 4 agents (16-byte aligned row ranges)
-                const long long lo = bounds[c], n = bounds[c + 1] - lo;
+                const long long lo = s.bounds[c], n = s.bounds[c + 1] - lo;
                 long long s0 = (n * idx / nthreads) & ~3ll, s1 = (n * (idx + 1) / nthreads) & ~3ll;
                 if (idx == nthreads - 1) s1 = n;
-                if (s1 > s0) expand_rows(lay, job, lo + s0, lo + s1);
+                if (s1 > s0) expand_rows(s.lay, s.job, lo + s0, lo + s1);
             }
-            done.fetch_add(1, std::memory_order_release);
+            s.done.fetch_add(1, std::memory_order_release);
         }
     }
 };
@@ -478,27 +493,51 @@ HostPool::~HostPool()
 
 int HostPool::threads() const { return (int)impl->workers.size(); }
 
-void HostPool::begin(const HostLayout &lay, const HostJob &job, const long long *bounds, int nchunks)
+unsigned long long HostPool::begin(const HostLayout &lay, const HostJob &job, const long long *bounds, int nchunks,
+                                   const volatile unsigned *flags, unsigned epoch)
 {
-    impl->lay = lay; impl->job = job;
-    impl->bounds.assign(bounds, bounds + nchunks + 1);
-    impl->nchunks = nchunks;
-    impl->ready.store(0, std::memory_order_relaxed);
-    impl->done.store(0, std::memory_order_relaxed);
+    std::lock_guard<std::mutex> post(impl->post_mu);         // callers on different threads queue one at a time
+    const unsigned long long id = impl->posted.load(std::memory_order_relaxed) + 1;
+    Impl::Slot &s = impl->slot(id);
+    if (id > Impl::RING) finish(id - Impl::RING);            // the slot's previous job (long done in any sane use)
+    s.lay = lay; s.job = job;
+    s.nchunks = nchunks < MAX_CHUNKS ? nchunks : MAX_CHUNKS;
+    for (int c = 0; c <= s.nchunks; ++c) s.bounds[c] = bounds[c];
+    s.flags = flags; s.epoch = epoch;
+    s.ready.store(0, std::memory_order_relaxed);
+    s.done.store(0, std::memory_order_relaxed);
+    s.aborted.store(false, std::memory_order_relaxed);
+    s.id.store(id, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> lock(impl->mu);          // (a worker between its spin phase and cv.wait sees the new value)
-        impl->job_seq.fetch_add(1, std::memory_order_release);
+        impl->posted.store(id, std::memory_order_release);
     }
     impl->cv.notify_all();
+    return id;
 }
 
-void HostPool::publish(int chunk) { impl->ready.store(chunk + 1, std::memory_order_release); }
-
-void HostPool::finish()
+void HostPool::publish(unsigned long long id, int chunk)
 {
-    const int n = (int)impl->workers.size();
+    Impl::Slot &s = impl->slot(id);
+    if (s.id.load(std::memory_order_relaxed) == id) s.ready.store(chunk + 1, std::memory_order_release);
+}
+
+bool HostPool::done(unsigned long long id) const
+{
+    const Impl::Slot &s = impl->slot(id);
+    return s.id.load(std::memory_order_acquire) != id || s.done.load(std::memory_order_acquire) >= (int)impl->workers.size();
+}
+
+void HostPool::abort(unsigned long long id)
+{
+    Impl::Slot &s = impl->slot(id);
+    if (s.id.load(std::memory_order_relaxed) == id) s.aborted.store(true, std::memory_order_release);
+}
+
+void HostPool::finish(unsigned long long id)
+{
     int spins = 0;
-    while (impl->done.load(std::memory_order_acquire) < n) {
+    while (!done(id)) {
         _mm_pause();
         if (++spins > 20000) { std::this_thread::yield(); spins = 0; }
     }

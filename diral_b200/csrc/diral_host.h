@@ -34,17 +34,24 @@ struct HostJob {                    // one call: per-agent inputs (index a = env
 // rows [a0, a1) of one job, on the calling thread
 void expand_rows(const HostLayout &lay, const HostJob &job, long long a0, long long a1);
 
-// Persistent worker threads.  begin() wakes them for one job split into `nchunks` consecutive agent ranges
-// [bounds[c], bounds[c+1]); publish(c) says chunk c's inputs have landed in host memory; finish() waits until every
-// row has been written.  The workers sleep between jobs and spin (pause) inside one.
+// Persistent worker threads with a small FIFO of jobs, so that several handles (groups of environments stepped with
+// diral_step_host_begin / _wait) can share one pool: begin() queues a job split into `nchunks` consecutive agent ranges
+// [bounds[c], bounds[c+1]) and returns its id; a chunk is released either by publish(id, c) ("chunk c's inputs have
+// landed in host memory") or, when `flags` is given, by the device itself (flags[c] == epoch: words the slot kernel
+// raises in mapped host memory); finish(id) waits until every row of that job has been written.  The workers take
+// the jobs in the order they were queued, sleep between bursts and spin (pause) inside one.
 class HostPool {
 public:
+    static constexpr int MAX_CHUNKS = 64;
     explicit HostPool(int threads);
     ~HostPool();
     int threads() const;
-    void begin(const HostLayout &lay, const HostJob &job, const long long *bounds, int nchunks);
-    void publish(int chunk);
-    void finish();
+    unsigned long long begin(const HostLayout &lay, const HostJob &job, const long long *bounds, int nchunks,
+                             const volatile unsigned *flags = nullptr, unsigned epoch = 0);
+    void publish(unsigned long long id, int chunk);
+    void finish(unsigned long long id);
+    bool done(unsigned long long id) const;     // every worker through with that job (non-blocking)
+    void abort(unsigned long long id);          // the chunks still missing will never come: workers skip them
 private:
     struct Impl;
     Impl *impl;

@@ -133,6 +133,8 @@ class TestEnv:
         self.layout = int(self.lib.diral_get_option(self._handle, b"layout"))
         self.T = int(self.lib.diral_get_option(self._handle, b"row_stride"))
         self.H = int(self.lib.diral_get_option(self._handle, b"ring_depth"))
+        self.host_stream = None          # torch.cuda.Stream for this env's launches (None: the current stream); envs
+                                         # pipelined with step_host_begin / step_host_wait want one each
         self.set_host_format(host_format, host_threads)
         self._alloc()
         self._trace = None
@@ -199,13 +201,15 @@ class TestEnv:
         except Exception:
             pass
 
-    def set_host_format(self, host_format="compact_stream", host_threads=None):
+    def set_host_format(self, host_format="compact_stream", host_threads=None, shared_pool=False):
         """How ``step_host`` moves a slot's results to the host: ``"full"`` copies the [E, N, S] float32 rows over
         PCIe; ``"compact"`` copies only what the host cannot know (VPD bin counts as bytes, rewards, ...) and lets
         ``host_threads`` library threads assemble the same rows in the caller's buffer (include/diral_env.h);
         ``"compact_stream"`` is the same record written by ONE launch straight into mapped host memory, the kernel
         raising a flag per chunk of environments that releases the assembly threads (lane-group kernel).
-        ``host_threads=None``: the CPUs this process may use, shared between the ranks of a torchrun job."""
+        ``host_threads=None``: the CPUs this process may use, shared between the ranks of a torchrun job.
+        ``shared_pool=True``: this env's rows are assembled by the process-wide pool (sized by the first env that asks
+        for it) -- what several envs pipelined with ``step_host_begin`` / ``step_host_wait`` should use."""
         formats = {"full": 0, "compact": 1, "compact_zero_copy": 2, "compact_stream": 3}
         if host_format not in formats:
             raise ValueError("host_format must be one of %s" % ", ".join(repr(k) for k in formats))
@@ -217,10 +221,13 @@ class TestEnv:
             share = cpus // local
             host_threads = max(min(share - (2 if share >= 8 else 1), 32), 1)   # room for the caller and the CUDA runtime's threads
         check(self.lib.diral_set_option(self._handle, b"host_threads", int(host_threads)))
+        check(self.lib.diral_set_option(self._handle, b"host_pool_shared", int(bool(shared_pool))))
         self.host_format = host_format if self.lib.diral_get_option(self._handle, b"compact_ok") else "full"
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
+        if self.host_stream is not None:
+            return C.c_void_p(self.host_stream.cuda_stream)
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _as_actions(self, actions):
@@ -391,6 +398,21 @@ class TestEnv:
                                            float(episode_number), float(epsilon), ptr(h_state), ptr(h_rews),
                                            ptr(h_obs) if h_obs is not None else None, self._stream()))
         self.t += 1
+
+    def step_host_begin(self, h_actions, h_state, h_rews, mode=None, episode_number=0, epsilon=1):
+        """First half of ``step_host`` (diral_step_host_begin, ``host_format="compact_stream"`` on a lane-group
+        configuration): enqueues the slot and returns; ``step_host_wait`` returns once ``h_state`` / ``h_rews`` hold
+        it.  Two or more envs stepped this way overlap one env's kernel and PCIe records with another's row assembly
+        (give each its own ``host_threads`` share)."""
+        mode = mode or ("my_step_ch" if self.enable_channel else "my_step")
+        ptr = lambda t: t.data_ptr() if isinstance(t, torch.Tensor) else t.ctypes.data
+        check(self.lib.diral_step_host_begin(self._handle, MODES[mode], ptr(h_actions), C.c_int64(self.t),
+                                             float(episode_number), float(epsilon), ptr(h_state), ptr(h_rews),
+                                             self._stream()))
+        self.t += 1
+
+    def step_host_wait(self):
+        check(self.lib.diral_step_host_wait(self._handle))
 
     # ------------------------------------------------------------------ metrics
     def information_age(self, timestep):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DIRAL_ABI_VERSION 2
+#define DIRAL_ABI_VERSION 3
 
 enum {
     DIRAL_OK = 0,
@@ -227,6 +227,16 @@ int diral_sps_step(int64_t agents, int32_t window_len, const double *selection_w
 int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t timestep,
                     double episode, double epsilon, float *h_state, float *h_rews, float *h_obs,
                     void *stream);
+
+/* diral_step_host in two halves ("host_format" 3 only): _begin enqueues the slot (one launch on `stream`, a few
+ * microseconds) and returns; _wait returns once every state row and reward of that slot is in the caller's buffers
+ * and the launch has retired.  A caller that keeps two or more handles (groups of environments) in flight overlaps
+ * one group's kernel and PCIe records with the row assembly of another.  The buffers passed to _begin must stay
+ * untouched until _wait; no other call on the handle in between.  DIRAL_ERR_UNSUPPORTED where host_format 3 does not
+ * apply (use diral_step_host). */
+int diral_step_host_begin(void *handle, int mode, const int32_t *h_actions, int64_t timestep,
+                          double episode, double epsilon, float *h_state, float *h_rews, void *stream);
+int diral_step_host_wait(void *handle);
 
 /* Compact host format of diral_step_host ("host_format" = 1, opt-in): the state rows of TestEnv.obtain_state
  * (test_env.py:527-583) are mostly known to the host already (the one-hot of the action it sent, index, episode,

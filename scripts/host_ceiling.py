@@ -86,13 +86,59 @@ def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, nt=-1, reps=40,
             "agent_steps_per_s": E_PER_GPU * N_UE / dt}
 
 
+def pipelined(groups, threads_each, chunks, reps=60, shared=False):
+    """diral_step_host_begin / _wait over `groups` handles of E / groups environments each, round robin."""
+    E = E_PER_GPU // groups
+    envs = [TestEnv(num_envs=E, device="cuda:0", seed=100 + g, host_threads=threads_each, **ENV_KW) for g in range(groups)]
+    bufs = []
+    for env in envs:
+        env.set_host_format("compact_stream", threads_each, shared_pool=shared)
+        env.host_stream = torch.cuda.Stream(env.device)
+        env.lib.diral_set_option(env._handle, b"stream_chunks", chunks)
+        acts = [env.sample(t).cpu().pin_memory() for t in range(8)]
+        for t in range(40):
+            env.step()
+        bufs.append((acts, torch.empty((E, N_UE, env.S), dtype=torch.float32).pin_memory(),
+                     torch.empty((E, N_UE), dtype=torch.float32).pin_memory()))
+    torch.cuda.synchronize()
+
+    def run(n):
+        for g, env in enumerate(envs):
+            env.step_host_begin(bufs[g][0][0], bufs[g][1], bufs[g][2])
+        for k in range(1, n):
+            for g, env in enumerate(envs):
+                env.step_host_wait()
+                env.step_host_begin(bufs[g][0][k % 8], bufs[g][1], bufs[g][2])
+        for env in envs:
+            env.step_host_wait()
+
+    run(6)
+    t0 = time.perf_counter()
+    run(reps)
+    dt = (time.perf_counter() - t0) / reps
+    for env in envs:
+        env.close()
+    return {"groups": groups, "envs_per_group": E, "threads_per_group": threads_each, "shared_pool": shared, "stream_chunks": chunks,
+            "us_per_slot_of_all_groups": dt * 1e6, "agent_steps_per_s": E * groups * N_UE / dt}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--quick", action="store_true", help="copy ceilings and the row-assembly rate only (multi-GPU boxes are charged per GPU)")
+    ap.add_argument("--pipeline", action="store_true", help="diral_step_host_begin / _wait over 2..4 env groups")
     ap.add_argument("--stream", action="store_true", help="diral_step_host only: chunked copy-engine format against the streamed one")
     args = ap.parse_args()
     cpus = len(os.sched_getaffinity(0))
+    if args.pipeline:
+        res = []
+        total = int(os.environ.get("DIRAL_POOL_THREADS", cpus - 2))      # (the shared pool keeps the size of its first user)
+        for rep in range(3):
+            for groups in (1, 2, 3, 4):
+                for chunks in (4, 8):
+                    res.append(pipelined(groups, total, chunks, reps=100, shared=True))
+                    print(json.dumps(res[-1]), flush=True)
+        return
     out = {"cpu_model": cpu_model(), "cpus_usable": cpus, "cpu_count": os.cpu_count(), "d2h": [], "expander": [], "step_host": []}
     full = E_PER_GPU * N_UE * 41 * 4
     compact = E_PER_GPU * N_UE * 24

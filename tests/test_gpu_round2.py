@@ -176,6 +176,46 @@ def test_compact_host_format_is_bit_identical(n, r, E, state, extra):
         e.close()
 
 
+def test_step_host_begin_wait_pipelines_two_env_groups():
+    """diral_step_host_begin / _wait: two handles in flight at once (each its own stream and assembly threads) deliver
+    the rows the synchronous call does; misuse is refused."""
+    from diral_b200 import DiralError
+    kw = dict(num_users=32, num_channels=20, highway_length=800, reward_design=2, communication_range=250,
+              mobility=True, bin_range=500, State=_state())
+    E = 1536
+    sync = [_env(E, seed=s, host_threads=3, **kw) for s in (5, 6)]
+    pipe = [_env(E, seed=s, host_threads=3, **kw) for s in (5, 6)]
+    for e in pipe:
+        e.set_host_format("compact_stream", 4, shared_pool=True)      # both groups on the process-wide assembly pool
+        e.host_stream = torch.cuda.Stream(e.device)
+    S = sync[0].S
+    mk = lambda: (torch.empty((E, 32, S), dtype=torch.float32).pin_memory(), torch.empty((E, 32), dtype=torch.float32).pin_memory())
+    ref, out = [mk(), mk()], [mk(), mk()]
+    acts = [[sync[g].sample(t).cpu().pin_memory() for t in range(12)] for g in range(2)]
+    torch.cuda.synchronize()
+    for g in range(2):
+        pipe[g].step_host_begin(acts[g][0], *out[g])
+    with pytest.raises(DiralError):                     # one slot in flight per handle
+        pipe[0].step_host_begin(acts[0][1], *out[0])
+    for t in range(12):
+        for g in range(2):
+            sync[g].step_host(acts[g][t], *ref[g])
+            pipe[g].step_host_wait()
+            assert torch.equal(out[g][0], ref[g][0]) and torch.equal(out[g][1], ref[g][1]), (t, g)
+            out[g][0].fill_(-3.0)
+            if t + 1 < 12:
+                pipe[g].step_host_begin(acts[g][t + 1], *out[g])
+    pipe[0].step_host_wait()                            # nothing pending: a no-op
+    for g in range(2):
+        assert torch.equal(sync[g]._tab_seq, pipe[g]._tab_seq) and torch.equal(sync[g].episode_metrics(), pipe[g].episode_metrics())
+    big = _env(8, seed=1, **dict(kw, num_users=64, num_channels=8, highway_length=1600))
+    h = (torch.empty((8, 64, big.S)).pin_memory(), torch.empty((8, 64)).pin_memory())
+    with pytest.raises(DiralError):                     # not a lane-group configuration: use step_host
+        big.step_host_begin(big.sample(0).cpu().pin_memory(), *h)
+    for e in sync + pipe + [big]:
+        e.close()
+
+
 # ---- advisor findings ----------------------------------------------------------------------------------------------------
 
 def test_update_velocity_draws_differ_between_episodes():
