@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <immintrin.h>
 #include <memory>
@@ -271,6 +272,8 @@ int require_bound(Handle *h)
 {
     if (!h) return fail(DIRAL_ERR_ARG, "handle is NULL");
     if (!h->bound) return fail(DIRAL_ERR_UNBOUND, "diral_bind() has not been called on this handle");
+    // (every stateful entry point comes through here: nothing may touch the environment while a begun slot is in flight)
+    if (h->async_pending) return fail(DIRAL_ERR_ARG, "a begun slot is pending: call diral_step_host_wait first");
     return DIRAL_OK;
 }
 
@@ -550,6 +553,7 @@ int diral_create(const diral_cfg *cfg, void **handle)
     Handle *h = new (std::nothrow) Handle();
     if (!h) return fail(DIRAL_ERR_ARG, "out of host memory");
     h->cfg = *cfg; h->device = dev;
+    if (const char *v = getenv("DIRAL_HOST_NT")) h->host_nt = atoi(v) < 0 ? -1 : (atoi(v) != 0);     // measurement knob
     std::vector<double> edges(2 * (cfg->B + 1));
     np_linspace(-cfg->W, cfg->W, cfg->B + 1, edges.data());
     np_linspace(-1.0, 1.0, cfg->B + 1, edges.data() + cfg->B + 1);
@@ -587,6 +591,7 @@ int diral_destroy(void *handle)
 {
     Handle *h = as_handle(handle);
     if (!h) return DIRAL_OK;
+    if (h->async_pending) diral_step_host_wait(handle);        // a slot in flight still reads and writes what is freed below
     DeviceGuard g(h->device);
     cudaFree(h->d_edges);
     cudaFree(h->d_actions);
@@ -967,7 +972,6 @@ int diral_step_host(void *handle, int mode, const int32_t *h_actions, int64_t ti
     if (int rc = require_bound(h)) return rc;
     if (!h_actions || !h_state || !h_rews) return fail(DIRAL_ERR_ARG, "h_actions/h_state/h_rews must not be NULL");
     if (mode < DIRAL_MY_STEP || mode > DIRAL_MY_STEP_CH) return fail(DIRAL_ERR_ARG, "mode must be 0, 1 or 2 (got %d)", mode);
-    if (h->async_pending) return fail(DIRAL_ERR_ARG, "a begun slot is pending: call diral_step_host_wait first");
     if (int rc = ensure_actions_staging(h)) return rc;
     DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1032,7 +1036,6 @@ int diral_step_host_begin(void *handle, int mode, const int32_t *h_actions, int6
     if (int rc = require_bound(h)) return rc;
     if (!h_actions || !h_state || !h_rews) return fail(DIRAL_ERR_ARG, "h_actions/h_state/h_rews must not be NULL");
     if (mode < DIRAL_MY_STEP || mode > DIRAL_MY_STEP_CH) return fail(DIRAL_ERR_ARG, "mode must be 0, 1 or 2 (got %d)", mode);
-    if (h->async_pending) return fail(DIRAL_ERR_ARG, "a begun slot is pending: call diral_step_host_wait first");
     if (h->host_format != 3 || !compact_ok(h->cfg))
         return fail(DIRAL_ERR_UNSUPPORTED, "diral_step_host_begin needs host_format 3 and a State block with a compact host format");
     if (int rc = ensure_actions_staging(h)) return rc;
@@ -1044,7 +1047,7 @@ int diral_step_host_begin(void *handle, int mode, const int32_t *h_actions, int6
 int diral_step_host_wait(void *handle)
 {
     Handle *h = as_handle(handle);
-    if (int rc = require_bound(h)) return rc;
+    if (!h) return fail(DIRAL_ERR_ARG, "handle is NULL");
     if (!h->async_pending) return DIRAL_OK;
     DeviceGuard g(h->device);
     h->async_pending = false;

@@ -197,6 +197,8 @@ def test_step_host_begin_wait_pipelines_two_env_groups():
         pipe[g].step_host_begin(acts[g][0], *out[g])
     with pytest.raises(DiralError):                     # one slot in flight per handle
         pipe[0].step_host_begin(acts[0][1], *out[0])
+    with pytest.raises(DiralError):                     # ... and nothing else touches the environment meanwhile
+        pipe[0].step()
     for t in range(12):
         for g in range(2):
             sync[g].step_host(acts[g][t], *ref[g])
