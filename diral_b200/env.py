@@ -133,8 +133,9 @@ class TestEnv:
         self.layout = int(self.lib.diral_get_option(self._handle, b"layout"))
         self.T = int(self.lib.diral_get_option(self._handle, b"row_stride"))
         self.H = int(self.lib.diral_get_option(self._handle, b"ring_depth"))
-        self.host_stream = None          # torch.cuda.Stream for this env's launches (None: the current stream); envs
-                                         # pipelined with step_host_begin / step_host_wait want one each
+        self._dev_calls = True
+        self.host_stream = None          # torch.cuda.Stream for step_host / step_host_begin (None: the current stream);
+                                         # envs pipelined with step_host_begin / step_host_wait want one each
         self.set_host_format(host_format, host_threads)
         self._alloc()
         self._trace = None
@@ -226,9 +227,18 @@ class TestEnv:
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
-        if self.host_stream is not None:
-            return C.c_void_p(self.host_stream.cuda_stream)
+        self._dev_calls = True
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _host_stream(self):
+        # the host-buffer calls return only after their own work has been synchronised, so they may run on a private
+        # stream; everything that hands device tensors back stays on torch's current stream (and is waited for here)
+        if self.host_stream is not None:
+            if self._dev_calls:
+                self.host_stream.wait_stream(torch.cuda.current_stream(self.device))
+                self._dev_calls = False
+            return C.c_void_p(self.host_stream.cuda_stream)
+        return self._stream()
 
     def _as_actions(self, actions):
         if isinstance(actions, torch.Tensor):
@@ -396,7 +406,7 @@ class TestEnv:
         with torch.cuda.device(self.device):
             check(self.lib.diral_step_host(self._handle, MODES[mode], ptr(h_actions), C.c_int64(self.t),
                                            float(episode_number), float(epsilon), ptr(h_state), ptr(h_rews),
-                                           ptr(h_obs) if h_obs is not None else None, self._stream()))
+                                           ptr(h_obs) if h_obs is not None else None, self._host_stream()))
         self.t += 1
 
     def step_host_begin(self, h_actions, h_state, h_rews, mode=None, episode_number=0, epsilon=1):
@@ -408,7 +418,7 @@ class TestEnv:
         ptr = lambda t: t.data_ptr() if isinstance(t, torch.Tensor) else t.ctypes.data
         check(self.lib.diral_step_host_begin(self._handle, MODES[mode], ptr(h_actions), C.c_int64(self.t),
                                              float(episode_number), float(epsilon), ptr(h_state), ptr(h_rews),
-                                             self._stream()))
+                                             self._host_stream()))
         self.t += 1
 
     def step_host_wait(self):
