@@ -98,8 +98,14 @@ __device__ __forceinline__ void pair_red_inc(unsigned *addr)
 }
 
 // FULL (N == 64) drops every "does this row / column exist" predicate and turns the table strides into constants.
+// (tuning knob, measured at 64 x 32 / 8192 envs: 18 resident warps = 96 registers 443 us, 24 = 80 registers with
+//  spills 503 us, unconstrained = 128 registers 413 us -- like the lane-group kernel, fewer registers cost more than
+//  the extra warps hide)
+#ifndef DIRAL_PAIR_MIN_BLOCKS
+#define DIRAL_PAIR_MIN_BLOCKS 1
+#endif
 template <int MODE, bool FULL>
-__global__ void __launch_bounds__(32) step_pair_kernel(const Params p)
+__global__ void __launch_bounds__(32, DIRAL_PAIR_MIN_BLOCKS) step_pair_kernel(const Params p)
 {
     const int u = threadIdx.x;
     const long long e = blockIdx.x;
