@@ -201,7 +201,12 @@ step_group_kernel(const Params p)
     const long long vbase = e * N;           // first vehicle of this env in the [E][N] arrays
     const long long tbase = e * (long long)N * N;
 
-    constexpr int SL = G < 8 ? G : 8;        // columns per slab
+    // (tuning knob, measured at C3: 4 columns = 80 registers, 24 warps / SM: 45.8 us; 8 = 114 registers, 16 warps: 44.3 us;
+    //  16 = 194 registers, 10 warps: 57.5 us -- warps traded for per-warp instruction-level parallelism, same throughput)
+#ifndef DIRAL_SLAB
+#define DIRAL_SLAB 8
+#endif
+    constexpr int SL = G < DIRAL_SLAB ? G : DIRAL_SLAB;        // columns per slab
     // Fused rollout: one launch runs n_slots consecutive slots of this environment.  Every global word a slot
     // reads was written by the same lane one slot earlier (table columns, own position) or never changes, so the
     // slots of an environment need no more than the group-wide __syncwarp at the end of the loop body.
