@@ -1061,6 +1061,8 @@ int diral_step_host_wait(void *handle)
         }
     }
     h->pool->finish(h->job_id);
+    h->pool->timeline(h->job_id, h->trace_us + 2);                 // [2..4]: first / last chunk released, rows written
+    h->trace_n = 5;
     DIRAL_CUDA(cudaStreamSynchronize(h->async_stream));            // the launch itself retires (tables, accumulators)
     return DIRAL_OK;
 }

@@ -419,6 +419,8 @@ struct HostPool::Impl {
         unsigned epoch = 0;
         std::atomic<bool> aborted{false};
         std::atomic<int> done{0};            // workers that have finished the job
+        std::chrono::steady_clock::time_point t_begin{};
+        double t_us[3] = {0.0, 0.0, 0.0};    // worker 0: first chunk released, last chunk released, last row written
     };
     std::vector<std::thread> workers;
     std::mutex mu, post_mu;
@@ -461,12 +463,16 @@ struct HostPool::Impl {
                 }
                 if (gone) break;
                 std::atomic_thread_fence(std::memory_order_acquire);
+                if (idx == 0 && (c == 0 || c == s.nchunks - 1))
+                    s.t_us[c == 0 ? 0 : 1] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - s.t_begin).count();
+                if (idx == 0 && s.nchunks == 1) s.t_us[1] = s.t_us[0];
                 // this worker's share of chunk c, cut at multiples of 4 agents (16-byte aligned row ranges)
                 const long long lo = s.bounds[c], n = s.bounds[c + 1] - lo;
                 long long s0 = (n * idx / nthreads) & ~3ll, s1 = (n * (idx + 1) / nthreads) & ~3ll;
                 if (idx == nthreads - 1) s1 = n;
                 if (s1 > s0) expand_rows(s.lay, s.job, lo + s0, lo + s1);
             }
+            if (idx == 0) s.t_us[2] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - s.t_begin).count();
             s.done.fetch_add(1, std::memory_order_release);
         }
     }
@@ -508,6 +514,7 @@ unsigned long long HostPool::begin(const HostLayout &lay, const HostJob &job, co
     s.done.store(0, std::memory_order_relaxed);
     s.aborted.store(false, std::memory_order_relaxed);
     s.id.store(id, std::memory_order_relaxed);
+    s.t_begin = std::chrono::steady_clock::now();
     {
         std::lock_guard<std::mutex> lock(impl->mu);          // (a worker between its spin phase and cv.wait sees the new value)
         impl->posted.store(id, std::memory_order_release);
@@ -532,6 +539,12 @@ void HostPool::abort(unsigned long long id)
 {
     Impl::Slot &s = impl->slot(id);
     if (s.id.load(std::memory_order_relaxed) == id) s.aborted.store(true, std::memory_order_release);
+}
+
+void HostPool::timeline(unsigned long long id, double out_us[3]) const
+{
+    const Impl::Slot &s = impl->slot(id);
+    for (int i = 0; i < 3; ++i) out_us[i] = s.id.load(std::memory_order_acquire) == id ? s.t_us[i] : 0.0;
 }
 
 void HostPool::finish(unsigned long long id)

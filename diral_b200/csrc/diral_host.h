@@ -52,6 +52,9 @@ public:
     void finish(unsigned long long id);
     bool done(unsigned long long id) const;     // every worker through with that job (non-blocking)
     void abort(unsigned long long id);          // the chunks still missing will never come: workers skip them
+    // measurement aid: microseconds from begin(id) until worker 0 was released on the job's first chunk / its last chunk /
+    // had written its last row (valid once done(id) and until the ring slot is reused)
+    void timeline(unsigned long long id, double out_us[3]) const;
 private:
     struct Impl;
     Impl *impl;

@@ -260,6 +260,8 @@ int diral_expand_state_host(const diral_cfg *cfg, int64_t agents, const int32_t 
 
 /* Timeline of the last compact-format diral_step_host call, microseconds since its entry: [0] host threads woken,
  * [1] all chunks enqueued, [2 + k] chunk k's record landed in host memory, [2 + chunks] every row assembled.
+ * After diral_step_host_begin + _wait: [0] host threads woken, [1] launch enqueued, then -- as seen by assembly thread 0 --
+ * [2] its first chunk released, [3] its last chunk released, [4] its last row written.
  * Returns the number of values written (<= n).  Measurement aid: says what bounds the end-to-end slot. */
 int32_t diral_host_trace(void *handle, double *out_us, int32_t n);
 

@@ -116,9 +116,13 @@ def pipelined(groups, threads_each, chunks, reps=60, shared=False):
     t0 = time.perf_counter()
     run(reps)
     dt = (time.perf_counter() - t0) / reps
+    traces = []
     for env in envs:
+        tr = (C.c_double * 8)()
+        n = env.lib.diral_host_trace(env._handle, tr, 8)
+        traces.append([round(tr[i], 1) for i in range(n)])
         env.close()
-    return {"groups": groups, "envs_per_group": E, "threads_per_group": threads_each, "shared_pool": shared, "stream_chunks": chunks,
+    return {"last_slot_timeline_us_per_group": traces,"groups": groups, "envs_per_group": E, "threads_per_group": threads_each, "shared_pool": shared, "stream_chunks": chunks,
             "us_per_slot_of_all_groups": dt * 1e6, "agent_steps_per_s": E * groups * N_UE / dt}
 
 
