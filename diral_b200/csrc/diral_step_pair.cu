@@ -101,11 +101,14 @@ __device__ __forceinline__ void pair_red_inc(unsigned *addr)
 // (tuning knob, measured at 64 x 32 / 8192 envs: 18 resident warps = 96 registers 443 us, 24 = 80 registers with
 //  spills 503 us, unconstrained = 128 registers 413 us -- like the lane-group kernel, fewer registers cost more than
 //  the extra warps hide)
-#ifndef DIRAL_PAIR_MIN_BLOCKS
-#define DIRAL_PAIR_MIN_BLOCKS 1
+//  (an explicit minimum of 1 is not the same as none: ptxas then takes 185 registers, 10 warps / SM: 538 us)
+#ifdef DIRAL_PAIR_MIN_BLOCKS
+#define DIRAL_PAIR_BOUNDS __launch_bounds__(32, DIRAL_PAIR_MIN_BLOCKS)
+#else
+#define DIRAL_PAIR_BOUNDS __launch_bounds__(32)
 #endif
 template <int MODE, bool FULL>
-__global__ void __launch_bounds__(32, DIRAL_PAIR_MIN_BLOCKS) step_pair_kernel(const Params p)
+__global__ void DIRAL_PAIR_BOUNDS step_pair_kernel(const Params p)
 {
     const int u = threadIdx.x;
     const long long e = blockIdx.x;
