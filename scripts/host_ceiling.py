@@ -71,6 +71,7 @@ def step_host(env, fmt, threads, chunks, h_act, h_state, h_rews, nt=-1, reps=40,
     env.set_host_format(fmt, threads)
     env.lib.diral_set_option(env._handle, b"stream_chunks" if fmt == "compact_stream" else b"host_chunks", chunks)
     env.lib.diral_set_option(env._handle, b"actions_direct", direct)
+    env.lib.diral_set_option(env._handle, b"tail_split", int(os.environ.get("DIRAL_TAIL_SPLIT", "0")))
     env.lib.diral_set_option(env._handle, b"host_nt", nt)
     for k in range(4):
         env.step_host(h_act[k % 8], h_state, h_rews)
@@ -93,6 +94,7 @@ def pipelined(groups, threads_each, chunks, reps=60, shared=False):
     bufs = []
     for env in envs:
         env.set_host_format("compact_stream", threads_each, shared_pool=shared)
+        env.lib.diral_set_option(env._handle, b"tail_split", int(os.environ.get("DIRAL_TAIL_SPLIT", "0")))
         env.host_stream = torch.cuda.Stream(env.device)
         env.lib.diral_set_option(env._handle, b"stream_chunks", chunks)
         acts = [env.sample(t).cpu().pin_memory() for t in range(8)]
