@@ -281,7 +281,8 @@ int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes
  * by the kernels into mapped host memory | 3 streamed: one launch + per-chunk flags), "host_threads", "host_chunks" (env
  * chunks pipelined per call, formats 1 and 2), "stream_chunks" (flags per slot, format 3), "actions_direct" (pinned
  * actions read in place: 0 never | 1 format 3 only | 2 always), "host_nt" (row stores: -1 auto | 0 ordinary | 1
- * non-temporal).  Checkpoint restore: "ticks" (table ticks since the reset = every vehicle's own sequence number) and
+ * non-temporal), "host_pool_shared" (1: this handle's rows are assembled by the process-wide pool, sized by the first handle
+ * that uses it -- what handles pipelined with diral_step_host_begin / _wait should share).  Checkpoint restore: "ticks" (table ticks since the reset = every vehicle's own sequence number) and
  * "lat_live" (a my_step_ch has stamped last_arrival_time); diral_get_option reads any of them back (-1: unknown),
  * plus "compact_ok" (1 when this State block has a compact host format), "kernel" (1 lane-group, 2 round-1
  * one-CTA-per-env, 3 row layout), "layout", "row_stride", "ring_depth" and "scratch_bytes" (what `scratch` must hold
