@@ -57,8 +57,6 @@ void stream_out(float *dst, const float *src, long long n, bool nt)
 
 namespace {
 
-#define DIRAL_TARGET_FMA_FWD __attribute__((target("avx2,fma")))
-
 // Rows whose blocks are all whole 16-byte groups (one-hot over R % 4 == 0 resources, obs likewise, B % 4 == 0 bins,
 // no scalar tail -- the shipped State block, S = R + B) are formed in registers and leave as non-temporal stores
 // straight from them: per agent R/4 compares for the one-hot and B/4 divisions (IEEE float32 division of two small
@@ -72,11 +70,6 @@ bool vector_rows_ok(const HostLayout &lay, const HostJob &job)
     return (lay.S & 3) == 0 && (reinterpret_cast<uintptr_t>(job.out) & 15) == 0;
 }
 
-DIRAL_TARGET_FMA_FWD inline __m128 fma_quotient(__m128 c, __m128 den, __m128 rcp, __m128 q0)
-{
-    return _mm_fmadd_ps(_mm_fnmadd_ps(q0, den, c), rcp, q0);
-}
-
 template <bool NT>
 inline void put4(float *w, __m128i v)
 {
@@ -84,16 +77,8 @@ inline void put4(float *w, __m128i v)
     else _mm_store_si128(reinterpret_cast<__m128i *>(w), v);
 }
 
-// counts / len without a division per bin: one correctly rounded reciprocal per agent, then per group of four bins
-//   q0 = c * rcp;  q = fma(fma(-q0, len, c), rcp, q0)
-// which equals the correctly rounded c / len for all 0 <= c <= len < 1024 (the lemma the kernels use, checked
-// exhaustively in tests/test_host.py).  Needs fused multiply-add: compiled for AVX2+FMA, chosen at run time.
-#define DIRAL_TARGET_FMA __attribute__((target("avx2,fma")))
-
-template <bool NT, bool FMA>
-#if defined(__GNUC__)
-__attribute__((always_inline))
-#endif
+// SSE2 flavour (any x86-64): IEEE division per group of four bins
+template <bool NT>
 inline void expand_rows_vector_impl(const HostLayout &lay, const HostJob &job, long long a0, long long a1)
 {
     const int R = lay.R, B = lay.B, S = lay.S;
@@ -131,25 +116,21 @@ inline void expand_rows_vector_impl(const HostLayout &lay, const HostJob &job, l
             acc = _mm_add_epi32(acc, _mm_shuffle_epi32(acc, 0xb1));       // every lane = len(s)
             // len == 0: every count is 0 too; dividing by 1 leaves the all-zero vector (network.py:502-505)
             const __m128 den = _mm_cvtepi32_ps(_mm_max_epi16(acc, _mm_set1_epi32(1)));
-            if (FMA) {
-                const __m128 rcp = _mm_div_ps(_mm_set1_ps(1.0f), den);
-                for (int b = 0; b < B; b += 4, w += 4) {
-                    const __m128 c = _mm_cvtepi32_ps(c32[b >> 2]);
-                    const __m128 q0 = _mm_mul_ps(c, rcp);
-                    put4<NT>(w, _mm_castps_si128(fma_quotient(c, den, rcp, q0)));
-                }
-            } else {
-                for (int b = 0; b < B; b += 4, w += 4) put4<NT>(w, _mm_castps_si128(_mm_div_ps(_mm_cvtepi32_ps(c32[b >> 2]), den)));
-            }
+            for (int b = 0; b < B; b += 4, w += 4) put4<NT>(w, _mm_castps_si128(_mm_div_ps(_mm_cvtepi32_ps(c32[b >> 2]), den)));
         }
     }
     if (NT) _mm_sfence();
 }
 
 
-// AVX2 + FMA flavour of the same row assembly: eight floats per step (one 4-float step closes a block whose length is
+// AVX2 + FMA flavour of the same row assembly (chosen at run time): counts / len without a division per bin -- one
+// correctly rounded reciprocal per agent, then  q0 = c * rcp;  q = fma(fma(-q0, len, c), rcp, q0),  which equals the
+// correctly rounded c / len for all 0 <= c <= len < 1024 (the lemma the kernels use, checked exhaustively in
+// tests/test_host.py).  Eight floats per step (one 4-float step closes a block whose length is
 // 4 mod 8), the sample count from one SAD over the count bytes, bytes widened with one VPMOVZXBD.
 // a block may start 16 (not 32) bytes into a row: 32-byte non-temporal stores need 32-byte addresses
+#define DIRAL_TARGET_FMA __attribute__((target("avx2,fma")))
+
 template <bool NT>
 DIRAL_TARGET_FMA inline void store8_avx(float *d, __m256 v, bool rows32)
 {
@@ -337,8 +318,8 @@ bool cpu_has_avx512vbmi()
     return yes;
 }
 
-void rows_sse_nt(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<true, false>(l, j, a0, a1); }
-void rows_sse_st(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<false, false>(l, j, a0, a1); }
+void rows_sse_nt(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<true>(l, j, a0, a1); }
+void rows_sse_st(const HostLayout &l, const HostJob &j, long long a0, long long a1) { expand_rows_vector_impl<false>(l, j, a0, a1); }
 
 bool cpu_has_fma()
 {
