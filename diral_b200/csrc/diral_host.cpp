@@ -200,21 +200,25 @@ DIRAL_TARGET_FMA void expand_rows_avx2(const HostLayout &lay, const HostJob &job
 }
 
 // Four agents per step (AVX-512 BW/VL/VBMI).  4 S floats are a whole number of 64-byte vectors when S % 4 == 0, so a
-// group of four rows leaves as S / 4 aligned full-width stores.  What each output lane holds -- a one-hot lane of agent j
-// at resource r, or the quotient of agent j's bin b -- depends only on the layout, so it is tabulated once per layout:
-// byte-permute indices that pull the count bytes of 64 output lanes out of the group's records at once, the agent of
-// every lane (to spread the four lengths / reciprocals / actions), and the resource of every one-hot lane.
+// group of four rows leaves as S / 4 aligned full-width stores.  What each output lane holds -- a one-hot lane, or the
+// quotient of agent j's bin b -- depends only on the layout, so it is tabulated once per layout: per output vector a byte
+// permute that drops every quotient lane's count byte (out of the group's 128-byte record block) into that lane's
+// dword and zeroes the one-hot lanes, and the agent of every lane (to spread the four lengths / reciprocals).  The
+// one-hot lanes leave as zeros; one scalar store per agent then sets the lane of its action.  Rewards embedded in the
+// records come out with one more byte permute.
 struct Rows512Plan {
     int Ra = -1, B = 0, S = 0;              // one-hot width (0: no action block), bins, row length
     long long stride = 0;                   // bytes between the count records of consecutive agents
     int nvec = 0, nsum = 0;
-    alignas(64) uint8_t byte_idx[8][64];    // per 4 output vectors: source byte (in the 128-byte record block) per lane
+    alignas(64) uint8_t byte_idx[32][64];   // per output vector: source byte (in the 128-byte record block) of every lane, in
+                                            // the low byte of the lane's dword
+    unsigned long long bmask[32];           // ... and which of the 64 bytes are taken at all (the rest become 0)
     alignas(64) int32_t agent[32][16];      // per output vector: agent (0..3) of every lane
-    alignas(64) int32_t res[32][16];        // per output vector: resource of a one-hot lane, -1 elsewhere
-    uint16_t qmask[32];                     // lanes that hold a quotient
     alignas(64) int8_t weight[128];         // 1 on count bytes, 0 elsewhere (rewards, padding)
     alignas(64) int32_t sum_idx[8][16];     // t-th group of four count bytes of each agent (dword index in the block)
     unsigned long long hi_mask = 0;         // bytes of the record block beyond the first 64
+    long long rew_off = -1;                 // rewards embedded in the records at this byte offset (-1: a separate array)
+    alignas(64) uint8_t rew_idx[64];        // ... and the 16 bytes of the four agents' rewards inside the record block
 };
 
 bool rows512_layout_ok(const HostLayout &lay, const HostJob &job)
@@ -230,19 +234,22 @@ const Rows512Plan &rows512_plan(const HostLayout &lay, const HostJob &job)
     static thread_local Rows512Plan plan;
     const int Ra = lay.add_action ? lay.R : 0, B = lay.piggy ? lay.B : 0;
     const long long stride = lay.piggy ? job.count_stride : 0;
-    if (plan.Ra == Ra && plan.B == B && plan.S == lay.S && plan.stride == stride) return plan;
-    plan.Ra = Ra; plan.B = B; plan.S = lay.S; plan.stride = stride;
+    const long long roff = reinterpret_cast<const uint8_t *>(job.rews) - job.counts;
+    const long long rew_off = (lay.piggy && job.rews_out && job.rew_stride == stride && roff >= 0 && roff + 4 <= stride) ? roff : -1;
+    if (plan.Ra == Ra && plan.B == B && plan.S == lay.S && plan.stride == stride && plan.rew_off == rew_off) return plan;
+    plan.Ra = Ra; plan.B = B; plan.S = lay.S; plan.stride = stride; plan.rew_off = rew_off;
+    memset(plan.rew_idx, 0, sizeof plan.rew_idx);
+    if (rew_off >= 0) for (int i = 0; i < 16; ++i) plan.rew_idx[i] = (uint8_t)((i >> 2) * stride + rew_off + (i & 3));
     plan.nvec = lay.S / 4;
     memset(plan.byte_idx, 0, sizeof plan.byte_idx);
     for (int v = 0; v < plan.nvec; ++v) {
-        plan.qmask[v] = 0;
+        plan.bmask[v] = 0ull;
         for (int l = 0; l < 16; ++l) {
             const int f = 16 * v + l, j = f / lay.S, sI = f % lay.S;
             plan.agent[v][l] = j;
-            plan.res[v][l] = sI < Ra ? sI : -1;
             if (sI >= Ra) {
-                plan.qmask[v] |= (uint16_t)(1u << l);
-                plan.byte_idx[v >> 2][(v & 3) * 16 + l] = (uint8_t)(j * stride + (sI - Ra));
+                plan.byte_idx[v][4 * l] = (uint8_t)(j * stride + (sI - Ra));
+                plan.bmask[v] |= 1ull << (4 * l);
             }
         }
     }
@@ -263,16 +270,20 @@ DIRAL_TARGET_512V void expand_rows_avx512x4(const Rows512Plan &pl, const HostJob
     const __m512 ones = _mm512_set1_ps(1.0f);
     const __m512i w_lo = _mm512_load_si512(pl.weight), w_hi = _mm512_load_si512(pl.weight + 64), ones16 = _mm512_set1_epi16(1);
     const __m128i rmax = _mm_set1_epi32(pl.Ra - 1), zero4 = _mm_setzero_si128();
+    const __m512i rew_idx = _mm512_load_si512(pl.rew_idx);
     const bool have_lo = pl.stride > 0, have_hi = pl.hi_mask != 0;
     for (long long a = a0; a < a1; a += 4) {
         float *w = job.out + a * pl.S;
-        if (job.rews_out) for (int j = 0; j < 4; ++j) job.rews_out[a + j] = rew_at(job, a + j);
+        if (job.rews_out && pl.rew_off < 0) for (int j = 0; j < 4; ++j) job.rews_out[a + j] = rew_at(job, a + j);
         __m512i blk_lo = _mm512_setzero_si512(), blk_hi = _mm512_setzero_si512();
         __m512 den16 = ones, rcp16 = ones;
         if (have_lo) {
             const uint8_t *c = job.counts + a * pl.stride;
             blk_lo = have_hi ? _mm512_loadu_si512(c) : _mm512_maskz_loadu_epi8(4 * pl.stride >= 64 ? ~0ull : ((1ull << (4 * pl.stride)) - 1ull), c);
             if (have_hi) blk_hi = _mm512_maskz_loadu_epi8(pl.hi_mask, c + 64);
+            if (pl.rew_off >= 0)           // the four rewards sit in the same block: one byte permute, one 16-byte store
+                _mm_storeu_si128(reinterpret_cast<__m128i *>(job.rews_out + a),
+                                 _mm512_castsi512_si128(_mm512_permutex2var_epi8(blk_lo, rew_idx, blk_hi)));
             // len(s) of the four agents: bytes -> sums of 4 (weights drop rewards / padding) -> one dword per agent
             const __m512i d_lo = _mm512_madd_epi16(_mm512_maddubs_epi16(blk_lo, w_lo), ones16);
             const __m512i d_hi = _mm512_madd_epi16(_mm512_maddubs_epi16(blk_hi, w_hi), ones16);
@@ -284,29 +295,25 @@ DIRAL_TARGET_512V void expand_rows_avx512x4(const Rows512Plan &pl, const HostJob
             den16 = _mm512_broadcast_f32x4(den4);
             rcp16 = _mm512_broadcast_f32x4(_mm_div_ps(_mm_set1_ps(1.0f), den4));
         }
-        __m512i act16 = _mm512_setzero_si512();
+        alignas(16) int32_t act_a[4] = {0, 0, 0, 0};
         if (pl.Ra > 0)
-            act16 = _mm512_broadcast_i32x4(_mm_min_epi32(_mm_max_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(job.actions + a)), zero4), rmax));
-        for (int v4 = 0; v4 < pl.nvec; v4 += 4) {
-            const __m512i bytes = have_lo ? _mm512_permutex2var_epi8(blk_lo, _mm512_load_si512(pl.byte_idx[v4 >> 2]), blk_hi) : _mm512_setzero_si512();
-#define DIRAL_ROW_VEC(i)                                                                                                   \
-            if (v4 + i < pl.nvec) {                                                                                        \
-                const int v = v4 + i;                                                                                      \
-                const __m512i ag = _mm512_load_si512(pl.agent[v]);                                                         \
-                __m512 q = _mm512_setzero_ps();                                                                            \
-                if (pl.qmask[v]) {                                                                                         \
-                    const __m512 cf = _mm512_cvtepi32_ps(_mm512_maskz_cvtepu8_epi32(pl.qmask[v], _mm512_extracti32x4_epi32(bytes, i))); \
-                    const __m512 den = _mm512_permutexvar_ps(ag, den16), rcp = _mm512_permutexvar_ps(ag, rcp16);           \
-                    const __m512 q0 = _mm512_mul_ps(cf, rcp);                                                              \
-                    q = _mm512_fmadd_ps(_mm512_fnmadd_ps(q0, den, cf), rcp, q0);                                           \
-                }                                                                                                          \
-                if (pl.qmask[v] != 0xffffu)                                                                                \
-                    q = _mm512_mask_mov_ps(q, _mm512_cmpeq_epi32_mask(_mm512_permutexvar_epi32(ag, act16), _mm512_load_si512(pl.res[v])), ones); \
-                _mm512_store_ps(w + 16 * v, q);                                                                            \
+            _mm_store_si128(reinterpret_cast<__m128i *>(act_a),
+                            _mm_min_epi32(_mm_max_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(job.actions + a)), zero4), rmax));
+        for (int v = 0; v < pl.nvec; ++v) {
+            __m512 q = _mm512_setzero_ps();
+            if (pl.bmask[v]) {
+                // one byte permute drops every lane's count into the low byte of its dword (zero elsewhere)
+                const __m512 cf = _mm512_cvtepi32_ps(_mm512_maskz_permutex2var_epi8(pl.bmask[v], blk_lo, _mm512_load_si512(pl.byte_idx[v]), blk_hi));
+                const __m512i ag = _mm512_load_si512(pl.agent[v]);
+                const __m512 den = _mm512_permutexvar_ps(ag, den16), rcp = _mm512_permutexvar_ps(ag, rcp16);
+                const __m512 q0 = _mm512_mul_ps(cf, rcp);
+                q = _mm512_fmadd_ps(_mm512_fnmadd_ps(q0, den, cf), rcp, q0);
             }
-            DIRAL_ROW_VEC(0) DIRAL_ROW_VEC(1) DIRAL_ROW_VEC(2) DIRAL_ROW_VEC(3)
-#undef DIRAL_ROW_VEC
+            _mm512_store_ps(w + 16 * v, q);
         }
+        // the one-hot lanes were written as zeros: one scalar store per agent sets its action's lane
+        if (pl.Ra > 0)
+            for (int j = 0; j < 4; ++j) w[j * pl.S + act_a[j]] = 1.0f;
     }
 }
 
