@@ -31,12 +31,46 @@ __device__ __forceinline__ void insertion_sort(const StridedBuf &a, int n)
     }
 }
 
+// Up to 32 values per thread sort in REGISTERS: a bitonic network with compile-time indices (240 compare-exchanges, no
+// shared-memory traffic, no data-dependent branch); unused slots hold +inf and end up behind the values.  Equal values
+// are bit-identical here (a zero signed distance is always -0.0), so the network's instability cannot show.
+__device__ __forceinline__ void bitonic32(double (&v)[32])
+{
+#pragma unroll
+    for (int ks = 1; ks <= 5; ++ks)
+#pragma unroll
+        for (int js = ks - 1; js >= 0; --js)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int k = 1 << ks, j = 1 << js, l = i ^ j;
+                if (l > i) {
+                    const double a = v[i], b = v[l];
+                    const bool sw = ((i & k) == 0) ? (a > b) : (a < b);
+                    v[i] = sw ? b : a; v[l] = sw ? a : b;
+                }
+            }
+}
+
+// the first n (<= 32) values of a thread's scratch array, sorted in place through registers (one copy of the network
+// for every caller: the unrolled code is ~1 200 instructions)
+__device__ __noinline__ void sort32(const StridedBuf buf, int n)
+{
+    double v[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) v[t] = t < n ? buf[t] : INFINITY;
+    bitonic32(v);
+#pragma unroll
+    for (int t = 0; t < 32; ++t) if (t < n) buf[t] = v[t];
+}
+
 // TestEnv.obtain_state (reference envs/test_env.py:527-583) on caller-supplied obs / actions /
 // rewards, one thread per (env, vehicle).  Every State flag is honoured, including the two variants
 // the fused kernels leave to this one: the direct sorted positional distribution
 // (Network.get_positional_dist, network.py:409-430) and VPD type 1
 // (Network.get_positional_dist_piggy, network.py:432-471).
-template <bool SORTED>
+// KIND: 0 no sorted block, 1 the direct distribution only, 2 VPD type 1 only (one inlined copy of the sorting network
+// each, values never leave registers before they are sorted), 3 both (they share the out-of-line sort32).
+template <int KIND>
 __global__ void __launch_bounds__(128) obtain_state_kernel(const Params p, const float *__restrict__ obs,
                                                            const int32_t *__restrict__ actions,
                                                            const float *__restrict__ rews, float *__restrict__ out,
@@ -58,18 +92,49 @@ __global__ void __launch_bounds__(128) obtain_state_kernel(const Params p, const
     }
     if (p.add_channel_obs) { for (int r = 0; r < R; ++r) row[k++] = obs[gid * R + r]; }
 
+    constexpr bool SORTED = KIND != 0;
     extern __shared__ double sort_scratch[];
     const StridedBuf buf{sort_scratch + threadIdx.x, (int)blockDim.x};      // (only touched by the SORTED instantiation)
-    if (SORTED && p.add_positional_dist) {          // network.py:409-430
+    if ((KIND & 1) && p.add_positional_dist) {      // network.py:409-430
         int m = 0; double max_dist = 0.0;
-        for (int t = 0; t < N; ++t) {
-            if (t == u) continue;
-            const double xt = p.pos_x[vbase + t], yt = p.pos_y[vbase + t];
-            const double d = dist2d(xt, yt, xu, yu);
-            if (d > max_dist) max_dist = d;
-            buf[m++] = (__dsub_rn(xt, xu) > 0.0) ? d : -d;
+        if (N <= 32) {
+          if constexpr (KIND == 1) {
+            double v[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                double sv = INFINITY;
+                if (t < N && t != u) {
+                    const double xt = p.pos_x[vbase + t], yt = p.pos_y[vbase + t];
+                    const double d = dist2d(xt, yt, xu, yu);
+                    if (d > max_dist) max_dist = d;
+                    sv = (__dsub_rn(xt, xu) > 0.0) ? d : -d;
+                }
+                v[t] = sv;
+            }
+            bitonic32(v);
+#pragma unroll
+            for (int t = 0; t < 32; ++t) if (t < N) buf[t] = v[t];
+            m = N - 1;
+          } else {
+            for (int t = 0; t < N; ++t) {
+                if (t == u) continue;
+                const double xt = p.pos_x[vbase + t], yt = p.pos_y[vbase + t];
+                const double d = dist2d(xt, yt, xu, yu);
+                if (d > max_dist) max_dist = d;
+                buf[m++] = (__dsub_rn(xt, xu) > 0.0) ? d : -d;
+            }
+            sort32(buf, m);
+          }
+        } else {
+            for (int t = 0; t < N; ++t) {
+                if (t == u) continue;
+                const double xt = p.pos_x[vbase + t], yt = p.pos_y[vbase + t];
+                const double d = dist2d(xt, yt, xu, yu);
+                if (d > max_dist) max_dist = d;
+                buf[m++] = (__dsub_rn(xt, xu) > 0.0) ? d : -d;
+            }
+            insertion_sort(buf, m);
         }
-        insertion_sort(buf, m);
         for (int q = 0; q < m; ++q) row[k++] = (float)__ddiv_rn(buf[q], max_dist);
     }
     if (p.piggy) {
@@ -96,18 +161,78 @@ __global__ void __launch_bounds__(128) obtain_state_kernel(const Params p, const
             }
             const float den = (float)m;
             for (int b = 0; b < B; ++b) row[k++] = m > 0 ? __fdiv_rn((float)hist[b], den) : 0.0f;
-        } else if (SORTED) {                                  // network.py:432-471 (type 1)
+        } else if (KIND & 2) {                                // network.py:432-471 (type 1)
             int m = 0;
-            for (int j = 0; j < N; ++j) {
-                if (j == u || lu_at(j) >= p.age_threshold) continue;
-                const double x1 = x_at(j);
-                const double y1 = seq_at(j) > 0 ? p.pos_y[vbase + j] : 0.0;
-                const double d = dist2d(x1, y1, xu, yu);
-                buf[m++] = (__dsub_rn(x1, xu) > 0.0) ? d : -d;
+            if (N <= 32 && !p.layout) {
+              if constexpr (KIND == 2) {
+                // subject-major tables: entry (u, j) of all three arrays sits at base + j * N; the loads of eight
+                // entries are issued before the first dependent use, the values sort in registers
+                const long long base = e * (long long)N * N + u;
+                double v[32];
+#pragma unroll
+                for (int j0 = 0; j0 < 32; j0 += 8) {
+                    int sq[8], lu8[8]; double x8[8], y8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int j = j0 + q;
+                        const bool have = j < N && j != u;
+                        const long long idx = base + (long long)j * N;
+                        sq[q] = have ? p.tab_seq[idx] : 0;
+                        lu8[q] = have ? p.tab_lu[idx] : p.age_threshold;
+                        x8[q] = have ? p.tab_x[idx] : 0.0;
+                        y8[q] = have ? p.pos_y[vbase + j] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        double sv = INFINITY;
+                        if (lu8[q] < p.age_threshold) {
+                            const double d = dist2d(x8[q], sq[q] > 0 ? y8[q] : 0.0, xu, yu);
+                            sv = (__dsub_rn(x8[q], xu) > 0.0) ? d : -d;
+                            ++m;
+                        }
+                        v[j0 + q] = sv;
+                    }
+                }
+                if (m > 0) {
+                    bitonic32(v);
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) if (t < N) buf[t] = v[t];
+                }
+              } else {
+                const long long base = e * (long long)N * N + u;
+                for (int j0 = 0; j0 < N; j0 += 8) {
+                    int sq[8], lu8[8]; double x8[8], y8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int j = j0 + q;
+                        const bool have = j < N && j != u;
+                        const long long idx = base + (long long)j * N;
+                        sq[q] = have ? p.tab_seq[idx] : 0;
+                        lu8[q] = have ? p.tab_lu[idx] : p.age_threshold;
+                        x8[q] = have ? p.tab_x[idx] : 0.0;
+                        y8[q] = have ? p.pos_y[vbase + j] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (lu8[q] >= p.age_threshold) continue;
+                        const double d = dist2d(x8[q], sq[q] > 0 ? y8[q] : 0.0, xu, yu);
+                        buf[m++] = (__dsub_rn(x8[q], xu) > 0.0) ? d : -d;
+                    }
+                }
+                if (m > 0) sort32(buf, m);
+              }
+            } else {
+                for (int j = 0; j < N; ++j) {
+                    if (j == u || lu_at(j) >= p.age_threshold) continue;
+                    const double x1 = x_at(j);
+                    const double y1 = seq_at(j) > 0 ? p.pos_y[vbase + j] : 0.0;
+                    const double d = dist2d(x1, y1, xu, yu);
+                    buf[m++] = (__dsub_rn(x1, xu) > 0.0) ? d : -d;
+                }
+                if (m > 0) insertion_sort(buf, m);
             }
             if (m == 0) { for (int b = 0; b < B; ++b) row[k++] = 0.0f; }
             else {
-                insertion_sort(buf, m);
                 double nrm = 0.0;
                 for (int q = 0; q < m; ++q) nrm = fmax(nrm, fabs(buf[q]));
                 for (int q = 0; q < m; ++q) buf[q] = __ddiv_rn(buf[q], nrm);
@@ -264,19 +389,25 @@ cudaError_t launch_obtain_state(const Params &p, const float *obs, const int32_t
     // edges1 (linspace(-1, 1, B+1)) lives right behind edges in the same device allocation
     const double *edges1 = p.edges + (p.B + 1);
     if (!sorted) {
-        obtain_state_kernel<false><<<blocks_for(p.E * p.N, 128), 128, 0, stream>>>(p, obs, actions, rews, out, edges1);
+        obtain_state_kernel<0><<<blocks_for(p.E * p.N, 128), 128, 0, stream>>>(p, obs, actions, rews, out, edges1);
         return cudaGetLastError();
     }
     // N doubles of shared-memory scratch per thread: as many threads per CTA as 200 KB allow, at most 128
     int threads = 128;
     while (threads > 32 && (size_t)threads * p.N * sizeof(double) > (size_t)200 * 1024) threads -= 32;
     const size_t smem = (size_t)threads * p.N * sizeof(double);
-    if (smem > 48 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(obtain_state_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-    }
-    obtain_state_kernel<true><<<blocks_for(p.E * p.N, threads), threads, smem, stream>>>(p, obs, actions, rews, out, edges1);
-    return cudaGetLastError();
+    const int kind = (p.add_positional_dist ? 1 : 0) | ((p.piggy && p.pos_dist_type == 1) ? 2 : 0);
+    auto launch = [&](auto kernel) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+        }
+        kernel<<<blocks_for(p.E * p.N, threads), threads, smem, stream>>>(p, obs, actions, rews, out, edges1);
+        return cudaGetLastError();
+    };
+    if (kind == 1) return launch(obtain_state_kernel<1>);
+    if (kind == 2) return launch(obtain_state_kernel<2>);
+    return launch(obtain_state_kernel<3>);
 }
 
 cudaError_t launch_reset(const Params &p, const double *x0, const double *y0, const double *v0, cudaStream_t stream)
