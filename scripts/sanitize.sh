@@ -5,7 +5,7 @@
 # pair kernel (33..64 vehicles), round-1 block kernel (shared-memory and scratch keys), row kernel (flag-ordered merges,
 # wide keys), compact host format (chunked, zero-copy, streamed records with TMA bulk stores and device-raised flags,
 # diral_step_host_begin / _wait).
-SEL='kat3_design6_ch_d3 or n48x10_my_step or c3_32x20_step_design-group-fused or toy4x3_shipped_T80-group-fused or n70x16_ch_d3 or n130x40_my_step-row-fused or n160x70 or n200x90_ch-block_v1 or c5_100x50-row'
+SEL='kat3_design6_ch_d3 or n48x10_my_step or c3_32x20_step_design-group-fused or toy4x3_shipped_T80-group-fused or n70x16_ch_d3 or n130x40_my_step-row-fused or n160x70 or n200x90_ch-block_v1 or c5_100x50-row or state_vpd1 or state_no_piggy_direct or state_real_action_vpd1'
 SEL2='fused_rollout_equals_slot_by_slot and 16-8 or split_environment_kernel_reproduces_fixtures and c3_32x20_ch_d3 or compact_host_format_is_bit_identical and 13-7 or compact_host_format_is_bit_identical and 32-20-2048 or begin_wait'
 for tool in memcheck racecheck synccheck; do
   echo "== $tool"
