@@ -1063,7 +1063,12 @@ int diral_step_host_wait(void *handle)
     h->pool->finish(h->job_id);
     h->pool->timeline(h->job_id, h->trace_us + 2);                 // [2..4]: first / last chunk released, rows written
     h->trace_n = 5;
-    DIRAL_CUDA(cudaStreamSynchronize(h->async_stream));            // the launch itself retires (tables, accumulators)
+    // the launch itself retires (tables, accumulators): it usually has by now -- the last rows were assembled after its
+    // last flag -- so ask before blocking
+    if (cudaStreamQuery(h->async_stream) != cudaSuccess) {
+        cudaGetLastError();
+        DIRAL_CUDA(cudaStreamSynchronize(h->async_stream));
+    }
     return DIRAL_OK;
 }
 

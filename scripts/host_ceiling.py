@@ -104,17 +104,25 @@ def pipelined(groups, threads_each, chunks, reps=60, shared=False):
                      torch.empty((E, N_UE), dtype=torch.float32).pin_memory()))
     torch.cuda.synchronize()
 
+    spent = {"begin": 0.0, "wait": 0.0}
+
     def run(n):
+        pc = time.perf_counter
         for g, env in enumerate(envs):
             env.step_host_begin(bufs[g][0][0], bufs[g][1], bufs[g][2])
         for k in range(1, n):
             for g, env in enumerate(envs):
+                t0 = pc()
                 env.step_host_wait()
+                t1 = pc()
                 env.step_host_begin(bufs[g][0][k % 8], bufs[g][1], bufs[g][2])
+                spent["wait"] += t1 - t0
+                spent["begin"] += pc() - t1
         for env in envs:
             env.step_host_wait()
 
     run(6)
+    spent["begin"] = spent["wait"] = 0.0
     t0 = time.perf_counter()
     run(reps)
     dt = (time.perf_counter() - t0) / reps
@@ -124,7 +132,8 @@ def pipelined(groups, threads_each, chunks, reps=60, shared=False):
         n = env.lib.diral_host_trace(env._handle, tr, 8)
         traces.append([round(tr[i], 1) for i in range(n)])
         env.close()
-    return {"last_slot_timeline_us_per_group": traces,"groups": groups, "envs_per_group": E, "threads_per_group": threads_each, "shared_pool": shared, "stream_chunks": chunks,
+    return {"last_slot_timeline_us_per_group": traces,
+            "calling_thread_us_per_slot": {k: round(v / reps * 1e6, 1) for k, v in spent.items()},"groups": groups, "envs_per_group": E, "threads_per_group": threads_each, "shared_pool": shared, "stream_chunks": chunks,
             "us_per_slot_of_all_groups": dt * 1e6, "agent_steps_per_s": E * groups * N_UE / dt}
 
 
