@@ -1051,12 +1051,16 @@ int diral_step_host_wait(void *handle)
     if (!h->async_pending) return DIRAL_OK;
     DeviceGuard g(h->device);
     h->async_pending = false;
+    unsigned retired_polls = 0;                                    // polls since the launch was first seen retired
     for (unsigned spins = 1; !h->pool->done(h->job_id); ++spins) {
         _mm_pause();
         if ((spins & 0xfff) == 0) {                                // every few tens of microseconds: is the launch still alive?
             const cudaError_t q = cudaStreamQuery(h->async_stream);
-            if (q == cudaSuccess || q == cudaErrorNotReady) { cudaGetLastError(); continue; }
+            if (q == cudaErrorNotReady) { cudaGetLastError(); continue; }
+            // retired: every flag is up, the rows follow within microseconds -- unless something is badly wrong
+            if (q == cudaSuccess && ++retired_polls < 100000u) continue;
             h->pool->abort(h->job_id); h->pool->finish(h->job_id);
+            if (q == cudaSuccess) return fail(DIRAL_ERR_CUDA, "slot kernel retired, but the row assembly did not complete");
             return fail(DIRAL_ERR_CUDA, "slot kernel failed: %s", cudaGetErrorString(q));
         }
     }
