@@ -15,14 +15,18 @@ from diral_b200 import TestEnv  # noqa: E402
 from oracle.c_oracle import COracle  # noqa: E402
 
 slots = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
-CASES = [("C3 32x20", 24, dict(num_users=32, num_channels=20, highway_length=800)),
-         ("sparse 32x8, L=4000", 24, dict(num_users=32, num_channels=8, highway_length=4000)),
-         ("64x32 (pair kernel)", 6, dict(num_users=64, num_channels=32, highway_length=1600)),
-         ("128x64 (row kernel)", 3, dict(num_users=128, num_channels=64, highway_length=3200))]
+CASES = [("C3 32x20", 24, dict(num_users=32, num_channels=20, highway_length=800), "my_step"),
+         ("sparse 32x8, L=4000", 24, dict(num_users=32, num_channels=8, highway_length=4000), "my_step"),
+         ("C3 32x20 PRR (design 3)", 24, dict(num_users=32, num_channels=20, highway_length=800, reward_design=3, enable_channel=True), "my_step_ch"),
+         ("24x10 design mode", 24, dict(num_users=24, num_channels=10, highway_length=600), "my_step_design"),
+         ("64x32 (pair kernel)", 6, dict(num_users=64, num_channels=32, highway_length=1600), "my_step"),
+         ("48x12 PRR (pair kernel)", 6, dict(num_users=48, num_channels=12, highway_length=1200, reward_design=4, enable_channel=True), "my_step_ch"),
+         ("128x64 (row kernel)", 3, dict(num_users=128, num_channels=64, highway_length=3200), "my_step"),
+         ("80x24 (round-1 block kernel)", 3, dict(num_users=80, num_channels=24, highway_length=2000), "my_step")]
 np32 = lambda t: t.detach().cpu().numpy()
 bad = 0
-for name, E, kw in CASES:
-    kw = dict(kw, reward_design=2, communication_range=250, mobility=True, bin_range=500, State=STATE)
+for name, E, kw, mode in CASES:
+    kw = dict(dict(reward_design=2, communication_range=250, mobility=True, bin_range=500, State=STATE), **kw)
     n = slots if kw["num_users"] <= 32 else max(slots // 4, 600)
     orc = COracle(num_envs=E, threads=8, **kw)
     orc.reset_philox(99)
@@ -30,10 +34,11 @@ for name, E, kw in CASES:
     t0 = time.time()
     for t in range(n):
         a = orc.philox_actions(99, t)
-        o_ref, r_ref = orc.step("my_step", a, t)
+        o_ref, r_ref = orc.step(mode, a, t)
         s_ref = orc.obtain_state(o_ref, a, r_ref)
-        s, r, info = env.step()
-        ok = (np32(r) == r_ref.astype(np.float32)).all() and (np32(s) == s_ref.astype(np.float32)).all() \
+        env._step(mode, None, t, True)
+        s, r, info = env._state, env._rews, {"obs": env._obs}
+        ok = (np32(env._actions) == a).all() and (np32(r) == r_ref.astype(np.float32)).all() and (np32(s) == s_ref.astype(np.float32)).all() \
             and (np32(info["obs"]) == o_ref.astype(np.float32)).all()
         if t % 100 == 99 or t == n - 1:
             ok = ok and (np32(env.tab_seq) == orc.tab_seq).all() and (np32(env.tab_lu) == orc.tab_lu).all() \
