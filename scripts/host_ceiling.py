@@ -149,8 +149,8 @@ def main():
         res = []
         total = int(os.environ.get("DIRAL_POOL_THREADS", cpus - 2))      # (the shared pool keeps the size of its first user)
         for rep in range(3):
-            for groups in (1, 2, 3, 4):
-                for chunks in (4, 8):
+            for groups in [int(c) for c in os.environ.get("DIRAL_PIPE_GROUPS", "1,2,3,4").split(",")]:
+                for chunks in [int(c) for c in os.environ.get("DIRAL_PIPE_CHUNKS", "4,8").split(",")]:
                     res.append(pipelined(groups, total, chunks, reps=100, shared=True))
                     print(json.dumps(res[-1]), flush=True)
         return
