@@ -376,7 +376,7 @@ def run_gpu(args):
     h_act = [a.cpu().pin_memory() for a in actions[:8]]
     h_state = torch.empty((E_PER_GPU, N_UE, S), dtype=torch.float32).pin_memory()
     h_rews = torch.empty((E_PER_GPU, N_UE), dtype=torch.float32).pin_memory()
-    e2e_steps = max(10, min(steps, 200))
+    e2e_steps = max(100, min(steps, 200))      # (host-side timing: long enough to average over scheduling noise)
 
     def e2e_leg(fmt):
         env.set_host_format(fmt)
