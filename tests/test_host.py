@@ -267,6 +267,22 @@ def test_host_row_assembly_matches_obtain_state_layout(state, extra, threads):
     assert ref.shape == out.shape and (out == ref).all()
 
 
+def test_host_pool_queue_flags_and_abort():
+    """The row-assembly pool behind diral_step_host / diral_step_host_begin (diral_host.cpp) as a plain C++ program:
+    five jobs queued at once and released by 'device' flags in a scrambled order, a publish()-released job, an
+    aborted job whose flags never come, more jobs than ring slots -- rows and rewards equal single-threaded
+    expand_rows throughout (tests/cpp/host_pool_test.cpp)."""
+    import subprocess
+    import tempfile
+    csrc = os.path.join(ROOT, "diral_b200", "csrc")
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "host_pool_test")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", csrc, os.path.join(ROOT, "tests", "cpp", "host_pool_test.cpp"),
+                               os.path.join(csrc, "diral_host.cpp"), "-lpthread", "-o", exe])
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "host pool ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_host_row_assembly_rejects_unfused_state_blocks():
     from diral_b200 import _lib, cfg_from_kwargs
     lib = _lib.load()
