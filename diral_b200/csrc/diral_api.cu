@@ -70,6 +70,9 @@ struct Handle {
                                     // 2 = the same, records written by the kernel straight into mapped host memory,
                                     // 3 = streamed: one launch, records into mapped host memory, per-chunk completion
                                     //     flags raised by the kernel (lane-group kernel; other kernels run as format 1)
+    int stream_split = 1;           // format 3: launch the split-environment instantiation (Params::tail_split = 2): half as
+                                    // many environments in flight, each twice as fast, so records -- and the PCIe writes
+                                    // and the row assembly behind them -- start 25 us earlier and arrive spread out
     int stream_chunks = 16;         // format 3: chunks the assembly threads are released by
     int actions_direct = 1;         // the kernel reads the caller's actions in place when they are pinned: 0 never, 1 format 3
                                     // only (measured: -12 us there, +15 us for the chunked formats), 2 always
@@ -433,6 +436,7 @@ int step_host_compact(Handle *h, int mode, const int32_t *h_actions, int64_t tim
         // to the assembly workers.
         if (!direct) DIRAL_CUDA(cudaMemcpyAsync(h->d_actions, h_actions, (size_t)A * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         p.chunk_count = h->d_chunk_count; p.chunk_flag = h->d_chunk_flag; p.chunk_envs = (int)chunk_envs; p.chunk_epoch = epoch;
+        if (h->stream_split) p.tail_split = 2;
         DIRAL_CUDA(launch_slot(h, p, s));
         h->launches += 1;
         if (c.add_piggy) h->ticks += 1;
@@ -671,6 +675,7 @@ int diral_set_option(void *handle, const char *name, int64_t value)
         h->stream_chunks = (int)value;
         return DIRAL_OK;
     }
+    if (!strcmp(name, "stream_split")) { h->stream_split = value != 0; return DIRAL_OK; }
     if (!strcmp(name, "actions_direct")) {
         if (value < 0 || value > 2) return fail(DIRAL_ERR_ARG, "actions_direct must be 0 (never), 1 (streamed format only) or 2 (always)");
         h->actions_direct = (int)value;
@@ -701,6 +706,7 @@ int64_t diral_get_option(void *handle, const char *name)
     if (!strcmp(name, "host_threads")) return h->pool ? h->pool->threads() : h->host_threads;
     if (!strcmp(name, "host_chunks")) return h->host_chunks;
     if (!strcmp(name, "stream_chunks")) return h->stream_chunks;
+    if (!strcmp(name, "stream_split")) return h->stream_split;
     if (!strcmp(name, "host_pool_shared")) return h->want_shared_pool;
     if (!strcmp(name, "actions_direct")) return h->actions_direct;
     if (!strcmp(name, "host_nt")) return h->host_nt;

@@ -701,11 +701,14 @@ size_t smem_bytes(const Params &p, int warps)
 // small groups pack 4 warps so that a CTA still carries a useful number of environments
 template <int G> struct WarpsFor { static constexpr int v = G >= 16 ? DIRAL_GROUP_WARPS : 4; };
 
+// (2 warps per split environment: measured for the streamed host records, where spreading the completions over the
+//  launch matters more than the launch time -- blocking diral_step_host 137-141 -> 114-118 us per C3 slot, 4 warps
+//  126-133 us; see profiles/README.md)
 #ifndef DIRAL_SPLIT_WARPS
-#define DIRAL_SPLIT_WARPS 4
+#define DIRAL_SPLIT_WARPS 2
 #endif
 constexpr size_t SPLIT_SMEM_LIMIT = 227 * 1024;
-constexpr int SPLIT_WARPS = DIRAL_SPLIT_WARPS;      // warps that share one environment of a batch's tail (one 8-column slab each at 32 vehicles)
+constexpr int SPLIT_WARPS = DIRAL_SPLIT_WARPS;      // warps that share one split environment (they interleave the 8-column slabs)
 
 // the same parameter block restricted to envs [e0, e0 + n) (every per-env array the lane-group kernel touches)
 Params env_slice(const Params &p, long long e0, long long n)

@@ -279,7 +279,8 @@ int diral_ring_put(void *ring, int64_t capacity, int64_t slot, int64_t row_bytes
  * "track_lat" = 1 keeps last_arrival_time bookkeeping on even before the first my_step_ch call.
  * diral_step_host: "host_format" (0 full rows | 1 compact, records through the copy engine | 2 compact, records written
  * by the kernels into mapped host memory | 3 streamed: one launch + per-chunk flags), "host_threads", "host_chunks" (env
- * chunks pipelined per call, formats 1 and 2), "stream_chunks" (flags per slot, format 3), "actions_direct" (pinned
+ * chunks pipelined per call, formats 1 and 2), "stream_chunks" (flags per slot, format 3), "stream_split" (format 3: 1 = launch
+ * the split-environment instantiation, two warps per environment, so that records start arriving earlier; default 1), "actions_direct" (pinned
  * actions read in place: 0 never | 1 format 3 only | 2 always), "host_nt" (row stores: -1 auto | 0 ordinary | 1
  * non-temporal), "host_pool_shared" (1: this handle's rows are assembled by the process-wide pool, sized by the first handle
  * that uses it -- what handles pipelined with diral_step_host_begin / _wait should share).  Checkpoint restore: "ticks" (table ticks since the reset = every vehicle's own sequence number) and

@@ -160,6 +160,7 @@ def test_compact_host_format_is_bit_identical(n, r, E, state, extra):
         comp.lib.diral_set_option(comp._handle, b"host_format", fmt)
         comp.lib.diral_set_option(comp._handle, b"actions_direct", [0, 2, 1][t % 3])   # pinned actions read in place or staged
         comp.lib.diral_set_option(comp._handle, b"stream_chunks", [32, 5, 64][t % 3])
+        comp.lib.diral_set_option(comp._handle, b"stream_split", int(t != 2))        # split-environment launch or the plain one
         with_obs = t == 7 or (t % 2 == 1 and fmt != 3)   # (an obs request sends format 3 down the chunked path)
         src = a.cpu().numpy().copy() if t == 5 else ha   # pageable actions: always staged
         bufs[1][0].fill_(-7.0)
