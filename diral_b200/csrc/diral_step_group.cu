@@ -322,11 +322,12 @@ step_group_kernel(const Params p)
     // transmitters, visited in ascending id with strict '<' (first wins ties): the two lowest are
     // compared branch-free, a third and later ones are rare.  Pure (no stores), so two resources can be
     // in flight at once.
+    const bool ov_best = MODE == MODE_STEP && p.state_type == 2;                       // observation = distance to the nearest
+    const float ov_const = (MODE != MODE_STEP || p.state_type == 1) ? 1.0f : 0.0f;     // ... or a constant
     auto decide = [&](auto flat_c, int r, unsigned txm, int &tstar, float &o, unsigned &more) {
         constexpr bool FL = decltype(flat_c)::value;
         const bool is_tx = (a == r);
         const unsigned cand = (act && !is_tx) ? (inr_mask & txm) : 0u;
-        n_pairs += __popc(cand);
         const unsigned rest = cand & (cand - 1u);
         const int t1 = (__ffs(cand) - 1) & (G - 1);      // cand == 0: any valid lane, the result is discarded
         const int f2 = __ffs(rest) - 1;
@@ -346,8 +347,7 @@ step_group_kernel(const Params p)
         if (!cand || !(best < sentinel)) { tstar = -1; best = sentinel; }              // network.py:385
         n_recv += tstar >= 0 ? 1 : 0;
         // channel observation (test_env.py:203-240 / :305-306 / :431)
-        float ov = 1.0f;
-        if (MODE == MODE_STEP) ov = p.state_type == 2 ? (float)best : (p.state_type == 1 ? 1.0f : 0.0f);
+        const float ov = ov_best ? (float)best : ov_const;
         o = (!is_tx && txm) ? ov : 0.0f;
     };
     // side effects of one resource, in resource order
@@ -391,6 +391,10 @@ step_group_kernel(const Params p)
         }
     };
     if (flat) run_decisions(std::true_type{}); else run_decisions(std::false_type{});
+    // candidate (receiver, transmitter) pairs of the slot: the transmitter masks of the resources partition the live
+    // vehicles, so summed over the resources a lane does not transmit on they are its in-range vehicles outside its own
+    // collision set
+    if (act) n_pairs += __popc(inr_mask & live_mask & ~own);
 
     // rewards (test_env.py:159-199 / :294-302 / :408-429), all lane-local
     if (MODE == MODE_STEP) {
@@ -579,14 +583,10 @@ step_group_kernel(const Params p)
 
     // ---- per-env metric accumulators -------------------------------------------------------------
     {
-        double rs = act ? rew : 0.0; int nr = n_recv, np = n_pairs, nb = bad;
+        double rs = act ? rew : 0.0;
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            rs += __shfl_xor_sync(gmask, rs, o, G);
-            nr += __shfl_xor_sync(gmask, nr, o, G);
-            np += __shfl_xor_sync(gmask, np, o, G);
-            nb += __shfl_xor_sync(gmask, nb, o, G);
-        }
+        for (int o = G / 2; o > 0; o >>= 1) rs += __shfl_xor_sync(gmask, rs, o, G);
+        const int nr = __reduce_add_sync(gmask, n_recv), np = __reduce_add_sync(gmask, n_pairs), nb = __reduce_add_sync(gmask, bad);
         if (u == 0) {    // reductions, not read-modify-writes: nothing waits for the old values
             atomicAdd(p.acc_reward + e, rs);
             unsigned long long *c = reinterpret_cast<unsigned long long *>(p.acc_count + e * ACC_COUNTS);
